@@ -1,0 +1,6 @@
+"""oracle/ -- TEST INFRASTRUCTURE ONLY (see oracle/cifcaf_oracle.c header).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this package.  The product package
+openpifpaf_b200 never does.
+"""
