@@ -1,0 +1,152 @@
+/*
+ * pifpaf_b200.h -- C ABI of the B200-native OpenPifPaf inference hot path.
+ *
+ * Plain C: opaque handles, raw pointers and sizes, int status codes; no C++
+ * exceptions cross this boundary and no torch types appear in any signature.
+ * Every entry point cites the reference interface it replaces (paths relative
+ * to /root/reference/src/openpifpaf/).  The shared library is
+ * openpifpaf_b200/csrc/libpifpaf_b200.so (sm_100a only; there is no CPU path:
+ * every call fails with PIFPAF_E_CUDA when no B200 is present).
+ *
+ * Threading: a handle is stateful and not re-entrant (like the reference's
+ * CifCaf instance, csrc/include/openpifpaf/decoder/cifcaf.hpp:91-94); use one
+ * handle per (GPU, stream) from one host thread at a time.  Configuration is
+ * passed BY VALUE per call (the reference keeps process-global statics,
+ * csrc/src/module.cpp:26-32,76-117).
+ */
+#ifndef PIFPAF_B200_H_
+#define PIFPAF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PIFPAF_OK 0
+#define PIFPAF_E_BADARG 1     /* TORCH_CHECK-class argument error in the reference */
+#define PIFPAF_E_CUDA 2       /* CUDA runtime/driver error (incl. "no device") */
+#define PIFPAF_E_OVERFLOW 3   /* a capacity given at create() time was exceeded */
+#define PIFPAF_E_NOMEM 4
+
+/* Last error message of the calling thread ("" if none). */
+const char* pifpaf_last_error(void);
+/* Library/ABI version and build architecture string ("sm_100a"). */
+int pifpaf_abi_version(void);
+const char* pifpaf_build_arch(void);
+
+/* ------------------------------------------------------------------------ */
+/* Decoder configuration: the reference's static knobs, by value.            */
+/* Defaults in brackets; citations are the reference definitions.            */
+typedef struct pifpaf_decoder_params {
+    int64_t cifhr_neighbors;           /* [16]    csrc/src/cif_hr.cpp:13 */
+    double cifhr_threshold;            /* [0.3]   csrc/src/cif_hr.cpp:14 */
+    int32_t cifhr_ablation_skip;       /* [0]     csrc/src/cif_hr.cpp:15 */
+    double seed_threshold;             /* [0.2]   csrc/src/cif_seeds.cpp:11 */
+    int32_t seeds_ablation_nms;        /* [0]     csrc/src/cif_seeds.cpp:13 */
+    int32_t seeds_ablation_no_rescore; /* [0]     csrc/src/cif_seeds.cpp:14 */
+    double caf_score_th;               /* [0.3]   csrc/src/caf_scored.cpp:11 */
+    double caf_cif_floor;              /* [0.1]   csrc/src/cifcaf.cpp:153 */
+    int32_t caf_ablation_no_rescore;   /* [0]     csrc/src/caf_scored.cpp:12 */
+    int32_t block_joints;              /* [0]     csrc/src/cifcaf.cpp:18 (no effect there either) */
+    int32_t greedy;                    /* [0]     csrc/src/cifcaf.cpp:19 */
+    double keypoint_threshold;         /* [0.15]  csrc/src/cifcaf.cpp:20 */
+    double keypoint_threshold_rel;     /* [0.5]   csrc/src/cifcaf.cpp:21 */
+    int32_t reverse_match;             /* [1]     csrc/src/cifcaf.cpp:22 */
+    int32_t force_complete;            /* [0]     csrc/src/cifcaf.cpp:23 */
+    double force_complete_caf_th;      /* [0.001] csrc/src/cifcaf.cpp:24 */
+    double nms_suppression;            /* [1e-5]  csrc/src/nms_keypoints.cpp:12 */
+    double nms_instance_threshold;     /* [0.15]  csrc/src/nms_keypoints.cpp:13 */
+    double nms_keypoint_threshold;     /* [0.15]  csrc/src/nms_keypoints.cpp:14 */
+    double occ_reduction;              /* [2.0]   csrc/include/openpifpaf/decoder/cifcaf.hpp:103 */
+    double occ_min_scale;              /* [4.0]   same */
+    /* CifHr revision the arithmetic is carried out at.  A fresh reference
+     * instance decodes at 1.0 (csrc/src/cif_hr.cpp:115); the parity contract is
+     * "fresh instance per image", so keep 1.0 unless reproducing a warm one. */
+    double cifhr_revision;             /* [1.0] */
+} pifpaf_decoder_params_t;
+
+int pifpaf_decoder_default_params(pifpaf_decoder_params_t* params);
+
+/* ------------------------------------------------------------------------ */
+/* CifCaf decoder.  Replaces torch.classes.openpifpaf_decoder.CifCaf
+ * (csrc/src/module.cpp:24-58; csrc/src/cifcaf.cpp:116-262).                  */
+typedef struct pifpaf_decoder pifpaf_decoder_t;
+
+/* CifCaf(n_keypoints, skeleton): csrc/include/openpifpaf/decoder/cifcaf.hpp:96-107.
+ * skeleton: [n_connections][2] int64, 0-BASED (the reference's Python passes
+ * skeleton-1, decoder/cifcaf.py:119-122).  n_cif_fields normally == n_keypoints.
+ * Capacities (no allocation happens on the decode path):
+ *   max_batch, max_h, max_w : largest field batch/shape (cells) to be decoded;
+ *   max_stride              : largest field stride (hi-res map side = (h-1)*stride+1);
+ *   max_annotations         : per-image capacity for annotations before NMS.
+ * device: CUDA device ordinal. */
+int pifpaf_decoder_create(pifpaf_decoder_t** out, int32_t device,
+                          int32_t n_keypoints, int32_t n_cif_fields,
+                          int32_t n_connections, const int64_t* skeleton,
+                          int32_t max_batch, int32_t max_h, int32_t max_w, int32_t max_stride,
+                          int32_t max_annotations);
+void pifpaf_decoder_destroy(pifpaf_decoder_t* dec);
+
+/* Batched decode of DEVICE-resident fields (the entry point the reference
+ * lacks: decoder/decoder.py:88-100 moves every field to the CPU first).
+ *   cif_dev [B][F][5][h][w] f32, caf_dev [B][C][8][h][w] f32, contiguous.
+ *   init_ann_dev: optional [B][init_cap][K][4] f32 (v,x,y,s) device pointer with
+ *   init_ids_dev [B][init_cap] i64 and init_counts_dev [B] i32, or NULL
+ *   (csrc/src/cifcaf.cpp:177-202).
+ * All work is enqueued on `stream` (a cudaStream_t); results stay on the device
+ * until pifpaf_decoder_fetch(). */
+int pifpaf_decoder_decode_device(pifpaf_decoder_t* dec,
+                                 const float* cif_dev, const float* caf_dev,
+                                 int32_t batch, int32_t h, int32_t w,
+                                 int32_t cif_stride, int32_t caf_stride,
+                                 const float* init_ann_dev, const int64_t* init_ids_dev,
+                                 const int32_t* init_counts_dev, int32_t init_cap,
+                                 const pifpaf_decoder_params_t* params, void* stream);
+
+/* Copy the results of the last decode to host buffers and wait for them.
+ *   counts [B] i32: annotations per image (after NMS);
+ *   ann [B][ann_cap][K][4] f32 (v,x,y,s), ids [B][ann_cap] i64 (-1 unless initial ids).
+ * Returns PIFPAF_E_OVERFLOW if any image exceeded max_annotations (pre-NMS) or
+ * ann_cap (post-NMS); counts[] then still holds the true post-NMS counts. */
+int pifpaf_decoder_fetch(pifpaf_decoder_t* dec, int32_t* counts, float* ann, int64_t* ids,
+                         int32_t ann_cap, void* stream);
+
+/* Single image, HOST buffers: the call the reference's binding makes.
+ * Replaces CifCaf::call / call_with_initial_annotations
+ * (csrc/src/cifcaf.cpp:116-262): cif [F][5][h][w], caf [C][8][h][w] on the host;
+ * H2D, decode and D2H happen inside.  *n_out receives N; out_ann [cap][K][4],
+ * out_ids [cap]. */
+int pifpaf_decoder_call(pifpaf_decoder_t* dec,
+                        const float* cif, int32_t cif_stride,
+                        const float* caf, int32_t caf_stride,
+                        int32_t h, int32_t w,
+                        const float* initial_annotations, const int64_t* initial_ids, int32_t n_initial,
+                        const pifpaf_decoder_params_t* params,
+                        float* out_ann, int64_t* out_ids, int32_t cap, int32_t* n_out);
+
+/* Stage taps of the last decode, for parity tests (the reference exposes the
+ * same stages through torch.classes.openpifpaf_decoder_utils, module.cpp:66-118).
+ * All copy to HOST buffers for image `b` and synchronise.
+ *   cifhr  [F][H][W] f32 (CifHr.get_accumulated, csrc/src/cif_hr.cpp:92-94);
+ *   seeds  f [n] i64 + vxys [n][4] f32 sorted (CifSeeds.get, csrc/src/cif_seeds.cpp:93-114);
+ *   caf    per connection [n][7] f32 (CafScored.get, csrc/src/caf_scored.cpp:86-104):
+ *          out_fwd/out_bwd are [C][h*w][7], counts in n_fwd/n_bwd [C]. */
+int pifpaf_decoder_tap_cifhr(pifpaf_decoder_t* dec, int32_t b, float* out, int64_t out_elems);
+int pifpaf_decoder_tap_seeds(pifpaf_decoder_t* dec, int32_t b, int64_t* out_f, float* out_vxys,
+                             int64_t cap, int64_t* n_out);
+int pifpaf_decoder_tap_caf(pifpaf_decoder_t* dec, int32_t b, float* out_fwd, int64_t* n_fwd,
+                           float* out_bwd, int64_t* n_bwd);
+
+/* Free op grow_connection_blend (csrc/src/cifcaf.cpp:32-113, module.cpp:60):
+ * caf [n][7] f32 HOST; writes x,y,s,v to out_xysv[4]. */
+int pifpaf_grow_connection_blend(const float* caf, int64_t n, double x, double y, double s,
+                                 double filter_sigmas, int32_t only_max, double* out_xysv);
+
+/* Number of kernels this library launched since load (bench.py's gpu_launches). */
+int64_t pifpaf_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* PIFPAF_B200_H_ */

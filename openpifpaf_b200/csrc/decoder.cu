@@ -1,0 +1,1494 @@
+// libpifpaf_b200 -- CifCaf decoder for sm_100a.
+//
+// B200-native re-design of the reference's CPU decoder (paths relative to
+// /root/reference/src/openpifpaf/csrc/):
+//   CifHr::accumulate/add_gauss   src/cif_hr.cpp:28-89      -> k_cif_compact + k_cifhr_tiles
+//   CifSeeds::fill/get            src/cif_seeds.cpp:33-114  -> k_seed_candidates + k_seed_sort
+//   CafScored::fill               src/caf_scored.cpp:29-83  -> k_caf_scored
+//   CifCaf::call_* / _grow / ...  src/cifcaf.cpp:126-449    -> k_grow (+ k_force_complete)
+//   Occupancy                     src/occupancy.cpp:13-77   -> byte map with epoch tags
+//   NMSKeypoints::call            src/nms_keypoints.cpp:17-69 -> k_nms, k_pack
+//
+// Design: images are independent, so every kernel is batched over
+// the image index; the order-dependent float accumulation of CifHr is turned from
+// a scatter into a per-pixel GATHER over an order-preserving compacted cell list so
+// that the result is bit-identical to the sequential reference; the frontier
+// priority queue is the libstdc++ binary heap restated in shared memory (same tie
+// order) driven by one thread, while the CAF list scans behind every frontier
+// entry are evaluated eagerly by one warp each.
+//
+// This translation unit is compiled with -fmad=false: the reference arithmetic
+// has no fused multiply-adds and parity needs the same roundings.
+#include <algorithm>
+#include <climits>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int NT = 256;            // threads per CTA for the streaming kernels
+constexpr int NW = NT / 32;
+constexpr int SORT_NT = 1024;
+constexpr int TILE = 32;           // CifHr tile edge in hi-res pixels
+constexpr int SC_CAP = 1024;       // per-warp score cache entries in k_grow
+
+struct Dims {
+    int B, F, C, K;
+    int h, w, hw;
+    int cif_stride, caf_stride;
+    int H, W, Wp;        // hi-res map size and padded row pitch (floats)
+    int Ho, Wo;          // occupancy map size
+    int tiles_x, tiles_y;
+    int max_ann;
+};
+
+struct Joint { double v, x, y, s; };
+
+struct GrowParams {
+    double keypoint_threshold, keypoint_threshold_rel;
+    int reverse_match, greedy;
+    double occ_reduction, occ_min_scale_reduced;
+    double nms_suppression, nms_instance_threshold, nms_keypoint_threshold;
+};
+
+// ---------------------------------------------------------------------------
+// order-preserving block compaction of up to two flags per thread.
+// Every thread of the CTA must call it.  base0/base1 are CTA-uniform running
+// totals held in registers.  wc is shared scratch of NWARPS ints.
+template <int NWARPS>
+__device__ __forceinline__ void block_compact2(bool f0, bool f1, int& base0, int& base1,
+                                               int& pos0, int& pos1, int* wc) {
+    const unsigned m0 = __ballot_sync(0xffffffffu, f0);
+    const unsigned m1 = __ballot_sync(0xffffffffu, f1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) wc[warp] = __popc(m0) | (__popc(m1) << 16);
+    __syncthreads();
+    int off0 = 0, off1 = 0, tot0 = 0, tot1 = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < NWARPS; w2++) {
+        const int c = wc[w2];
+        const int c0 = c & 0xffff, c1 = c >> 16;
+        if (w2 < warp) { off0 += c0; off1 += c1; }
+        tot0 += c0; tot1 += c1;
+    }
+    const unsigned lt = (1u << lane) - 1u;
+    pos0 = base0 + off0 + __popc(m0 & lt);
+    pos1 = base1 + off1 + __popc(m1 & lt);
+    base0 += tot0;
+    base1 += tot1;
+    __syncthreads();
+}
+
+__device__ __forceinline__ long long clamp_ll(long long v, long long lo, long long hi) {
+    return v < lo ? lo : (hi < v ? hi : v);
+}
+
+// src/cif_hr.cpp:18-25
+__device__ __forceinline__ float approx_exp(float x) {
+    if ((double)x > 2.0 || (double)x < -2.0) return 0.0f;
+    x = (float)(1.0 + (double)x / 8.0);
+    x = x * x;
+    x = x * x;
+    x = x * x;
+    return x;
+}
+
+// src/cif_seeds.cpp:17-30 == src/caf_scored.cpp:15-26.  hr is the image base [F][H][Wp].
+__device__ __forceinline__ float cifhr_value(const float* __restrict__ hr, int F, int H, int W, int Wp,
+                                             double revision, long long f, float x, float y,
+                                             float default_value) {
+    const float max_x = (float)((double)(float)W - 0.51);
+    const float max_y = (float)((double)(float)H - 0.51);
+    if (f >= F || (double)x < -0.49 || (double)y < -0.49 || x > max_x || y > max_y) return default_value;
+    const long long yi = (long long)((double)y + 0.5), xi = (long long)((double)x + 0.5);
+    const float value = (float)((double)hr[((size_t)f * H + yi) * Wp + xi] - revision);
+    if ((double)value < 0.0) return default_value;
+    return value;
+}
+
+// ---------------------------------------------------------------------------
+// CifHr step 1: compact the cells that contribute (src/cif_hr.cpp:36-51), in
+// (j,i) order, with their add_gauss box (src/cif_hr.cpp:61-64).
+__global__ void __launch_bounds__(NT) k_cif_compact(const float* __restrict__ cif, Dims d,
+                                                    double threshold, long long neighbors,
+                                                    float min_scale_f, double factor,
+                                                    float4* __restrict__ cells, int4* __restrict__ boxes,
+                                                    int* __restrict__ counts) {
+    __shared__ int wc[NW];
+    const int f = blockIdx.x, b = blockIdx.y;
+    const float* cf = cif + ((size_t)(b * d.F + f) * 5) * d.hw;
+    float4* out_c = cells + (size_t)(b * d.F + f) * d.hw;
+    int4* out_b = boxes + (size_t)(b * d.F + f) * d.hw;
+    int base = 0, dummy = 0;
+    for (int start = 0; start < d.hw; start += NT) {
+        const int idx = start + threadIdx.x;
+        bool flag = false;
+        float v = 0.f, scale = 0.f;
+        if (idx < d.hw) {
+            v = cf[1 * d.hw + idx];
+            if (!((double)v < threshold)) {
+                scale = cf[4 * d.hw + idx];
+                if (!(scale < min_scale_f)) flag = true;
+            }
+        }
+        int pos, pos1;
+        block_compact2<NW>(flag, false, base, dummy, pos, pos1, wc);
+        if (flag) {
+            const float x = cf[2 * d.hw + idx] * (float)d.cif_stride;
+            const float y = cf[3 * d.hw + idx] * (float)d.cif_stride;
+            const float sigma = fmaxf(1.0f, (float)(0.5 * (double)scale * (double)d.cif_stride));
+            const float vn = (float)((double)(v / (float)neighbors) * factor);
+            const float truncate = 1.0f;
+            const long long minx = clamp_ll((long long)(x - truncate * sigma), 0, d.W - 1);
+            const long long miny = clamp_ll((long long)(y - truncate * sigma), 0, d.H - 1);
+            const long long maxx = clamp_ll((long long)(x + truncate * sigma + 1.0f), minx + 1, d.W);
+            const long long maxy = clamp_ll((long long)(y + truncate * sigma + 1.0f), miny + 1, d.H);
+            out_c[pos] = make_float4(x, y, sigma, vn);
+            out_b[pos] = make_int4((int)minx, (int)miny, (int)maxx, (int)maxy);
+        }
+    }
+    if (threadIdx.x == 0) counts[b * d.F + f] = base;
+}
+
+// CifHr step 2: one CTA per 32x32 hi-res tile gathers, in cell order, every
+// compacted cell whose box touches the tile (src/cif_hr.cpp:66-88 per pixel).
+// Fuses the clear: each pixel is written exactly once and never read.
+__global__ void __launch_bounds__(NT) k_cifhr_tiles(Dims d, double revision,
+                                                    const float4* __restrict__ cells,
+                                                    const int4* __restrict__ boxes,
+                                                    const int* __restrict__ counts,
+                                                    float* __restrict__ cifhr) {
+    __shared__ int wc[NW];
+    __shared__ float4 s_cell[NT];
+    __shared__ int4 s_box[NT];
+    const int tile = blockIdx.x, f = blockIdx.y, b = blockIdx.z;
+    const int tx0 = (tile % d.tiles_x) * TILE, ty0 = (tile / d.tiles_x) * TILE;
+    const int px = tx0 + (threadIdx.x & 7) * 4;
+    const int py = ty0 + (threadIdx.x >> 3);
+    const float4* in_c = cells + (size_t)(b * d.F + f) * d.hw;
+    const int4* in_b = boxes + (size_t)(b * d.F + f) * d.hw;
+    const int n = counts[b * d.F + f];
+    const float rev_f = (float)revision;
+    const float rev_p1_f = (float)(revision + 1.0);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+
+    for (int start = 0; start < n; start += NT) {
+        const int e = start + threadIdx.x;
+        bool flag = false;
+        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+        int4 bx = make_int4(0, 0, 0, 0);
+        if (e < n) {
+            bx = in_b[e];
+            flag = bx.x < tx0 + TILE && bx.z > tx0 && bx.y < ty0 + TILE && bx.w > ty0;
+            if (flag) c = in_c[e];
+        }
+        int m = 0, dummy = 0, pos, pos1;
+        block_compact2<NW>(flag, false, m, dummy, pos, pos1, wc);
+        if (flag) { s_cell[pos] = c; s_box[pos] = bx; }
+        __syncthreads();
+        for (int k = 0; k < m; k++) {
+            const float4 cc = s_cell[k];
+            const int4 bb = s_box[k];
+            if (py < bb.y || py >= bb.w) continue;
+            const float sigma2 = cc.z * cc.z;           // truncate^2 * sigma2 == sigma2 for truncate 1
+            const float dyf = (float)py - cc.y;
+            const float deltay2 = dyf * dyf;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int xx = px + q;
+                if (xx < bb.x || xx >= bb.z) continue;
+                const float dxf = (float)xx - cc.x;
+                const float deltax2 = dxf * dxf;
+                if (deltax2 + deltay2 > sigma2) continue;
+                float vv;
+                if ((double)deltax2 < 0.25 && (double)deltay2 < 0.25) {
+                    vv = cc.w;
+                } else {
+                    vv = cc.w * approx_exp((float)(-0.5 * (double)(deltax2 + deltay2) / (double)sigma2));
+                }
+                float entry = fmaxf(acc[q], rev_f) + vv;
+                acc[q] = fminf(entry, rev_p1_f);
+            }
+        }
+        __syncthreads();
+    }
+    if (py < d.H) {
+        float4* dst = reinterpret_cast<float4*>(cifhr + ((size_t)(b * d.F + f) * d.H + py) * d.Wp + px);
+        *dst = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// CifSeeds::fill (src/cif_seeds.cpp:33-66), per (image, field), order preserving.
+__global__ void __launch_bounds__(NT) k_seed_candidates(const float* __restrict__ cif, Dims d,
+                                                        const float* __restrict__ cifhr, double revision,
+                                                        double threshold, int ablation_nms, int no_rescore,
+                                                        float* __restrict__ seg_v, float4* __restrict__ seg_xys,
+                                                        int* __restrict__ seg_counts) {
+    __shared__ int wc[NW];
+    const int f = blockIdx.x, b = blockIdx.y;
+    const float* cf = cif + ((size_t)(b * d.F + f) * 5) * d.hw;
+    const float* hr = cifhr + (size_t)b * d.F * d.H * d.Wp;
+    float* out_v = seg_v + (size_t)(b * d.F + f) * d.hw;
+    float4* out_x = seg_xys + (size_t)(b * d.F + f) * d.hw;
+    int base = 0, dummy = 0;
+    for (int start = 0; start < d.hw; start += NT) {
+        const int idx = start + threadIdx.x;
+        bool flag = false;
+        float c = 0.f, x = 0.f, y = 0.f;
+        if (idx < d.hw) {
+            c = cf[1 * d.hw + idx];
+            flag = !((double)c < threshold);
+            if (flag && ablation_nms) {
+                // torch.max_pool2d(confidence, 3, 1, 1): src/cif_seeds.cpp:36-40,49-51
+                const int j = idx / d.w, i = idx % d.w;
+                float m = c;
+                for (int dj = -1; dj <= 1; dj++)
+                    for (int di = -1; di <= 1; di++) {
+                        const int jj = j + dj, ii = i + di;
+                        if (jj < 0 || jj >= d.h || ii < 0 || ii >= d.w) continue;
+                        m = fmaxf(m, cf[1 * d.hw + jj * d.w + ii]);
+                    }
+                if (c < m) flag = false;
+            }
+            if (flag) {
+                x = cf[2 * d.hw + idx] * (float)d.cif_stride;
+                y = cf[3 * d.hw + idx] * (float)d.cif_stride;
+                if (!no_rescore) {
+                    const float hv = cifhr_value(hr, d.F, d.H, d.W, d.Wp, revision, f, x, y, -1.0f);
+                    c = (float)(0.9 * (double)hv + 0.1 * (double)c);
+                }
+                flag = !((double)c < threshold);
+            }
+        }
+        int pos, pos1;
+        block_compact2<NW>(flag, false, base, dummy, pos, pos1, wc);
+        if (flag) {
+            const float s = cf[4 * d.hw + idx] * (float)d.cif_stride;
+            out_v[pos] = c;
+            out_x[pos] = make_float4(x, y, s, 0.f);
+        }
+    }
+    if (threadIdx.x == 0) seg_counts[b * d.F + f] = base;
+}
+
+__device__ __forceinline__ unsigned float_key_desc(float v) {
+    const unsigned bits = __float_as_uint(v);
+    const unsigned asc = bits ^ ((bits >> 31) ? 0xffffffffu : 0x80000000u);
+    return ~asc;   // ascending key order == descending v
+}
+
+// CifSeeds::get (src/cif_seeds.cpp:93-114): sort by v descending.  One CTA per
+// image: concatenate the per-field segments (fill order) and run a stable LSD
+// radix sort, so exact float ties keep fill order (f, j, i) -- std::sort in the
+// reference leaves tie order unspecified.
+__global__ void __launch_bounds__(SORT_NT) k_seed_sort(Dims d, const int* __restrict__ seg_counts,
+                                                       const float* __restrict__ seg_v,
+                                                       const float4* __restrict__ seg_xys,
+                                                       unsigned* __restrict__ keys_a, unsigned* __restrict__ vals_a,
+                                                       unsigned* __restrict__ keys_b, unsigned* __restrict__ vals_b,
+                                                       int* __restrict__ seed_f, float4* __restrict__ seed_vxys,
+                                                       int* __restrict__ n_seeds) {
+    extern __shared__ unsigned char smem_raw[];
+    int* s_off = reinterpret_cast<int*>(smem_raw);                 // F + 1
+    int* hist = s_off + ((d.F + 1 + 3) & ~3);                      // 256
+    int* dbase = hist + 256;                                       // 256
+    int* wsum = dbase + 256;                                       // 8
+    unsigned short* wc = reinterpret_cast<unsigned short*>(wsum + 8);   // 32 x 256
+    __shared__ int s_skip;
+
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t img = (size_t)b * d.F * d.hw;
+    const float* in_v = seg_v + img;
+    const float4* in_x = seg_xys + img;
+    unsigned* kin = keys_a + img; unsigned* vin = vals_a + img;
+    unsigned* kout = keys_b + img; unsigned* vout = vals_b + img;
+
+    if (tid == 0) {
+        int run = 0;
+        for (int f = 0; f < d.F; f++) { s_off[f] = run; run += seg_counts[b * d.F + f]; }
+        s_off[d.F] = run;
+    }
+    __syncthreads();
+    const int n = s_off[d.F];
+    for (int f = 0; f < d.F; f++) {
+        const int off = s_off[f], cnt = s_off[f + 1] - off;
+        for (int p = tid; p < cnt; p += SORT_NT) {
+            const unsigned src = (unsigned)(f * d.hw + p);
+            kin[off + p] = float_key_desc(in_v[src]);
+            vin[off + p] = src;
+        }
+    }
+    __syncthreads();
+
+    for (int pass = 0; pass < 4; pass++) {
+        const int shift = pass * 8;
+        if (tid < 256) hist[tid] = 0;
+        if (tid == 0) s_skip = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += SORT_NT) atomicAdd(&hist[(kin[i] >> shift) & 255u], 1);
+        __syncthreads();
+        if (tid < 256 && n > 0 && hist[tid] == n) s_skip = 1;
+        __syncthreads();
+        const int skip = s_skip;
+        __syncthreads();
+        if (skip || n == 0) continue;       // CTA-uniform
+        int excl_local = 0;
+        if (tid < 256) {
+            const int v = hist[tid];
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) wsum[warp] = incl;
+            excl_local = incl - v;
+        }
+        __syncthreads();
+        if (tid < 256) {
+            int add = 0;
+            for (int w2 = 0; w2 < warp; w2++) add += wsum[w2];
+            dbase[tid] = excl_local + add;
+        }
+        __syncthreads();
+        for (int t0 = 0; t0 < n; t0 += SORT_NT) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) reinterpret_cast<unsigned*>(wc)[tid + q * SORT_NT] = 0u;
+            __syncthreads();
+            const int i = t0 + tid;
+            const bool valid = i < n;
+            const unsigned key = valid ? kin[i] : 0u;
+            const unsigned dg = valid ? ((key >> shift) & 255u) : 256u;
+            const unsigned peers = __match_any_sync(0xffffffffu, dg);
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            if (valid && rank == 0) wc[warp * 256 + dg] = (unsigned short)__popc(peers);
+            __syncthreads();
+            int tile_tot = 0;
+            if (tid < 256) {
+                int run = 0;
+                for (int w2 = 0; w2 < 32; w2++) {
+                    const int c = wc[w2 * 256 + tid];
+                    wc[w2 * 256 + tid] = (unsigned short)run;
+                    run += c;
+                }
+                tile_tot = run;
+            }
+            __syncthreads();
+            if (valid) {
+                const int dst = dbase[dg] + wc[warp * 256 + dg] + rank;
+                kout[dst] = key;
+                vout[dst] = vin[i];
+            }
+            __syncthreads();
+            if (tid < 256) dbase[tid] += tile_tot;
+        }
+        __syncthreads();
+        unsigned* t;
+        t = kin; kin = kout; kout = t;
+        t = vin; vin = vout; vout = t;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += SORT_NT) {
+        const unsigned src = vin[i];
+        const float4 xs = in_x[src];
+        seed_f[img + i] = (int)(src / (unsigned)d.hw);
+        seed_vxys[img + i] = make_float4(in_v[src], xs.x, xs.y, xs.z);
+    }
+    if (tid == 0) n_seeds[b] = n;
+}
+
+// ---------------------------------------------------------------------------
+// CafScored::fill (src/caf_scored.cpp:29-83).  Output lists are SoA:
+// lists[(((b*C + c)*2 + dir)*7 + comp)*hw + pos], dir 0 = forward, 1 = backward.
+__global__ void __launch_bounds__(NT) k_caf_scored(const float* __restrict__ caf, Dims d,
+                                                   const int* __restrict__ skeleton,
+                                                   const float* __restrict__ cifhr, double revision,
+                                                   double score_th, double cif_floor, int no_rescore,
+                                                   float* __restrict__ lists, int* __restrict__ list_counts) {
+    __shared__ int wc[NW];
+    const int c = blockIdx.x, b = blockIdx.y;
+    const float* cf = caf + ((size_t)(b * d.C + c) * 8) * d.hw;
+    const float* hr = cifhr + (size_t)b * d.F * d.H * d.Wp;
+    float* fw = lists + ((size_t)((b * d.C + c) * 2 + 0) * 7) * d.hw;
+    float* bw = lists + ((size_t)((b * d.C + c) * 2 + 1) * 7) * d.hw;
+    const long long kp_a = skeleton[2 * c], kp_b = skeleton[2 * c + 1];
+    int nf = 0, nb = 0;
+    for (int start = 0; start < d.hw; start += NT) {
+        const int idx = start + threadIdx.x;
+        bool ff = false, bf = false;
+        float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f, s1 = 0.f, s2 = 0.f, cfw = 0.f, cbw = 0.f;
+        if (idx < d.hw) {
+            const float cc = cf[1 * d.hw + idx];
+            if (!((double)cc < score_th)) {
+                const float st = (float)d.caf_stride;
+                x1 = cf[2 * d.hw + idx] * st; y1 = cf[3 * d.hw + idx] * st;
+                x2 = cf[4 * d.hw + idx] * st; y2 = cf[5 * d.hw + idx] * st;
+                s1 = cf[6 * d.hw + idx] * st; s2 = cf[7 * d.hw + idx] * st;
+                cfw = cc; cbw = cc;
+                if (!no_rescore) {
+                    const float fhr = cifhr_value(hr, d.F, d.H, d.W, d.Wp, revision, kp_b, x2, y2, 0.0f);
+                    const float bhr = cifhr_value(hr, d.F, d.H, d.W, d.Wp, revision, kp_a, x1, y1, 0.0f);
+                    cfw = (float)((double)cc * (cif_floor + (1.0 - cif_floor) * (double)fhr));
+                    cbw = (float)((double)cc * (cif_floor + (1.0 - cif_floor) * (double)bhr));
+                }
+                ff = (double)cfw > score_th;
+                bf = (double)cbw > score_th;
+            }
+        }
+        int pf, pb;
+        block_compact2<NW>(ff, bf, nf, nb, pf, pb, wc);
+        if (ff) {
+            fw[0 * d.hw + pf] = cfw; fw[1 * d.hw + pf] = x1; fw[2 * d.hw + pf] = y1;
+            fw[3 * d.hw + pf] = x2; fw[4 * d.hw + pf] = y2; fw[5 * d.hw + pf] = s1; fw[6 * d.hw + pf] = s2;
+        }
+        if (bf) {
+            bw[0 * d.hw + pb] = cbw; bw[1 * d.hw + pb] = x2; bw[2 * d.hw + pb] = y2;
+            bw[3 * d.hw + pb] = x1; bw[4 * d.hw + pb] = y1; bw[5 * d.hw + pb] = s2; bw[6 * d.hw + pb] = s1;
+        }
+    }
+    if (threadIdx.x == 0) {
+        list_counts[(b * d.C + c) * 2 + 0] = nf;
+        list_counts[(b * d.C + c) * 2 + 1] = nb;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// grow_connection_blend (src/cifcaf.cpp:32-103), one warp per call.  L is the
+// SoA list base (component stride `cap`), n its length.  The sequential top-2
+// rule of the reference (">=" shifts 1->2, ">" replaces 2) is reproduced exactly:
+//   i1 = LAST index of the maximum score M;
+//   second = the running maximum of the prefix [0,i1) (last index on ties) unless
+//   a suffix element is strictly larger (first index on ties).
+__device__ Joint warp_blend(const float* __restrict__ L, int cap, int n, double x, double y,
+                            double xy_scale, double filter_sigmas, bool only_max,
+                            float* cache, int lane) {
+    Joint zero; zero.v = 0.0; zero.x = 0.0; zero.y = 0.0; zero.s = 0.0;
+    xy_scale = fmax(xy_scale, 0.5);
+    const float sigma_filter = (float)(filter_sigmas * xy_scale / 2.0);
+    const float sigma2 = (float)(0.25 * xy_scale * xy_scale);
+    const double xlo = x - (double)sigma_filter, xhi = x + (double)sigma_filter;
+    const double ylo = y - (double)sigma_filter, yhi = y + (double)sigma_filter;
+    const float* C0 = L;
+    const float* X1 = L + cap;
+    const float* Y1 = L + 2 * (size_t)cap;
+
+    auto score_at = [&](int i) -> float {
+        const float ex = X1[i], ey = Y1[i];
+        if ((double)ex < xlo) return -1.0f;
+        if ((double)ex > xhi) return -1.0f;
+        if ((double)ey < ylo) return -1.0f;
+        if ((double)ey > yhi) return -1.0f;
+        const double dx = (double)ex - x, dy = (double)ey - y;
+        const float d2 = (float)(dx * dx + dy * dy);
+        return (float)(exp(-0.5 * (double)d2 / (double)sigma2) * (double)C0[i]);
+    };
+
+    float best = -1.0f; int besti = -1;
+    for (int i = lane; i < n; i += 32) {
+        const float s = score_at(i);
+        if (i < SC_CAP) cache[i] = s;
+        if (s >= 0.0f && s >= best) { best = s; besti = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (ob > best || (ob == best && oi > besti)) { best = ob; besti = oi; }
+    }
+    if (besti < 0 || best == 0.0f) return zero;
+    __syncwarp();
+    const int i1 = besti;
+    const float score_1 = best;
+
+    float p = -1.0f; int pi = -1;          // prefix: max score, ties -> larger index
+    float q = -1.0f; int qi = INT_MAX;     // suffix: max score, ties -> smaller index
+    for (int i = lane; i < n; i += 32) {
+        if (i == i1) continue;
+        const float s = (i < SC_CAP) ? cache[i] : score_at(i);
+        if (s < 0.0f) continue;
+        if (i < i1) { if (s >= p) { p = s; pi = i; } }
+        else { if (s > q) { q = s; qi = i; } }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float op = __shfl_xor_sync(0xffffffffu, p, o);
+        const int opi = __shfl_xor_sync(0xffffffffu, pi, o);
+        if (op > p || (op == p && opi > pi)) { p = op; pi = opi; }
+        const float oq = __shfl_xor_sync(0xffffffffu, q, o);
+        const int oqi = __shfl_xor_sync(0xffffffffu, qi, o);
+        if (oq > q || (oq == q && oqi < qi)) { q = oq; qi = oqi; }
+    }
+    __syncwarp();
+    float score_2 = (pi >= 0) ? p : 0.0f;
+    int i2 = (pi >= 0) ? pi : 0;
+    if (qi != INT_MAX && q > score_2) { score_2 = q; i2 = qi; }
+
+    const float e1x = L[3 * (size_t)cap + i1], e1y = L[4 * (size_t)cap + i1];
+    const float e1s = fmaxf(0.0f, L[6 * (size_t)cap + i1]);
+    Joint r;
+    if (only_max) { r.v = score_1; r.x = e1x; r.y = e1y; r.s = e1s; return r; }
+    if ((double)score_2 < 0.01 || (double)score_2 < 0.5 * (double)score_1) {
+        r.v = 0.5 * (double)score_1; r.x = e1x; r.y = e1y; r.s = e1s; return r;
+    }
+    const float e2x = L[3 * (size_t)cap + i2], e2y = L[4 * (size_t)cap + i2];
+    const float e2s = fmaxf(0.0f, L[6 * (size_t)cap + i2]);
+    const double bdx = (double)(e1x - e2x), bdy = (double)(e1y - e2y);
+    const float blend_d2 = (float)(bdx * bdx + bdy * bdy);
+    if ((double)blend_d2 > ((double)e1s * (double)e1s) / 4.0) {
+        r.v = 0.5 * (double)score_1; r.x = e1x; r.y = e1y; r.s = e1s; return r;
+    }
+    r.v = 0.5 * (double)(score_1 + score_2);
+    r.x = (score_1 * e1x + score_2 * e2x) / (score_1 + score_2);
+    r.y = (score_1 * e1y + score_2 * e2y) / (score_1 + score_2);
+    r.s = (score_1 * e1s + score_2 * e2s) / (score_1 + score_2);
+    return r;
+}
+
+// Shared-memory working set of one image's grow CTA.
+struct GrowCtx {
+    Joint* joints;          // [K]
+    Joint* eval_joint;      // [2C] eagerly evaluated _connection_value per directed edge
+    float* heap_score;      // [2C + 1]
+    int* heap_item;         // [2C + 1]: edge | computed << 30
+    unsigned char* in_frontier;   // [2C] by pair id
+    int* new_edges;         // [2C]
+    float* score_cache;     // [NW][SC_CAP]
+    int* ctl;               // [8]: 0 heap_n, 1 n_new, 2 done
+    // graph (global)
+    const int* skeleton;    // [C][2]
+    const int* adj_start;   // [K+1]
+    const int* adj_edge;    // [<=2C] directed edge ids (2*c + dir, start = skeleton[c][dir]) in skeleton order
+    const int* edge_lookup; // [2C]: caf_i*2 + forward  (first-match rule of src/cifcaf.cpp:360-373)
+    const int* pair_id;     // [2C]: canonical id of the (start,end) pair for in_frontier
+    // lists
+    const float* lists;     // image base: [C][2][7][hw]
+    const int* list_counts; // image base: [C][2]
+    int K, C, F, hw;
+    GrowParams gp;
+};
+
+__device__ __forceinline__ bool heap_less(float a, float b) { return a < b; }   // src/cifcaf.cpp:27-29
+
+// libstdc++ std::push_heap / std::pop_heap restated (bits/stl_heap.h), single thread.
+__device__ void heap_push(GrowCtx& g, float score, int item) {
+    int hole = g.ctl[0]++;
+    int parent = (hole - 1) / 2;
+    while (hole > 0 && heap_less(g.heap_score[parent], score)) {
+        g.heap_score[hole] = g.heap_score[parent];
+        g.heap_item[hole] = g.heap_item[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    g.heap_score[hole] = score;
+    g.heap_item[hole] = item;
+}
+
+__device__ void heap_pop(GrowCtx& g, float& top_score, int& top_item) {
+    top_score = g.heap_score[0];
+    top_item = g.heap_item[0];
+    const int n = g.ctl[0];
+    if (n > 1) {
+        const int len = n - 1;
+        const float vs = g.heap_score[len];
+        const int vi = g.heap_item[len];
+        int hole = 0, second = 0;
+        while (second < (len - 1) / 2) {
+            second = 2 * (second + 1);
+            if (heap_less(g.heap_score[second], g.heap_score[second - 1])) second--;
+            g.heap_score[hole] = g.heap_score[second];
+            g.heap_item[hole] = g.heap_item[second];
+            hole = second;
+        }
+        if ((len & 1) == 0 && second == (len - 2) / 2) {
+            second = 2 * (second + 1);
+            g.heap_score[hole] = g.heap_score[second - 1];
+            g.heap_item[hole] = g.heap_item[second - 1];
+            hole = second - 1;
+        }
+        int parent = (hole - 1) / 2;
+        while (hole > 0 && heap_less(g.heap_score[parent], vs)) {
+            g.heap_score[hole] = g.heap_score[parent];
+            g.heap_item[hole] = g.heap_item[parent];
+            hole = parent;
+            parent = (hole - 1) / 2;
+        }
+        g.heap_score[hole] = vs;
+        g.heap_item[hole] = vi;
+    }
+    g.ctl[0] = n - 1;
+}
+
+// src/cifcaf.cpp:316-346 (single thread)
+__device__ void frontier_add_from(GrowCtx& g, int start_i) {
+    const float max_score = (float)sqrt(g.joints[start_i].v);
+    for (int a = g.adj_start[start_i]; a < g.adj_start[start_i + 1]; a++) {
+        const int edge = g.adj_edge[a];
+        const int c = edge >> 1, dir = edge & 1;
+        const int end_i = g.skeleton[2 * c + (1 - dir)];
+        if (g.joints[end_i].v > 0.0) continue;
+        const int pid = g.pair_id[edge];
+        if (g.in_frontier[pid]) continue;
+        heap_push(g, max_score, edge);
+        g.in_frontier[pid] = 1;
+        g.new_edges[g.ctl[1]++] = edge;
+    }
+}
+
+// src/cifcaf.cpp:349-411, one warp
+__device__ Joint warp_connection_value(GrowCtx& g, int edge, bool reverse_match_, double filter_sigmas,
+                                       float* cache, int lane) {
+    const int c = edge >> 1, dir = edge & 1;
+    const int start_i = g.skeleton[2 * c + dir];
+    const int lk = g.edge_lookup[edge];
+    const int caf_i = lk >> 1;
+    const int forward = lk & 1;
+    const float* Lf = g.lists + ((size_t)(caf_i * 2 + (forward ? 0 : 1)) * 7) * g.hw;
+    const float* Lb = g.lists + ((size_t)(caf_i * 2 + (forward ? 1 : 0)) * 7) * g.hw;
+    const int nf = g.list_counts[caf_i * 2 + (forward ? 0 : 1)];
+    const int nb = g.list_counts[caf_i * 2 + (forward ? 1 : 0)];
+    const Joint start_j = g.joints[start_i];
+    Joint new_j = warp_blend(Lf, g.hw, nf, start_j.x, start_j.y, start_j.s, filter_sigmas, false, cache, lane);
+    if (new_j.v == 0.0) return new_j;
+    new_j.v = sqrt(new_j.v * start_j.v);
+    if (new_j.v < g.gp.keypoint_threshold || new_j.v < start_j.v * g.gp.keypoint_threshold_rel) {
+        new_j.v = 0.0;
+        return new_j;
+    }
+    if (g.gp.reverse_match && reverse_match_ && start_i < g.F) {
+        const Joint rev = warp_blend(Lb, g.hw, nb, new_j.x, new_j.y, new_j.s, filter_sigmas, false, cache, lane);
+        if (rev.v == 0.0) { new_j.v = 0.0; return new_j; }
+        if (fabs(start_j.x - rev.x) + fabs(start_j.y - rev.y) > start_j.s) { new_j.v = 0.0; return new_j; }
+    }
+    return new_j;
+}
+
+// src/cifcaf.cpp:265-313 (_grow) and :429-449 (_flood_fill when flood == true).
+// Called by the whole CTA; g.joints holds the annotation.
+__device__ void cta_grow(GrowCtx& g, bool reverse_match_, double filter_sigmas, bool flood) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __syncthreads();
+    for (int i = tid; i < 2 * g.C; i += NT) g.in_frontier[i] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        g.ctl[0] = 0; g.ctl[1] = 0; g.ctl[2] = 0;
+        for (int j = 0; j < g.K; j++) {
+            if (g.joints[j].v == 0.0) continue;
+            frontier_add_from(g, j);
+        }
+    }
+    for (;;) {
+        __syncthreads();
+        const int n_new = g.ctl[1];
+        if (!flood) {
+            for (int e = warp; e < n_new; e += NW) {
+                const int edge = g.new_edges[e];
+                const Joint r = warp_connection_value(g, edge, reverse_match_, filter_sigmas,
+                                                      g.score_cache + warp * SC_CAP, lane);
+                if (lane == 0) g.eval_joint[edge] = r;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            g.ctl[1] = 0;
+            while (g.ctl[0] > 0 && g.ctl[1] == 0) {
+                float score; int item;
+                heap_pop(g, score, item);
+                const int edge = item & 0x3fffffff;
+                const bool computed = (item >> 30) & 1;
+                const int c = edge >> 1, dir = edge & 1;
+                const int start_i = g.skeleton[2 * c + dir];
+                const int end_i = g.skeleton[2 * c + (1 - dir)];
+                if (g.joints[end_i].v > 0.0) continue;
+                if (flood) {
+                    Joint nj = g.joints[start_i];
+                    nj.v = 0.00001;
+                    g.joints[end_i] = nj;
+                    frontier_add_from(g, end_i);
+                    g.ctl[1] = 0;          // nothing to evaluate in flood mode
+                    continue;
+                }
+                const Joint nj = g.eval_joint[edge];
+                if (!computed) {
+                    if (nj.v == 0.0) continue;     // block_joints has no effect (src/cifcaf.cpp:291-295)
+                    if (!g.gp.greedy) {
+                        heap_push(g, (float)nj.v, edge | (1 << 30));
+                        continue;
+                    }
+                }
+                g.joints[end_i] = nj;
+                frontier_add_from(g, end_i);
+            }
+            g.ctl[2] = (g.ctl[0] == 0 && g.ctl[1] == 0) ? 1 : 0;
+        }
+        __syncthreads();
+        if (g.ctl[2]) break;
+    }
+    __syncthreads();
+}
+
+// Occupancy (src/occupancy.cpp:13-43) on a byte map with epoch tags.
+struct Occ {
+    unsigned char* map;   // image base [F][Ho][Wo]
+    int F, Ho, Wo;
+    double reduction, min_scale_reduced;
+    unsigned char tag;
+};
+
+__device__ __forceinline__ bool occ_get(const Occ& o, long long f, double x, double y) {
+    if (f >= o.F) return true;
+    if (o.reduction != 1.0) { x /= o.reduction; y /= o.reduction; }
+    const long long xi = clamp_ll((long long)x, 0, o.Wo - 1);
+    const long long yi = clamp_ll((long long)y, 0, o.Ho - 1);
+    return reinterpret_cast<const volatile unsigned char*>(o.map)[((size_t)f * o.Ho + yi) * o.Wo + xi] == o.tag;
+}
+
+// one warp fills the box
+__device__ __forceinline__ void occ_set_warp(const Occ& o, long long f, double x, double y, double sigma, int lane) {
+    if (o.reduction != 1.0) {
+        x /= o.reduction; y /= o.reduction;
+        sigma = fmax(o.min_scale_reduced, sigma / o.reduction);
+    }
+    const long long minx = clamp_ll((long long)(x - sigma), 0, o.Wo - 1);
+    const long long miny = clamp_ll((long long)(y - sigma), 0, o.Ho - 1);
+    const long long maxx = clamp_ll((long long)(x + sigma), minx + 1, o.Wo);
+    const long long maxy = clamp_ll((long long)(y + sigma), miny + 1, o.Ho);
+    const int bw = (int)(maxx - minx), bh = (int)(maxy - miny);
+    volatile unsigned char* base = o.map + ((size_t)f * o.Ho + miny) * o.Wo + minx;
+    for (int k = lane; k < bw * bh; k += 32) base[(size_t)(k / bw) * o.Wo + (k % bw)] = o.tag;
+}
+
+__device__ void grow_ctx_init(GrowCtx& g, unsigned char* smem, int K, int C) {
+    size_t off = 0;
+    g.joints = reinterpret_cast<Joint*>(smem + off); off += sizeof(Joint) * K;
+    g.eval_joint = reinterpret_cast<Joint*>(smem + off); off += sizeof(Joint) * 2 * C;
+    g.score_cache = reinterpret_cast<float*>(smem + off); off += sizeof(float) * NW * SC_CAP;
+    g.heap_score = reinterpret_cast<float*>(smem + off); off += sizeof(float) * (2 * C + 2);
+    g.heap_item = reinterpret_cast<int*>(smem + off); off += sizeof(int) * (2 * C + 2);
+    g.new_edges = reinterpret_cast<int*>(smem + off); off += sizeof(int) * (2 * C + 2);
+    g.ctl = reinterpret_cast<int*>(smem + off); off += sizeof(int) * 8;
+    g.in_frontier = smem + off;
+}
+
+size_t grow_smem_bytes(int K, int C) {
+    return sizeof(Joint) * K + sizeof(Joint) * 2 * C + sizeof(float) * NW * SC_CAP
+           + (sizeof(float) + 2 * sizeof(int)) * (2 * C + 2) + sizeof(int) * 8 + 2 * C + 16;
+}
+
+struct Graph {
+    const int* skeleton; const int* adj_start; const int* adj_edge; const int* edge_lookup; const int* pair_id;
+};
+
+// Seed loop of CifCaf::call_with_initial_annotations (src/cifcaf.cpp:173-231).  One CTA per image.
+__global__ void __launch_bounds__(NT) k_grow(Dims d, Graph gr, GrowParams gp,
+                                             const int* __restrict__ seed_f, const float4* __restrict__ seed_vxys,
+                                             const int* __restrict__ n_seeds,
+                                             const float* __restrict__ lists, const int* __restrict__ list_counts,
+                                             unsigned char* __restrict__ occ_map, unsigned char occ_tag,
+                                             const float* __restrict__ init_ann, const long long* __restrict__ init_ids,
+                                             const int* __restrict__ init_counts, int init_cap,
+                                             Joint* __restrict__ anns, long long* __restrict__ ann_ids,
+                                             int* __restrict__ n_anns, int* __restrict__ flags) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_next;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    GrowCtx g;
+    grow_ctx_init(g, smem, d.K, d.C);
+    g.skeleton = gr.skeleton; g.adj_start = gr.adj_start; g.adj_edge = gr.adj_edge;
+    g.edge_lookup = gr.edge_lookup; g.pair_id = gr.pair_id;
+    g.lists = lists + ((size_t)b * d.C * 2 * 7) * d.hw;
+    g.list_counts = list_counts + (size_t)b * d.C * 2;
+    g.K = d.K; g.C = d.C; g.F = d.F; g.hw = d.hw; g.gp = gp;
+
+    Occ occ;
+    occ.map = occ_map + (size_t)b * d.F * d.Ho * d.Wo;
+    occ.F = d.F; occ.Ho = d.Ho; occ.Wo = d.Wo;
+    occ.reduction = gp.occ_reduction; occ.min_scale_reduced = gp.occ_min_scale_reduced;
+    occ.tag = occ_tag;
+
+    Joint* my_anns = anns + (size_t)b * d.max_ann * d.K;
+    long long* my_ids = ann_ids + (size_t)b * d.max_ann;
+    int n_ann = 0;
+    bool overflow = false;
+
+    auto finish_annotation = [&](long long id) {
+        // occupancy.set for every joint (src/cifcaf.cpp:196-200, 225-229) + store
+        __syncthreads();
+        for (int of = warp; of < d.F && of < d.K; of += NW) {
+            const Joint j = g.joints[of];
+            if (j.v == 0.0) continue;
+            occ_set_warp(occ, of, j.x, j.y, j.s, lane);
+        }
+        for (int k = tid; k < d.K; k += NT) my_anns[(size_t)n_ann * d.K + k] = g.joints[k];
+        if (tid == 0) my_ids[n_ann] = id;
+        n_ann++;
+        __syncthreads();
+    };
+
+    // initial annotations (src/cifcaf.cpp:177-202)
+    const int n_init = (init_ann != nullptr && init_counts != nullptr) ? init_counts[b] : 0;
+    for (int a = 0; a < n_init; a++) {
+        if (n_ann >= d.max_ann) { overflow = true; break; }
+        __syncthreads();
+        for (int k = tid; k < d.K; k += NT) {
+            const float* s = init_ann + (((size_t)b * init_cap + a) * d.K + k) * 4;
+            Joint j; j.v = s[0]; j.x = s[1]; j.y = s[2]; j.s = s[3];
+            g.joints[k] = j;
+        }
+        cta_grow(g, true, 1.0, false);
+        finish_annotation(init_ids[(size_t)b * init_cap + a]);
+    }
+
+    const int ns = n_seeds[b];
+    const int* sf = seed_f + (size_t)b * d.F * d.hw;
+    const float4* sv = seed_vxys + (size_t)b * d.F * d.hw;
+    int ptr = 0;
+    while (ptr < ns && !overflow) {
+        __syncthreads();
+        if (tid == 0) s_next = INT_MAX;
+        __syncthreads();
+        const int idx = ptr + tid;
+        if (idx < ns) {
+            const float4 s = sv[idx];
+            if (!occ_get(occ, sf[idx], (double)s.y, (double)s.z)) atomicMin(&s_next, idx);
+        }
+        __syncthreads();
+        const int next = s_next;
+        if (next == INT_MAX) { ptr += NT; continue; }
+        ptr = next + 1;
+        if (n_ann >= d.max_ann) { overflow = true; break; }
+        const float4 s = sv[next];
+        const int f = sf[next];
+        for (int k = tid; k < d.K; k += NT) {
+            Joint j; j.v = 0.0; j.x = 0.0; j.y = 0.0; j.s = 0.0;
+            if (k == f) { j.v = (double)s.x; j.x = (double)s.y; j.y = (double)s.z; j.s = (double)s.w; }
+            g.joints[k] = j;
+        }
+        cta_grow(g, true, 1.0, false);
+        finish_annotation(-1);
+    }
+    if (tid == 0) {
+        n_anns[b] = n_ann;
+        flags[b] = overflow ? 1 : 0;
+    }
+}
+
+// _force_complete + _flood_fill (src/cifcaf.cpp:233-236, 414-449); lists were
+// refilled at force_complete_caf_th by k_caf_scored.
+__global__ void __launch_bounds__(NT) k_force_complete(Dims d, Graph gr, GrowParams gp,
+                                                       const float* __restrict__ lists,
+                                                       const int* __restrict__ list_counts,
+                                                       Joint* __restrict__ anns, const int* __restrict__ n_anns) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    GrowCtx g;
+    grow_ctx_init(g, smem, d.K, d.C);
+    g.skeleton = gr.skeleton; g.adj_start = gr.adj_start; g.adj_edge = gr.adj_edge;
+    g.edge_lookup = gr.edge_lookup; g.pair_id = gr.pair_id;
+    g.lists = lists + ((size_t)b * d.C * 2 * 7) * d.hw;
+    g.list_counts = list_counts + (size_t)b * d.C * 2;
+    g.K = d.K; g.C = d.C; g.F = d.F; g.hw = d.hw; g.gp = gp;
+    Joint* my_anns = anns + (size_t)b * d.max_ann * d.K;
+    const int n = n_anns[b];
+    for (int a = 0; a < n; a++) {
+        __syncthreads();
+        for (int k = tid; k < d.K; k += NT) g.joints[k] = my_anns[(size_t)a * d.K + k];
+        cta_grow(g, false, 4.0, false);
+        cta_grow(g, false, 4.0, true);     // per-annotation order is equivalent: annotations are independent here
+        for (int k = tid; k < d.K; k += NT) my_anns[(size_t)a * d.K + k] = g.joints[k];
+    }
+}
+
+// include/openpifpaf/decoder/utils/nms_keypoints.hpp:25-32
+__device__ double uniform_score(const Joint* joints, int K) {
+    double init = 0.0;
+    for (int k = 0; k < K; k++) { const float i = (float)init; init = (double)i + joints[k].v; }
+    return init / (double)K;
+}
+
+// NMSKeypoints::call (src/nms_keypoints.cpp:17-69) + output packing (src/cifcaf.cpp:246-261).
+__global__ void __launch_bounds__(NT) k_nms(Dims d, GrowParams gp, Joint* __restrict__ anns,
+                                            const long long* __restrict__ ann_ids, const int* __restrict__ n_anns,
+                                            unsigned char* __restrict__ occ_map, unsigned char occ_tag,
+                                            float4* __restrict__ out_ann, long long* __restrict__ out_ids,
+                                            int* __restrict__ out_counts) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double* score = reinterpret_cast<double*>(smem);                 // [max_ann]
+    int* order = reinterpret_cast<int*>(score + d.max_ann);          // [max_ann] sorted position -> annotation
+    int* keep_rank = order + d.max_ann;                              // [max_ann]
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    Joint* my_anns = anns + (size_t)b * d.max_ann * d.K;
+    const int n = n_anns[b];
+
+    Occ occ;
+    occ.map = occ_map + (size_t)b * d.F * d.Ho * d.Wo;
+    occ.F = d.F; occ.Ho = d.Ho; occ.Wo = d.Wo;
+    occ.reduction = gp.occ_reduction; occ.min_scale_reduced = gp.occ_min_scale_reduced;
+    occ.tag = occ_tag;     // fresh tag == occupancy->clear() (src/nms_keypoints.cpp:18)
+
+    for (int a = tid; a < n; a += NT) score[a] = uniform_score(my_anns + (size_t)a * d.K, d.K);
+    __syncthreads();
+    // std::sort descending; exact ties keep creation order
+    for (int a = tid; a < n; a += NT) {
+        const double s = score[a];
+        int r = 0;
+        for (int o = 0; o < n; o++) {
+            const double so = score[o];
+            if (so > s || (so == s && o < a)) r++;
+        }
+        order[r] = a;
+    }
+    __syncthreads();
+    // occupancy planes of different keypoints are independent: one warp per field,
+    // annotations in sorted order inside (src/nms_keypoints.cpp:29-45)
+    for (int f = warp; f < d.K && f < d.F; f += NW) {
+        for (int r = 0; r < n; r++) {
+            Joint* jp = my_anns + (size_t)order[r] * d.K + f;
+            const Joint j = *jp;
+            if (j.v == 0.0) continue;
+            if (occ_get(occ, f, j.x, j.y)) {
+                if (lane == 0) jp->v = j.v * gp.nms_suppression;
+            } else {
+                occ_set_warp(occ, f, j.x, j.y, j.s, lane);
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < n * d.K; i += NT) {
+        if (!(my_anns[i].v > gp.nms_keypoint_threshold)) my_anns[i].v = 0.0;
+    }
+    __syncthreads();
+    for (int a = tid; a < n; a += NT) score[a] = uniform_score(my_anns + (size_t)a * d.K, d.K);
+    __syncthreads();
+    // remove_if(score < instance_threshold) keeps the first sort's order; second sort
+    for (int r = tid; r < n; r += NT) {
+        const int a = order[r];
+        const double s = score[a];
+        int kr = -1;
+        if (!(s < gp.nms_instance_threshold)) {
+            kr = 0;
+            for (int r2 = 0; r2 < n; r2++) {
+                const double so = score[order[r2]];
+                if (so < gp.nms_instance_threshold) continue;
+                if (so > s || (so == s && r2 < r)) kr++;
+            }
+        }
+        keep_rank[a] = kr;
+    }
+    __syncthreads();
+    int kept = 0;
+    for (int a = 0; a < n; a++) kept += (keep_rank[a] >= 0) ? 1 : 0;     // uniform, n is small
+    float4* my_out = out_ann + (size_t)b * d.max_ann * d.K;
+    for (int i = tid; i < n * d.K; i += NT) {
+        const int a = i / d.K, k = i % d.K;
+        const int kr = keep_rank[a];
+        if (kr < 0) continue;
+        const Joint j = my_anns[(size_t)a * d.K + k];
+        my_out[(size_t)kr * d.K + k] = make_float4((float)j.v, (float)j.x, (float)j.y, (float)j.s);
+    }
+    for (int a = tid; a < n; a += NT) {
+        const int kr = keep_rank[a];
+        if (kr >= 0) out_ids[(size_t)b * d.max_ann + kr] = ann_ids[(size_t)b * d.max_ann + a];
+    }
+    if (tid == 0) out_counts[b] = kept;
+}
+
+// pack every image's annotations contiguously for one small D2H copy
+__global__ void __launch_bounds__(NT) k_pack(Dims d, const float4* __restrict__ out_ann,
+                                             const long long* __restrict__ out_ids,
+                                             const int* __restrict__ out_counts,
+                                             float4* __restrict__ packed_ann, long long* __restrict__ packed_ids,
+                                             int* __restrict__ offsets) {
+    __shared__ int s_off;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) {
+        int off = 0;
+        for (int i = 0; i < b; i++) off += out_counts[i];
+        s_off = off;
+        offsets[b] = off;
+        if (b == d.B - 1) offsets[d.B] = off + out_counts[b];
+    }
+    __syncthreads();
+    const int off = s_off, n = out_counts[b];
+    const float4* src = out_ann + (size_t)b * d.max_ann * d.K;
+    for (int i = tid; i < n * d.K; i += NT) packed_ann[(size_t)off * d.K + i] = src[i];
+    for (int i = tid; i < n; i += NT) packed_ids[off + i] = out_ids[(size_t)b * d.max_ann + i];
+}
+
+__global__ void k_blend_single(const float* __restrict__ L, int n, double x, double y, double s,
+                               double filter_sigmas, int only_max, double* __restrict__ out) {
+    __shared__ float cache[SC_CAP];
+    const Joint j = warp_blend(L, n, n, x, y, s, filter_sigmas, only_max != 0, cache, threadIdx.x & 31);
+    if (threadIdx.x == 0) { out[0] = j.x; out[1] = j.y; out[2] = j.s; out[3] = j.v; }
+}
+
+template <typename T>
+int dev_alloc(T** p, size_t n) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), sizeof(T) * (n ? n : 1));
+    if (e != cudaSuccess) {
+        pifpaf::set_error("cudaMalloc of %zu bytes failed: %s", sizeof(T) * n, cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? PIFPAF_E_NOMEM : PIFPAF_E_CUDA;
+    }
+    return PIFPAF_OK;
+}
+
+}  // namespace
+
+struct pifpaf_decoder {
+    int device = 0;
+    int K = 0, F = 0, C = 0;
+    int max_batch = 0, max_h = 0, max_w = 0, max_stride = 0, max_ann = 0;
+    std::vector<int64_t> skeleton;
+    // graph
+    int *d_skeleton = nullptr, *d_adj_start = nullptr, *d_adj_edge = nullptr, *d_edge_lookup = nullptr, *d_pair_id = nullptr;
+    // workspace
+    float* d_cifhr = nullptr;
+    float4* d_cells = nullptr; int4* d_boxes = nullptr; int* d_cell_counts = nullptr;
+    float* d_seg_v = nullptr; float4* d_seg_xys = nullptr; int* d_seg_counts = nullptr;
+    unsigned *d_keys_a = nullptr, *d_vals_a = nullptr, *d_keys_b = nullptr, *d_vals_b = nullptr;
+    int* d_seed_f = nullptr; float4* d_seed_vxys = nullptr; int* d_n_seeds = nullptr;
+    float* d_lists = nullptr; int* d_list_counts = nullptr;
+    unsigned char* d_occ = nullptr; size_t occ_bytes = 0;
+    Joint* d_anns = nullptr; long long* d_ann_ids = nullptr; int* d_n_anns = nullptr; int* d_flags = nullptr;
+    float4* d_out_ann = nullptr; long long* d_out_ids = nullptr; int* d_out_counts = nullptr;
+    float4* d_packed_ann = nullptr; long long* d_packed_ids = nullptr; int* d_offsets = nullptr;
+    // single-image host path
+    float *d_in_cif = nullptr, *d_in_caf = nullptr, *d_in_init = nullptr; long long* d_in_init_ids = nullptr;
+    int* d_in_init_count = nullptr; int in_init_cap = 0;
+    // pinned staging
+    int* h_meta = nullptr;            // counts[B], flags[B], offsets[B+1], n_anns[B]
+    float* h_packed_ann = nullptr; long long* h_packed_ids = nullptr;
+    cudaStream_t own_stream = nullptr;
+    unsigned epoch = 1;               // occupancy tags: epoch (seed loop), epoch+1 (NMS)
+    Dims last{};
+    bool has_last = false;
+    double last_revision = 1.0;
+};
+
+namespace {
+
+int validate_dims(pifpaf_decoder* dec, int batch, int h, int w, int cif_stride, int caf_stride) {
+    PIFPAF_CHECK_ARG(dec != nullptr, "decoder handle is null");
+    PIFPAF_CHECK_ARG(batch >= 1 && batch <= dec->max_batch, "batch exceeds max_batch given at create()");
+    PIFPAF_CHECK_ARG(h >= 1 && w >= 1 && h <= dec->max_h && w <= dec->max_w, "field shape exceeds max_h/max_w");
+    PIFPAF_CHECK_ARG(cif_stride >= 1 && cif_stride <= dec->max_stride, "cif_stride exceeds max_stride");
+    PIFPAF_CHECK_ARG(caf_stride >= 1 && caf_stride <= dec->max_stride, "caf_stride exceeds max_stride");
+    return PIFPAF_OK;
+}
+
+Dims make_dims(const pifpaf_decoder* dec, int batch, int h, int w, int cif_stride, int caf_stride,
+               double occ_reduction) {
+    Dims d;
+    d.B = batch; d.F = dec->F; d.C = dec->C; d.K = dec->K;
+    d.h = h; d.w = w; d.hw = h * w;
+    d.cif_stride = cif_stride; d.caf_stride = caf_stride;
+    d.H = (h - 1) * cif_stride + 1; d.W = (w - 1) * cif_stride + 1;     // src/cif_hr.cpp:110-114
+    d.Wp = (d.W + TILE - 1) / TILE * TILE;
+    d.Ho = (int)((double)d.H / occ_reduction) + 1;                      // src/occupancy.cpp:47-48
+    d.Wo = (int)((double)d.W / occ_reduction) + 1;
+    d.tiles_x = d.Wp / TILE; d.tiles_y = (d.H + TILE - 1) / TILE;
+    d.max_ann = dec->max_ann;
+    return d;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pifpaf_decoder_default_params(pifpaf_decoder_params_t* p) {
+    PIFPAF_CHECK_ARG(p != nullptr, "params is null");
+    std::memset(p, 0, sizeof(*p));
+    p->cifhr_neighbors = 16; p->cifhr_threshold = 0.3;
+    p->seed_threshold = 0.2;
+    p->caf_score_th = 0.3; p->caf_cif_floor = 0.1;
+    p->keypoint_threshold = 0.15; p->keypoint_threshold_rel = 0.5;
+    p->reverse_match = 1; p->force_complete_caf_th = 0.001;
+    p->nms_suppression = 0.00001; p->nms_instance_threshold = 0.15; p->nms_keypoint_threshold = 0.15;
+    p->occ_reduction = 2.0; p->occ_min_scale = 4.0;
+    p->cifhr_revision = 1.0;
+    return PIFPAF_OK;
+}
+
+void pifpaf_decoder_destroy(pifpaf_decoder_t* dec) {
+    if (!dec) return;
+    cudaSetDevice(dec->device);
+    void* dev_ptrs[] = {dec->d_skeleton, dec->d_adj_start, dec->d_adj_edge, dec->d_edge_lookup, dec->d_pair_id,
+        dec->d_cifhr, dec->d_cells, dec->d_boxes, dec->d_cell_counts, dec->d_seg_v, dec->d_seg_xys,
+        dec->d_seg_counts, dec->d_keys_a, dec->d_vals_a, dec->d_keys_b, dec->d_vals_b, dec->d_seed_f,
+        dec->d_seed_vxys, dec->d_n_seeds, dec->d_lists, dec->d_list_counts, dec->d_occ, dec->d_anns,
+        dec->d_ann_ids, dec->d_n_anns, dec->d_flags, dec->d_out_ann, dec->d_out_ids, dec->d_out_counts,
+        dec->d_packed_ann, dec->d_packed_ids, dec->d_offsets, dec->d_in_cif, dec->d_in_caf, dec->d_in_init,
+        dec->d_in_init_ids, dec->d_in_init_count};
+    for (void* p : dev_ptrs) if (p) cudaFree(p);
+    if (dec->h_meta) cudaFreeHost(dec->h_meta);
+    if (dec->h_packed_ann) cudaFreeHost(dec->h_packed_ann);
+    if (dec->h_packed_ids) cudaFreeHost(dec->h_packed_ids);
+    if (dec->own_stream) cudaStreamDestroy(dec->own_stream);
+    delete dec;
+}
+
+int pifpaf_decoder_create(pifpaf_decoder_t** out, int32_t device, int32_t n_keypoints, int32_t n_cif_fields,
+                          int32_t n_connections, const int64_t* skeleton,
+                          int32_t max_batch, int32_t max_h, int32_t max_w, int32_t max_stride,
+                          int32_t max_annotations) {
+    PIFPAF_CHECK_ARG(out != nullptr, "out is null");
+    *out = nullptr;
+    PIFPAF_CHECK_ARG(n_keypoints >= 1 && n_cif_fields >= 1 && n_connections >= 0, "bad keypoint/field/connection count");
+    PIFPAF_CHECK_ARG(n_cif_fields <= n_keypoints,
+                     "NMS occupancy map must be of same size or smaller as annotation");   // src/nms_keypoints.cpp:30-31
+    PIFPAF_CHECK_ARG(skeleton != nullptr || n_connections == 0, "skeleton is null");
+    PIFPAF_CHECK_ARG(max_batch >= 1 && max_h >= 1 && max_w >= 1 && max_stride >= 1, "bad capacity");
+    PIFPAF_CHECK_ARG(max_annotations >= 1 && max_annotations <= 8192, "max_annotations must be in [1, 8192]");
+    PIFPAF_CHECK_ARG(n_connections <= (1 << 20), "too many connections");
+    for (int c = 0; c < n_connections; c++) {
+        PIFPAF_CHECK_ARG(skeleton[2 * c] >= 0 && skeleton[2 * c] < n_keypoints &&
+                         skeleton[2 * c + 1] >= 0 && skeleton[2 * c + 1] < n_keypoints,
+                         "skeleton index out of range (must be 0-based and < n_keypoints)");
+    }
+    int n_dev = 0;
+    PIFPAF_CUDA_TRY(cudaGetDeviceCount(&n_dev));
+    PIFPAF_CHECK_ARG(device >= 0 && device < n_dev, "no such CUDA device");
+    PIFPAF_CUDA_TRY(cudaSetDevice(device));
+
+    pifpaf_decoder* dec = new pifpaf_decoder();
+    dec->device = device;
+    dec->K = n_keypoints; dec->F = n_cif_fields; dec->C = n_connections;
+    dec->max_batch = max_batch; dec->max_h = max_h; dec->max_w = max_w; dec->max_stride = max_stride;
+    dec->max_ann = max_annotations;
+    dec->skeleton.assign(skeleton, skeleton + 2 * (size_t)n_connections);
+
+    const int K = dec->K, C = dec->C, F = dec->F;
+    // graph tables -------------------------------------------------------
+    std::vector<int> sk(2 * (size_t)C + 2, 0);
+    for (int i = 0; i < 2 * C; i++) sk[i] = (int)skeleton[i];
+    std::vector<int> adj_start(K + 1, 0), adj_edge;
+    for (int j = 0; j < K; j++) {
+        adj_start[j] = (int)adj_edge.size();
+        for (int c = 0; c < C; c++) {           // src/cifcaf.cpp:323-345: first branch wins
+            if (sk[2 * c] == j) adj_edge.push_back(2 * c);
+            else if (sk[2 * c + 1] == j) adj_edge.push_back(2 * c + 1);
+        }
+    }
+    adj_start[K] = (int)adj_edge.size();
+    std::vector<int> edge_lookup(2 * (size_t)C + 2, 0), pair_id(2 * (size_t)C + 2, 0);
+    for (int e = 0; e < 2 * C; e++) {
+        const int c = e >> 1, dir = e & 1;
+        const int start_i = sk[2 * c + dir], end_i = sk[2 * c + 1 - dir];
+        int caf_i = 0, forward = 1;
+        for (int f = 0; f < C; f++) {           // src/cifcaf.cpp:360-373
+            if (sk[2 * f] == start_i && sk[2 * f + 1] == end_i) { forward = 1; break; }
+            if (sk[2 * f + 1] == start_i && sk[2 * f] == end_i) { forward = 0; break; }
+            caf_i++;
+        }
+        edge_lookup[e] = caf_i * 2 + forward;
+        int pid = e;
+        for (int e2 = 0; e2 < e; e2++) {
+            const int c2 = e2 >> 1, d2 = e2 & 1;
+            if (sk[2 * c2 + d2] == start_i && sk[2 * c2 + 1 - d2] == end_i) { pid = e2; break; }
+        }
+        pair_id[e] = pid;
+    }
+    if (adj_edge.empty()) adj_edge.push_back(0);
+
+    int rc = PIFPAF_OK;
+#define ALLOC(ptr, n) do { rc = dev_alloc(&(ptr), (n)); if (rc != PIFPAF_OK) { pifpaf_decoder_destroy(dec); return rc; } } while (0)
+#define TRY_D(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { pifpaf::set_error("%s failed: %s", #expr, cudaGetErrorString(e__)); pifpaf_decoder_destroy(dec); return PIFPAF_E_CUDA; } } while (0)
+    ALLOC(dec->d_skeleton, sk.size()); ALLOC(dec->d_adj_start, adj_start.size());
+    ALLOC(dec->d_adj_edge, adj_edge.size()); ALLOC(dec->d_edge_lookup, edge_lookup.size());
+    ALLOC(dec->d_pair_id, pair_id.size());
+    TRY_D(cudaMemcpy(dec->d_skeleton, sk.data(), sizeof(int) * sk.size(), cudaMemcpyHostToDevice));
+    TRY_D(cudaMemcpy(dec->d_adj_start, adj_start.data(), sizeof(int) * adj_start.size(), cudaMemcpyHostToDevice));
+    TRY_D(cudaMemcpy(dec->d_adj_edge, adj_edge.data(), sizeof(int) * adj_edge.size(), cudaMemcpyHostToDevice));
+    TRY_D(cudaMemcpy(dec->d_edge_lookup, edge_lookup.data(), sizeof(int) * edge_lookup.size(), cudaMemcpyHostToDevice));
+    TRY_D(cudaMemcpy(dec->d_pair_id, pair_id.data(), sizeof(int) * pair_id.size(), cudaMemcpyHostToDevice));
+
+    // workspace ------------------------------------------------------------
+    const size_t B = max_batch, hw = (size_t)max_h * max_w;
+    const size_t Hm = (size_t)(max_h - 1) * max_stride + 1, Wm = (size_t)(max_w - 1) * max_stride + 1;
+    const size_t Wpm = (Wm + TILE - 1) / TILE * TILE;
+    ALLOC(dec->d_cifhr, B * F * Hm * Wpm);
+    ALLOC(dec->d_cells, B * F * hw); ALLOC(dec->d_boxes, B * F * hw); ALLOC(dec->d_cell_counts, B * F);
+    ALLOC(dec->d_seg_v, B * F * hw); ALLOC(dec->d_seg_xys, B * F * hw); ALLOC(dec->d_seg_counts, B * F);
+    ALLOC(dec->d_keys_a, B * F * hw); ALLOC(dec->d_vals_a, B * F * hw);
+    ALLOC(dec->d_keys_b, B * F * hw); ALLOC(dec->d_vals_b, B * F * hw);
+    ALLOC(dec->d_seed_f, B * F * hw); ALLOC(dec->d_seed_vxys, B * F * hw); ALLOC(dec->d_n_seeds, B);
+    ALLOC(dec->d_lists, B * (size_t)C * 2 * 7 * hw); ALLOC(dec->d_list_counts, B * (size_t)C * 2);
+    // occupancy never needs more than the un-reduced map (reduction >= 1)
+    dec->occ_bytes = B * F * (Hm + 1) * (Wm + 1);
+    ALLOC(dec->d_occ, dec->occ_bytes);
+    TRY_D(cudaMemset(dec->d_occ, 0, dec->occ_bytes));
+    const size_t A = max_annotations;
+    ALLOC(dec->d_anns, B * A * K); ALLOC(dec->d_ann_ids, B * A); ALLOC(dec->d_n_anns, B); ALLOC(dec->d_flags, B);
+    ALLOC(dec->d_out_ann, B * A * K); ALLOC(dec->d_out_ids, B * A); ALLOC(dec->d_out_counts, B);
+    ALLOC(dec->d_packed_ann, B * A * K); ALLOC(dec->d_packed_ids, B * A); ALLOC(dec->d_offsets, B + 1);
+    ALLOC(dec->d_in_cif, (size_t)F * 5 * hw); ALLOC(dec->d_in_caf, (size_t)C * 8 * hw);
+    dec->in_init_cap = max_annotations;
+    ALLOC(dec->d_in_init, A * K * 4); ALLOC(dec->d_in_init_ids, A); ALLOC(dec->d_in_init_count, 1);
+    TRY_D(cudaMallocHost(reinterpret_cast<void**>(&dec->h_meta), sizeof(int) * (4 * B + 2)));
+    TRY_D(cudaMallocHost(reinterpret_cast<void**>(&dec->h_packed_ann), sizeof(float4) * B * A * K));
+    TRY_D(cudaMallocHost(reinterpret_cast<void**>(&dec->h_packed_ids), sizeof(long long) * B * A));
+    TRY_D(cudaStreamCreateWithFlags(&dec->own_stream, cudaStreamNonBlocking));
+
+    const size_t gs = grow_smem_bytes(K, C);
+    TRY_D(cudaFuncSetAttribute(k_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs));
+    TRY_D(cudaFuncSetAttribute(k_force_complete, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs));
+    const size_t ns = (sizeof(double) + 2 * sizeof(int)) * A + 16;
+    TRY_D(cudaFuncSetAttribute(k_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ns));
+    const size_t ss = sizeof(int) * (((size_t)F + 1 + 3) / 4 * 4 + 256 + 256 + 8) + 2 * 32 * 256 + 16;
+    TRY_D(cudaFuncSetAttribute(k_seed_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss));
+#undef ALLOC
+#undef TRY_D
+    *out = dec;
+    return PIFPAF_OK;
+}
+
+int pifpaf_decoder_decode_device(pifpaf_decoder_t* dec, const float* cif_dev, const float* caf_dev,
+                                 int32_t batch, int32_t h, int32_t w, int32_t cif_stride, int32_t caf_stride,
+                                 const float* init_ann_dev, const int64_t* init_ids_dev,
+                                 const int32_t* init_counts_dev, int32_t init_cap,
+                                 const pifpaf_decoder_params_t* params, void* stream_v) {
+    int rc = validate_dims(dec, batch, h, w, cif_stride, caf_stride);
+    if (rc != PIFPAF_OK) return rc;
+    PIFPAF_CHECK_ARG(cif_dev != nullptr && caf_dev != nullptr, "field pointer is null");
+    PIFPAF_CHECK_ARG(params != nullptr, "params is null");
+    PIFPAF_CHECK_ARG(params->occ_reduction >= 1.0, "occ_reduction must be >= 1");
+    PIFPAF_CHECK_ARG(params->cifhr_neighbors != 0, "cifhr_neighbors must be non-zero");
+    PIFPAF_CHECK_ARG(init_ann_dev == nullptr || (init_ids_dev != nullptr && init_counts_dev != nullptr),
+                     "require initial_ids when initial_annotations are given");   // src/cifcaf.cpp:178
+    PIFPAF_CUDA_TRY(cudaSetDevice(dec->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
+    const pifpaf_decoder_params_t& p = *params;
+    const Dims d = make_dims(dec, batch, h, w, cif_stride, caf_stride, p.occ_reduction);
+    dec->last = d; dec->has_last = true; dec->last_revision = p.cifhr_revision;
+
+    // occupancy epoch tags (Occupancy::clear == revision++, src/occupancy.cpp:71-77)
+    if (dec->epoch + 1 > 254) {
+        PIFPAF_CUDA_TRY(cudaMemsetAsync(dec->d_occ, 0, dec->occ_bytes, st));
+        dec->epoch = 1;
+    }
+    const unsigned char tag_seed = (unsigned char)dec->epoch, tag_nms = (unsigned char)(dec->epoch + 1);
+    dec->epoch += 2;
+
+    GrowParams gp;
+    gp.keypoint_threshold = p.keypoint_threshold; gp.keypoint_threshold_rel = p.keypoint_threshold_rel;
+    gp.reverse_match = p.reverse_match; gp.greedy = p.greedy;
+    gp.occ_reduction = p.occ_reduction; gp.occ_min_scale_reduced = p.occ_min_scale / p.occ_reduction;
+    gp.nms_suppression = p.nms_suppression; gp.nms_instance_threshold = p.nms_instance_threshold;
+    gp.nms_keypoint_threshold = p.nms_keypoint_threshold;
+    Graph gr{dec->d_skeleton, dec->d_adj_start, dec->d_adj_edge, dec->d_edge_lookup, dec->d_pair_id};
+
+    // CifHr (src/cifcaf.cpp:140-142: accumulate(cif, stride, min_scale 0.0, factor 1.0))
+    if (p.cifhr_ablation_skip) {
+        PIFPAF_CUDA_TRY(cudaMemsetAsync(dec->d_cifhr, 0, sizeof(float) * (size_t)d.B * d.F * d.H * d.Wp, st));
+    } else {
+        const float min_scale_f = (float)(0.0 / (double)cif_stride);
+        k_cif_compact<<<dim3(d.F, d.B), NT, 0, st>>>(cif_dev, d, p.cifhr_threshold, (long long)p.cifhr_neighbors,
+                                                     min_scale_f, 1.0, dec->d_cells, dec->d_boxes, dec->d_cell_counts);
+        PIFPAF_LAUNCH_CHECK();
+        k_cifhr_tiles<<<dim3(d.tiles_x * d.tiles_y, d.F, d.B), NT, 0, st>>>(d, p.cifhr_revision, dec->d_cells,
+                                                                            dec->d_boxes, dec->d_cell_counts, dec->d_cifhr);
+        PIFPAF_LAUNCH_CHECK();
+    }
+    // seeds (src/cifcaf.cpp:144-148)
+    k_seed_candidates<<<dim3(d.F, d.B), NT, 0, st>>>(cif_dev, d, dec->d_cifhr, p.cifhr_revision, p.seed_threshold,
+                                                     p.seeds_ablation_nms, p.seeds_ablation_no_rescore,
+                                                     dec->d_seg_v, dec->d_seg_xys, dec->d_seg_counts);
+    PIFPAF_LAUNCH_CHECK();
+    const size_t ss = sizeof(int) * (((size_t)d.F + 1 + 3) / 4 * 4 + 256 + 256 + 8) + 2 * 32 * 256 + 16;
+    k_seed_sort<<<d.B, SORT_NT, ss, st>>>(d, dec->d_seg_counts, dec->d_seg_v, dec->d_seg_xys, dec->d_keys_a,
+                                          dec->d_vals_a, dec->d_keys_b, dec->d_vals_b, dec->d_seed_f,
+                                          dec->d_seed_vxys, dec->d_n_seeds);
+    PIFPAF_LAUNCH_CHECK();
+    // caf scored (src/cifcaf.cpp:153-161: CafScored(cifhr, rev, -1.0, 0.1))
+    if (d.C > 0) {
+        k_caf_scored<<<dim3(d.C, d.B), NT, 0, st>>>(caf_dev, d, dec->d_skeleton, dec->d_cifhr, p.cifhr_revision,
+                                                    p.caf_score_th, p.caf_cif_floor, p.caf_ablation_no_rescore,
+                                                    dec->d_lists, dec->d_list_counts);
+        PIFPAF_LAUNCH_CHECK();
+    }
+    const size_t gs = grow_smem_bytes(d.K, d.C);
+    k_grow<<<d.B, NT, gs, st>>>(d, gr, gp, dec->d_seed_f, dec->d_seed_vxys, dec->d_n_seeds, dec->d_lists,
+                                dec->d_list_counts, dec->d_occ, tag_seed, init_ann_dev,
+                                reinterpret_cast<const long long*>(init_ids_dev), init_counts_dev, init_cap,
+                                dec->d_anns, dec->d_ann_ids, dec->d_n_anns, dec->d_flags);
+    PIFPAF_LAUNCH_CHECK();
+    if (p.force_complete && d.C > 0) {
+        // src/cifcaf.cpp:414-426: CafScored(cifhr, rev, force_complete_caf_th, 0.1); score_th_ >= 0 ? it : default
+        const double th = p.force_complete_caf_th >= 0.0 ? p.force_complete_caf_th : p.caf_score_th;
+        k_caf_scored<<<dim3(d.C, d.B), NT, 0, st>>>(caf_dev, d, dec->d_skeleton, dec->d_cifhr, p.cifhr_revision,
+                                                    th, 0.1, p.caf_ablation_no_rescore, dec->d_lists, dec->d_list_counts);
+        PIFPAF_LAUNCH_CHECK();
+        k_force_complete<<<d.B, NT, gs, st>>>(d, gr, gp, dec->d_lists, dec->d_list_counts, dec->d_anns, dec->d_n_anns);
+        PIFPAF_LAUNCH_CHECK();
+    }
+    const size_t ns = (sizeof(double) + 2 * sizeof(int)) * (size_t)d.max_ann + 16;
+    k_nms<<<d.B, NT, ns, st>>>(d, gp, dec->d_anns, dec->d_ann_ids, dec->d_n_anns, dec->d_occ, tag_nms,
+                               dec->d_out_ann, dec->d_out_ids, dec->d_out_counts);
+    PIFPAF_LAUNCH_CHECK();
+    k_pack<<<d.B, NT, 0, st>>>(d, dec->d_out_ann, dec->d_out_ids, dec->d_out_counts, dec->d_packed_ann,
+                               dec->d_packed_ids, dec->d_offsets);
+    PIFPAF_LAUNCH_CHECK();
+    return PIFPAF_OK;
+}
+
+int pifpaf_decoder_fetch(pifpaf_decoder_t* dec, int32_t* counts, float* ann, int64_t* ids,
+                         int32_t ann_cap, void* stream_v) {
+    PIFPAF_CHECK_ARG(dec != nullptr && dec->has_last, "no decode to fetch");
+    PIFPAF_CHECK_ARG(counts != nullptr, "counts is null");
+    PIFPAF_CUDA_TRY(cudaSetDevice(dec->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
+    const Dims& d = dec->last;
+    const int B = d.B;
+    int* h_counts = dec->h_meta; int* h_flags = dec->h_meta + B; int* h_off = dec->h_meta + 2 * B;
+    PIFPAF_CUDA_TRY(cudaMemcpyAsync(h_counts, dec->d_out_counts, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    PIFPAF_CUDA_TRY(cudaMemcpyAsync(h_flags, dec->d_flags, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    PIFPAF_CUDA_TRY(cudaMemcpyAsync(h_off, dec->d_offsets, sizeof(int) * (B + 1), cudaMemcpyDeviceToHost, st));
+    PIFPAF_CUDA_TRY(cudaStreamSynchronize(st));
+    const int total = h_off[B];
+    if (total > 0 && ann != nullptr) {
+        PIFPAF_CUDA_TRY(cudaMemcpyAsync(dec->h_packed_ann, dec->d_packed_ann, sizeof(float4) * (size_t)total * d.K,
+                                        cudaMemcpyDeviceToHost, st));
+        PIFPAF_CUDA_TRY(cudaMemcpyAsync(dec->h_packed_ids, dec->d_packed_ids, sizeof(long long) * (size_t)total,
+                                        cudaMemcpyDeviceToHost, st));
+        PIFPAF_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    bool overflow = false;
+    for (int b = 0; b < B; b++) {
+        counts[b] = h_counts[b];
+        if (h_flags[b]) overflow = true;
+        if (ann == nullptr) continue;
+        int n = h_counts[b];
+        if (n > ann_cap) { overflow = true; n = ann_cap; }
+        std::memcpy(ann + (size_t)b * ann_cap * d.K * 4, dec->h_packed_ann + (size_t)h_off[b] * d.K * 4,
+                    sizeof(float) * 4 * (size_t)n * d.K);
+        if (ids) std::memcpy(ids + (size_t)b * ann_cap, dec->h_packed_ids + h_off[b], sizeof(int64_t) * (size_t)n);
+    }
+    if (overflow) {
+        pifpaf::set_error("annotation capacity exceeded (max_annotations=%d, ann_cap=%d): "
+                          "create the decoder with a larger max_annotations", d.max_ann, ann_cap);
+        return PIFPAF_E_OVERFLOW;
+    }
+    return PIFPAF_OK;
+}
+
+int pifpaf_decoder_call(pifpaf_decoder_t* dec, const float* cif, int32_t cif_stride,
+                        const float* caf, int32_t caf_stride, int32_t h, int32_t w,
+                        const float* initial_annotations, const int64_t* initial_ids, int32_t n_initial,
+                        const pifpaf_decoder_params_t* params,
+                        float* out_ann, int64_t* out_ids, int32_t cap, int32_t* n_out) {
+    int rc = validate_dims(dec, 1, h, w, cif_stride, caf_stride);
+    if (rc != PIFPAF_OK) return rc;
+    PIFPAF_CHECK_ARG(cif != nullptr && caf != nullptr, "cif_field / caf_field is null");
+    PIFPAF_CHECK_ARG(n_out != nullptr, "n_out is null");
+    PIFPAF_CHECK_ARG(n_initial >= 0 && n_initial <= dec->in_init_cap, "too many initial annotations");
+    PIFPAF_CHECK_ARG(n_initial == 0 || (initial_annotations != nullptr && initial_ids != nullptr),
+                     "require initial_ids when initial_annotations are given");
+    PIFPAF_CUDA_TRY(cudaSetDevice(dec->device));
+    cudaStream_t st = dec->own_stream;
+    const size_t hw = (size_t)h * w;
+    PIFPAF_CUDA_TRY(cudaMemcpyAsync(dec->d_in_cif, cif, sizeof(float) * dec->F * 5 * hw, cudaMemcpyHostToDevice, st));
+    PIFPAF_CUDA_TRY(cudaMemcpyAsync(dec->d_in_caf, caf, sizeof(float) * dec->C * 8 * hw, cudaMemcpyHostToDevice, st));
+    const float* d_init = nullptr; const int64_t* d_ids = nullptr; const int* d_cnt = nullptr;
+    if (n_initial > 0) {
+        PIFPAF_CUDA_TRY(cudaMemcpyAsync(dec->d_in_init, initial_annotations, sizeof(float) * 4 * (size_t)n_initial * dec->K,
+                                        cudaMemcpyHostToDevice, st));
+        PIFPAF_CUDA_TRY(cudaMemcpyAsync(dec->d_in_init_ids, initial_ids, sizeof(int64_t) * (size_t)n_initial,
+                                        cudaMemcpyHostToDevice, st));
+        PIFPAF_CUDA_TRY(cudaMemcpyAsync(dec->d_in_init_count, &n_initial, sizeof(int), cudaMemcpyHostToDevice, st));
+        d_init = dec->d_in_init; d_ids = reinterpret_cast<const int64_t*>(dec->d_in_init_ids); d_cnt = dec->d_in_init_count;
+    }
+    rc = pifpaf_decoder_decode_device(dec, dec->d_in_cif, dec->d_in_caf, 1, h, w, cif_stride, caf_stride,
+                                      d_init, d_ids, d_cnt, dec->in_init_cap, params, st);
+    if (rc != PIFPAF_OK) return rc;
+    int32_t count = 0;
+    rc = pifpaf_decoder_fetch(dec, &count, out_ann, out_ids, cap, st);
+    *n_out = count;
+    return rc;
+}
+
+int pifpaf_decoder_tap_cifhr(pifpaf_decoder_t* dec, int32_t b, float* out, int64_t out_elems) {
+    PIFPAF_CHECK_ARG(dec != nullptr && dec->has_last, "no decode to tap");
+    const Dims& d = dec->last;
+    PIFPAF_CHECK_ARG(b >= 0 && b < d.B, "image index out of range");
+    PIFPAF_CHECK_ARG(out != nullptr && out_elems >= (int64_t)d.F * d.H * d.W, "output buffer too small");
+    PIFPAF_CUDA_TRY(cudaSetDevice(dec->device));
+    PIFPAF_CUDA_TRY(cudaDeviceSynchronize());
+    PIFPAF_CUDA_TRY(cudaMemcpy2D(out, sizeof(float) * d.W, dec->d_cifhr + (size_t)b * d.F * d.H * d.Wp,
+                                 sizeof(float) * d.Wp, sizeof(float) * d.W, (size_t)d.F * d.H, cudaMemcpyDeviceToHost));
+    return PIFPAF_OK;
+}
+
+int pifpaf_decoder_tap_seeds(pifpaf_decoder_t* dec, int32_t b, int64_t* out_f, float* out_vxys,
+                             int64_t cap, int64_t* n_out) {
+    PIFPAF_CHECK_ARG(dec != nullptr && dec->has_last, "no decode to tap");
+    const Dims& d = dec->last;
+    PIFPAF_CHECK_ARG(b >= 0 && b < d.B && n_out != nullptr, "bad argument");
+    PIFPAF_CUDA_TRY(cudaSetDevice(dec->device));
+    PIFPAF_CUDA_TRY(cudaDeviceSynchronize());
+    int n = 0;
+    PIFPAF_CUDA_TRY(cudaMemcpy(&n, dec->d_n_seeds + b, sizeof(int), cudaMemcpyDeviceToHost));
+    *n_out = n;
+    const int m = (int)std::min<int64_t>(n, cap);
+    if (m > 0 && out_f != nullptr && out_vxys != nullptr) {
+        std::vector<int> f(m);
+        const size_t img = (size_t)b * d.F * d.hw;
+        PIFPAF_CUDA_TRY(cudaMemcpy(f.data(), dec->d_seed_f + img, sizeof(int) * m, cudaMemcpyDeviceToHost));
+        PIFPAF_CUDA_TRY(cudaMemcpy(out_vxys, dec->d_seed_vxys + img, sizeof(float4) * m, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < m; i++) out_f[i] = f[i];
+    }
+    return PIFPAF_OK;
+}
+
+int pifpaf_decoder_tap_caf(pifpaf_decoder_t* dec, int32_t b, float* out_fwd, int64_t* n_fwd,
+                           float* out_bwd, int64_t* n_bwd) {
+    PIFPAF_CHECK_ARG(dec != nullptr && dec->has_last, "no decode to tap");
+    const Dims& d = dec->last;
+    PIFPAF_CHECK_ARG(b >= 0 && b < d.B, "image index out of range");
+    PIFPAF_CHECK_ARG(out_fwd && n_fwd && out_bwd && n_bwd, "output pointer is null");
+    PIFPAF_CUDA_TRY(cudaSetDevice(dec->device));
+    PIFPAF_CUDA_TRY(cudaDeviceSynchronize());
+    std::vector<float> soa((size_t)d.C * 2 * 7 * d.hw);
+    std::vector<int> cnt((size_t)d.C * 2);
+    if (d.C == 0) return PIFPAF_OK;
+    PIFPAF_CUDA_TRY(cudaMemcpy(soa.data(), dec->d_lists + (size_t)b * d.C * 2 * 7 * d.hw, sizeof(float) * soa.size(),
+                               cudaMemcpyDeviceToHost));
+    PIFPAF_CUDA_TRY(cudaMemcpy(cnt.data(), dec->d_list_counts + (size_t)b * d.C * 2, sizeof(int) * cnt.size(),
+                               cudaMemcpyDeviceToHost));
+    for (int c = 0; c < d.C; c++) {
+        for (int dir = 0; dir < 2; dir++) {
+            const int n = cnt[c * 2 + dir];
+            float* dst = (dir == 0 ? out_fwd : out_bwd) + (size_t)c * d.hw * 7;
+            const float* src = soa.data() + ((size_t)(c * 2 + dir) * 7) * d.hw;
+            for (int i = 0; i < n; i++)
+                for (int k = 0; k < 7; k++) dst[(size_t)i * 7 + k] = src[(size_t)k * d.hw + i];
+            (dir == 0 ? n_fwd : n_bwd)[c] = n;
+        }
+    }
+    return PIFPAF_OK;
+}
+
+int pifpaf_grow_connection_blend(const float* caf, int64_t n, double x, double y, double s,
+                                 double filter_sigmas, int32_t only_max, double* out_xysv) {
+    PIFPAF_CHECK_ARG(out_xysv != nullptr, "out is null");
+    PIFPAF_CHECK_ARG(n >= 0 && n < (1 << 28), "bad list length");
+    PIFPAF_CHECK_ARG(caf != nullptr || n == 0, "caf is null");
+    float* d_l = nullptr; double* d_o = nullptr;
+    std::vector<float> soa((size_t)7 * (n ? n : 1));
+    for (int64_t i = 0; i < n; i++)
+        for (int k = 0; k < 7; k++) soa[(size_t)k * n + i] = caf[(size_t)i * 7 + k];
+    PIFPAF_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_l), sizeof(float) * soa.size()));
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&d_o), sizeof(double) * 4);
+    if (e != cudaSuccess) { cudaFree(d_l); pifpaf::set_error("cudaMalloc failed"); return PIFPAF_E_CUDA; }
+    cudaMemcpy(d_l, soa.data(), sizeof(float) * soa.size(), cudaMemcpyHostToDevice);
+    k_blend_single<<<1, 32>>>(d_l, (int)n, x, y, s, filter_sigmas, only_max, d_o);
+    pifpaf::count_launch();
+    e = cudaMemcpy(out_xysv, d_o, sizeof(double) * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d_l); cudaFree(d_o);
+    if (e != cudaSuccess) { pifpaf::set_error("grow_connection_blend failed: %s", cudaGetErrorString(e)); return PIFPAF_E_CUDA; }
+    return PIFPAF_OK;
+}
+
+}  // extern "C"
