@@ -143,6 +143,76 @@ int pifpaf_decoder_tap_caf(pifpaf_decoder_t* dec, int32_t b, float* out_fwd, int
 int pifpaf_grow_connection_blend(const float* caf, int64_t n, double x, double y, double s,
                                  double filter_sigmas, int32_t only_max, double* out_xysv);
 
+
+/* ------------------------------------------------------------------------ */
+/* Network forward: backbone + CompositeField4 heads (network/nets.py:35-48,
+ * network/basenetworks.py:186-355, network/heads.py:272-378), as a list of fused
+ * ops over NHWC bf16 activation tensors.  The host mirror of the reference
+ * modules (openpifpaf_b200/network.py) walks a Shell-like module, folds
+ * BatchNorm (eval) into weights+bias and channel_shuffle/chunk into physical
+ * channel placement, and emits these ops once; forward() replays them.
+ * All weights are HOST f32 pointers (copied/converted at emit time).         */
+typedef struct pifpaf_net pifpaf_net_t;
+
+int pifpaf_net_create(pifpaf_net_t** out, int32_t device, int32_t max_batch);
+void pifpaf_net_destroy(pifpaf_net_t* net);
+
+/* Activation tensor NHWC bf16 [max_batch][h][w][c_phys] (zero-initialised;
+ * c_phys % 8 == 0).  *id receives its handle. */
+int pifpaf_net_tensor(pifpaf_net_t* net, int32_t h, int32_t w, int32_t c_phys, int32_t* id);
+
+/* Input block conv (basenetworks.py:275-280; torchvision resnet conv1): dense kxk conv on the
+ * f32 NCHW image [B][3][in_h][in_w] -> bf16 NHWC, + bias (folded BN) (+ReLU). weight [c_out][3][k][k]. */
+int pifpaf_net_input_conv(pifpaf_net_t* net, int32_t in_h, int32_t in_w, int32_t kernel, int32_t stride,
+                          int32_t pad, int32_t c_out, const float* weight, const float* bias,
+                          int32_t relu, int32_t out_tensor);
+
+/* 1x1 conv == GEMM on tensor cores (tcgen05, TMA-fed): reads columns [in_col_off, in_col_off+k_cols)
+ * of in_tensor; weight [n_out][k_cols] in the same physical column order; + bias (+ReLU).
+ * shuffle_src_tensor < 0: plain output at columns [out_col_off, out_col_off+n_out) of out_tensor.
+ * shuffle_src_tensor >= 0: fused cat + channel_shuffle(2) (basenetworks.py:233-242): output logical
+ *   channel 2n <- shuffle_src[n], 2n+1 <- this conv[n]; out_tensor holds the two logical halves each
+ *   padded to a multiple of 8 channels (c_phys == 2*pad8(n_out)). */
+int pifpaf_net_conv1x1(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off, int32_t k_cols,
+                       int32_t n_out, const float* weight, const float* bias, int32_t relu,
+                       int32_t out_tensor, int32_t out_col_off,
+                       int32_t shuffle_src_tensor, int32_t shuffle_src_col_off);
+
+/* Depthwise kxk conv (basenetworks.py:228-231), weight [channels][k][k], + bias (folded BN) (+ReLU). */
+int pifpaf_net_dwconv(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off, int32_t channels,
+                      int32_t kernel, int32_t stride, int32_t pad, const float* weight, const float* bias,
+                      int32_t relu, int32_t out_tensor, int32_t out_col_off);
+
+/* All CompositeField4 heads as ONE GEMM with the eval epilogue fused (heads.py:330-378):
+ * head i has n_fields[i] x n_comp[i] output channels (channel = f*n_comp + comp);
+ * comp_ops (concatenated per head, length sum n_comp): 0 raw, 1 sigmoid, 2 +x index, 3 +y index,
+ * 4 softplus.  weight [sum n_fields*n_comp][k_cols], bias likewise.
+ * Outputs are f32 [B][n_fields][n_comp][h][w] device buffers owned by the net. */
+int pifpaf_net_heads(pifpaf_net_t* net, int32_t in_tensor, int32_t k_cols, int32_t n_heads,
+                     const int32_t* n_fields, const int32_t* n_comp, const int32_t* comp_ops,
+                     const float* weight, const float* bias);
+int pifpaf_net_head_output(pifpaf_net_t* net, int32_t head, float** dev_ptr,
+                           int32_t* n_fields, int32_t* n_comp, int32_t* h, int32_t* w);
+
+/* Shell.forward (network/nets.py:35-48) on images_dev [batch][3][in_h][in_w] f32 (device), async on stream.
+ * gemm_impl: 0 = tcgen05 tensor-core kernels (the product); 1 = plain SIMT debug kernel used only
+ * by tests to cross-check the tensor-core path. */
+int pifpaf_net_forward(pifpaf_net_t* net, const float* images_dev, int32_t batch, int32_t gemm_impl,
+                       void* stream);
+/* Same as pifpaf_net_forward but brackets every op with CUDA events on `stream` and, after a final
+ * synchronise, writes per-op milliseconds to op_ms[num_ops] (profiling leg of bench.py; never the
+ * headline timing).  op_kind[i]: 0 input conv, 1 tcgen05 GEMM, 2 depthwise conv; op_flops/op_bytes are
+ * the algorithmic FLOPs and bytes (inputs + outputs + weights, each once) of op i for this batch. */
+int pifpaf_net_forward_timed(pifpaf_net_t* net, const float* images_dev, int32_t batch, int32_t gemm_impl,
+                             void* stream, float* op_ms, int32_t* op_kind, double* op_flops, double* op_bytes);
+/* Debug/parity tap: copy activation tensor `id` (first `batch` images) to host as f32 [B][h][w][c_phys]. */
+int pifpaf_net_tap_tensor(pifpaf_net_t* net, int32_t id, int32_t batch, float* out, int64_t out_elems);
+/* Debug/parity: fill activation tensor `id` (first `batch` images) from host f32 [B][h][w][c_phys] (rounded to bf16). */
+int pifpaf_net_set_tensor(pifpaf_net_t* net, int32_t id, int32_t batch, const float* data, int64_t n_elems);
+/* Algorithmic FLOPs (2*MAC) of one forward per image, and number of ops emitted. */
+double pifpaf_net_flops_per_image(pifpaf_net_t* net);
+int32_t pifpaf_net_num_ops(pifpaf_net_t* net);
+
 /* Number of kernels this library launched since load (bench.py's gpu_launches). */
 int64_t pifpaf_launch_count(void);
 

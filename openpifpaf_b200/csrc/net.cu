@@ -1,0 +1,1003 @@
+// libpifpaf_b200 -- backbone + heads forward for sm_100a.
+//
+// Replaces the cuDNN/ATen kernels behind the reference's torch.nn modules
+// (paths relative to /root/reference/src/openpifpaf/):
+//   Shell.forward                 network/nets.py:35-48
+//   ShuffleNetV2K/InvertedResidualK   network/basenetworks.py:186-355
+//   CompositeField4 (eval)        network/heads.py:330-378
+//
+// Activations are NHWC bf16 ("rows" = pixels, "columns" = channels).  Every 1x1
+// convolution (97 % of the MACs of shufflenetv2k16) is one GEMM
+//   out[M = B*H*W, N] = act[M, K] * W[N, K]^T,  f32 accumulate
+// executed by k_gemm_tc: a persistent, warp-specialised tcgen05 kernel -- TMA
+// (128B-swizzled tiles) -> shared-memory ring -> tcgen05.mma with the f32
+// accumulator in TMEM (two accumulator stages) -> epilogue warps (tcgen05.ld,
+// bias + ReLU, bf16) that also fuse torch.cat + channel_shuffle(2) (interleaving
+// with the pass-through half) or the CompositeField4 eval epilogue (sigmoid,
+// index-field add, softplus, f32 [B,F,comp,h,w] layout).
+// Depthwise 5x5 and the 3-channel input conv are bandwidth-bound direct kernels.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, f32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------ descriptors
+constexpr int BM = 128;          // UMMA M (cta_group::1): TMEM lane == tile row
+constexpr int BK = 64;           // one 128-byte swizzle atom of bf16 per smem row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;    // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
+constexpr int CHUNK = 16;        // epilogue column chunk (one tcgen05.ld.32x32b.x16)
+constexpr int STAGE_WORDS = CHUNK + 1;   // padded staging row (words)
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start>>4 | LBO(ignored for swizzled K-major)=1 @16 | SBO = 1024 B (8 rows x 128 B) >>4 @32 | version 1 @46 | layout 2 @61
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3fffu);
+    d |= static_cast<uint64_t>(1u) << 16;
+    d |= static_cast<uint64_t>(1024u >> 4) << 32;
+    d |= static_cast<uint64_t>(1u) << 46;
+    d |= static_cast<uint64_t>(2u) << 61;
+    return d;
+}
+// cute::UMMA::InstrDescriptor for kind::f16: c_format F32 (1) @4, a/b format BF16 (1) @7/@10,
+// a/b K-major (0) @15/@16, N>>3 @17, M>>4 @24
+__host__ __device__ inline uint32_t make_instr_desc(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+           (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ GEMM arguments
+enum { MODE_PLAIN = 0, MODE_SHUFFLE = 1, MODE_HEADS = 2 };
+
+struct HeadCol { int head; int plane; int op; int pad; };   // per GEMM output column (heads mode)
+
+struct GemmArgs {
+    int M, N, K;                 // rows, real output channels, k extent (columns of the A view)
+    int block_n, n_blocks, m_blocks, num_k_blocks, stages;
+    int mode, relu;
+    const float* bias;           // [n_blocks * block_n], zero padded
+    // plain / shuffle
+    __nv_bfloat16* out; int ldo; int out_col_off;
+    const __nv_bfloat16* src0; int ld0; int src0_col_off; int half; int gap;
+    // heads
+    const HeadCol* head_cols;    // [n_blocks * block_n]
+    float* head_base[4]; int head_planes[4];
+    int hw, w;                   // pixels per image, field width
+    // debug (SIMT) operand views
+    const __nv_bfloat16* a; int lda; const __nv_bfloat16* wgt; int ldw;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float softplus_f(float x) {   // torch softplus beta=1 threshold=20 (heads.py:378)
+    return x > 20.0f ? x : log1pf(expf(x));
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// Epilogue for one warp: 32 rows (lane == row) x CHUNK columns starting at GEMM column n0.
+// acc[] holds this lane's CHUNK accumulators.  stage: per-warp staging [32][STAGE_WORDS] words.
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, int m0, int n0, const float* acc,
+                                               uint32_t* stage, int lane) {
+    const int m = m0 + lane;
+    if (g.mode == MODE_HEADS) {
+        if (m >= g.M) return;
+        const int b = m / g.hw, pix = m - b * g.hw;
+        const int y = pix / g.w, x = pix - y * g.w;
+#pragma unroll
+        for (int j = 0; j < CHUNK; j++) {
+            const int n = n0 + j;
+            if (n >= g.N) break;
+            const HeadCol hc = g.head_cols[n];
+            float v = acc[j] + g.bias[n];
+            if (hc.op == 1) v = sigmoid_f(v);
+            else if (hc.op == 2) v += (float)x;
+            else if (hc.op == 3) v += (float)y;
+            else if (hc.op == 4) v = softplus_f(v);
+            g.head_base[hc.head][((size_t)b * g.head_planes[hc.head] + hc.plane) * g.hw + pix] = v;
+        }
+        return;
+    }
+    uint32_t* my = stage + lane * STAGE_WORDS;
+    if (g.mode == MODE_PLAIN) {
+#pragma unroll
+        for (int j = 0; j < CHUNK; j += 2) {
+            float a0 = acc[j] + g.bias[n0 + j], a1 = acc[j + 1] + g.bias[n0 + j + 1];
+            if (g.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+            my[j >> 1] = pack_bf16(a0, a1);
+        }
+        __syncwarp();
+        // rows are CHUNK/2 = 8 words: 4 rows per warp store
+        uint32_t* outw = reinterpret_cast<uint32_t*>(g.out);
+        const int word0 = (g.out_col_off + n0) >> 1;
+        const int n_words = (min((g.N + 7) & ~7, n0 + CHUNK) - n0) >> 1;        // up to pad8(N)
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int idx = it * 32 + lane;
+            const int r = idx >> 3, wd = idx & 7;
+            const int mr = m0 + r;
+            if (mr < g.M && wd < n_words && wd < (CHUNK >> 1))
+                outw[(size_t)mr * (g.ldo >> 1) + word0 + wd] = stage[r * STAGE_WORDS + wd];
+        }
+        __syncwarp();
+        return;
+    }
+    // MODE_SHUFFLE: word n = { src0[m][n] (logical channel 2n), conv[m][n] (logical 2n+1) }
+    {
+        uint4 s0 = make_uint4(0, 0, 0, 0), s1 = make_uint4(0, 0, 0, 0);
+        if (m < g.M) {
+            const uint4* sp = reinterpret_cast<const uint4*>(g.src0 + (size_t)m * g.ld0 + g.src0_col_off + n0);
+            s0 = sp[0];
+            s1 = sp[1];
+        }
+        const uint32_t sw[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+        for (int j = 0; j < CHUNK; j++) {
+            float a = acc[j] + g.bias[n0 + j];
+            if (g.relu) a = fmaxf(a, 0.f);
+            const uint32_t src_bits = (j & 1) ? (sw[j >> 1] >> 16) : (sw[j >> 1] & 0xffffu);
+            __nv_bfloat16 hb = __float2bfloat16_rn(a);
+            my[j] = src_bits | (static_cast<uint32_t>(*reinterpret_cast<unsigned short*>(&hb)) << 16);
+        }
+        __syncwarp();
+        uint32_t* outw = reinterpret_cast<uint32_t*>(g.out);
+#pragma unroll
+        for (int it = 0; it < 16; it++) {
+            const int idx = it * 32 + lane;
+            const int r = idx >> 4, wd = idx & 15;
+            const int mr = m0 + r, n = n0 + wd;
+            if (mr < g.M && n < g.N) {
+                const int pw = n + ((2 * n >= g.half) ? (g.gap >> 1) : 0) + (g.out_col_off >> 1);
+                outw[(size_t)mr * (g.ldo >> 1) + pw] = stage[r * STAGE_WORDS + wd];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------ tcgen05 GEMM
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmArgs g) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // carve: [stages][A 16 KB | B block_n*128 B] then barriers, tmem ptr, staging
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int a_bytes = BM * BK * 2;
+    const int b_bytes = g.block_n * BK * 2;
+    const int stage_bytes = a_bytes + b_bytes;
+    unsigned char* tail = smem + (size_t)g.stages * stage_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);            // [stages]
+    uint64_t* empty_bar = full_bar + g.stages;                          // [stages]
+    uint64_t* tmem_full = empty_bar + g.stages;                         // [2]
+    uint64_t* tmem_empty = tmem_full + 2;                               // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint32_t* staging = tmem_ptr + 4;                                   // [4 warps][32][STAGE_WORDS]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tmem_cols = (2 * g.block_n <= 32) ? 32 : (2 * g.block_n <= 64) ? 64 : (2 * g.block_n <= 128) ? 128
+                               : (2 * g.block_n <= 256) ? 256 : 512;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < g.stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+            for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_ptr, tmem_cols);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int num_tiles = g.m_blocks * g.n_blocks;
+
+    if (warp == 0) {
+        // ===== TMA producer (one elected lane) =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / g.n_blocks, n_blk = tile % g.n_blocks;
+                for (int kb = 0; kb < g.num_k_blocks; kb++) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char* sa = smem + (size_t)stage * stage_bytes;
+                    unsigned char* sb = sa + a_bytes;
+                    mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+                    tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+                    tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * g.block_n);
+                    if (++stage == g.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one elected lane) =====
+        if (lane == 0) {
+            const uint32_t idesc = make_instr_desc(BM, g.block_n);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * g.block_n);
+                for (int kb = 0; kb < g.num_k_blocks; kb++) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint32_t sb = sa + a_bytes;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; k++) {
+                        const uint64_t adesc = make_smem_desc(sa + k * UMMA_K * 2);
+                        const uint64_t bdesc = make_smem_desc(sb + k * UMMA_K * 2);
+                        umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);          // frees the smem slot when the MMAs retire
+                    if (++stage == g.stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);                // accumulator ready for the epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue warps: TMEM lane quadrant = warp % 4 =====
+        const int q = warp & 3;
+        uint32_t* stage_w = staging + (warp - 2) * 32 * STAGE_WORDS;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile / g.n_blocks, n_blk = tile % g.n_blocks;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tcgen05_fence_after();
+            const int m0 = m_blk * BM + q * 32;
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (uint32_t)(acc * g.block_n);
+            for (int c = 0; c < g.block_n; c += CHUNK) {
+                uint32_t v[CHUNK];
+                tmem_ld16(t_row + (uint32_t)c, v);
+                float accf[CHUNK];
+#pragma unroll
+                for (int j = 0; j < CHUNK; j++) accf[j] = __uint_as_float(v[j]);
+                const int n0 = n_blk * g.block_n + c;
+                if (n0 < ((g.N + 7) & ~7) || g.mode == MODE_HEADS) epilogue_chunk(g, m0, n0, accf, stage_w, lane);
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------ SIMT debug GEMM (tests only)
+// One warp per 32 rows x CHUNK columns; same epilogue as the tensor-core kernel.
+__global__ void __launch_bounds__(128) k_gemm_simt(GemmArgs g) {
+    __shared__ uint32_t staging[4 * 32 * STAGE_WORDS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_chunks = g.n_blocks * g.block_n / CHUNK;
+    const long long total = (long long)((g.M + 31) / 32) * n_chunks;
+    for (long long job = (long long)blockIdx.x * 4 + warp; job < total; job += (long long)gridDim.x * 4) {
+        const int mb = (int)(job / n_chunks), ch = (int)(job % n_chunks);
+        const int m0 = mb * 32, n0 = ch * CHUNK;
+        const int m = m0 + lane;
+        float acc[CHUNK];
+#pragma unroll
+        for (int j = 0; j < CHUNK; j++) acc[j] = 0.f;
+        if (m < g.M) {
+            for (int k = 0; k < g.K; k++) {
+                const float a = __bfloat162float(g.a[(size_t)m * g.lda + k]);
+#pragma unroll
+                for (int j = 0; j < CHUNK; j++) {
+                    const int n = n0 + j;
+                    const float wv = (n < g.N) ? __bfloat162float(g.wgt[(size_t)n * g.ldw + k]) : 0.f;
+                    acc[j] = fmaf(a, wv, acc[j]);
+                }
+            }
+        }
+        if (n0 < ((g.N + 7) & ~7) || g.mode == MODE_HEADS)
+            epilogue_chunk(g, m0, n0, acc, staging + warp * 32 * STAGE_WORDS, lane);
+    }
+}
+
+// ------------------------------------------------------------------ depthwise kxk conv, NHWC bf16
+// one thread: one output pixel x 8 channels (16-byte vectors); weights [k*k][C8*8] f32, bias [C]
+struct DwArgs {
+    const __nv_bfloat16* in; int ld_in; int in_col_off;
+    __nv_bfloat16* out; int ld_out; int out_col_off;
+    const float* weight; const float* bias;
+    int B, Hin, Win, Hout, Wout, C8, kernel, stride, pad, relu;
+};
+
+__global__ void __launch_bounds__(256) k_dwconv(DwArgs a) {
+    const long long total = (long long)a.B * a.Hout * a.Wout * a.C8;
+    const int C = a.C8 * 8;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(t % a.C8);
+        long long p = t / a.C8;
+        const int ox = (int)(p % a.Wout); p /= a.Wout;
+        const int oy = (int)(p % a.Hout);
+        const int b = (int)(p / a.Hout);
+        float acc[8];
+        const float4 b0 = *reinterpret_cast<const float4*>(a.bias + c8 * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(a.bias + c8 * 8 + 4);
+        acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
+        acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+        for (int ky = 0; ky < a.kernel; ky++) {
+            const int iy = oy * a.stride - a.pad + ky;
+            if (iy < 0 || iy >= a.Hin) continue;
+            for (int kx = 0; kx < a.kernel; kx++) {
+                const int ix = ox * a.stride - a.pad + kx;
+                if (ix < 0 || ix >= a.Win) continue;
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(
+                    a.in + ((size_t)(b * a.Hin + iy) * a.Win + ix) * a.ld_in + a.in_col_off + c8 * 8));
+                const float* wp = a.weight + (size_t)(ky * a.kernel + kx) * C + c8 * 8;
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
+                const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+                const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
+                const float2 f2 = __bfloat1622float2(h[2]), f3 = __bfloat1622float2(h[3]);
+                acc[0] = fmaf(f0.x, w0.x, acc[0]); acc[1] = fmaf(f0.y, w0.y, acc[1]);
+                acc[2] = fmaf(f1.x, w0.z, acc[2]); acc[3] = fmaf(f1.y, w0.w, acc[3]);
+                acc[4] = fmaf(f2.x, w1.x, acc[4]); acc[5] = fmaf(f2.y, w1.y, acc[5]);
+                acc[6] = fmaf(f3.x, w1.z, acc[6]); acc[7] = fmaf(f3.y, w1.w, acc[7]);
+            }
+        }
+        if (a.relu) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[j] = fmaxf(acc[j], 0.f);
+        }
+        uint4 o;
+        o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
+        o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
+        *reinterpret_cast<uint4*>(a.out + ((size_t)(b * a.Hout + oy) * a.Wout + ox) * a.ld_out + a.out_col_off + c8 * 8) = o;
+    }
+}
+
+// ------------------------------------------------------------------ input conv: f32 NCHW [B,3,H,W] -> bf16 NHWC
+struct InConvArgs {
+    const float* in; __nv_bfloat16* out; int ld_out;
+    const float* weight;   // [3*k*k][C8*8] (tap-major)
+    const float* bias;     // [C8*8]
+    int B, Hin, Win, Hout, Wout, C8, kernel, stride, pad, relu;
+};
+
+__global__ void __launch_bounds__(256) k_input_conv(InConvArgs a) {
+    extern __shared__ float s_w[];      // weights + bias
+    const int C = a.C8 * 8;
+    const int n_w = 3 * a.kernel * a.kernel * C;
+    for (int i = threadIdx.x; i < n_w; i += blockDim.x) s_w[i] = a.weight[i];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) s_w[n_w + i] = a.bias[i];
+    __syncthreads();
+    const long long total = (long long)a.B * a.Hout * a.Wout * a.C8;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(t % a.C8);
+        long long p = t / a.C8;
+        const int ox = (int)(p % a.Wout); p /= a.Wout;
+        const int oy = (int)(p % a.Hout);
+        const int b = (int)(p / a.Hout);
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = s_w[n_w + c8 * 8 + j];
+        for (int ci = 0; ci < 3; ci++) {
+            const float* plane = a.in + ((size_t)b * 3 + ci) * a.Hin * a.Win;
+            for (int ky = 0; ky < a.kernel; ky++) {
+                const int iy = oy * a.stride - a.pad + ky;
+                if (iy < 0 || iy >= a.Hin) continue;
+                for (int kx = 0; kx < a.kernel; kx++) {
+                    const int ix = ox * a.stride - a.pad + kx;
+                    if (ix < 0 || ix >= a.Win) continue;
+                    const float v = __ldg(plane + (size_t)iy * a.Win + ix);
+                    const float* wp = s_w + (size_t)((ci * a.kernel + ky) * a.kernel + kx) * C + c8 * 8;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) acc[j] = fmaf(v, wp[j], acc[j]);
+                }
+            }
+        }
+        if (a.relu) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[j] = fmaxf(acc[j], 0.f);
+        }
+        uint4 o;
+        o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
+        o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
+        *reinterpret_cast<uint4*>(a.out + ((size_t)(b * a.Hout + oy) * a.Wout + ox) * a.ld_out + c8 * 8) = o;
+    }
+}
+
+__global__ void k_f32_to_bf16(const float* in, __nv_bfloat16* out, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = __float2bfloat16_rn(in[i]);
+}
+
+__global__ void k_bf16_to_f32(const __nv_bfloat16* in, float* out, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = __bfloat162float(in[i]);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+// 2-D bf16 row-major view [rows][cols] with row pitch ld (elements); box = [box_rows][64 cols], 128B swizzle
+int make_tmap(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (!fn) { pifpaf::set_error("cuTensorMapEncodeTiled entry point not available"); return PIFPAF_E_CUDA; }
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {ld * 2};
+    const cuuint32_t box[2] = {BK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        pifpaf::set_error("cuTensorMapEncodeTiled failed (%d): rows=%llu cols=%llu ld=%llu box_rows=%u base=%p",
+                          (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld,
+                          box_rows, base);
+        return PIFPAF_E_CUDA;
+    }
+    return PIFPAF_OK;
+}
+
+struct Tensor { int h, w, c; __nv_bfloat16* data; };
+
+enum OpKind { OP_INPUT_CONV, OP_GEMM, OP_DW };
+
+struct Op {
+    OpKind kind;
+    // gemm
+    GemmArgs g{};
+    CUtensorMap tmap_a{}, tmap_b{};
+    int a_tensor = -1; int rows_per_image = 0;
+    size_t smem = 0;
+    // dw
+    DwArgs dw{};
+    // input conv
+    InConvArgs ic{};
+    int n_out_pixels = 0;
+    double flops_per_image = 0;
+    double bytes_per_image = 0;      // algorithmic activation bytes (inputs once + outputs once)
+    double weight_bytes = 0;
+};
+
+}  // namespace
+
+struct pifpaf_net {
+    int device = 0, max_batch = 0, n_sm = 148;
+    std::vector<Tensor> tensors;
+    std::vector<Op> ops;
+    std::vector<void*> owned;            // device allocations (weights, biases, tables)
+    // heads
+    int n_heads = 0;
+    float* head_out[4] = {nullptr, nullptr, nullptr, nullptr};
+    int head_fields[4] = {0, 0, 0, 0}, head_comp[4] = {0, 0, 0, 0}, head_h = 0, head_w = 0;
+    int in_h = 0, in_w = 0;
+};
+
+namespace {
+
+template <typename T>
+int net_alloc(pifpaf_net* net, T** p, size_t n, bool zero) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), sizeof(T) * (n ? n : 1));
+    if (e != cudaSuccess) {
+        pifpaf::set_error("cudaMalloc of %zu bytes failed: %s", sizeof(T) * n, cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? PIFPAF_E_NOMEM : PIFPAF_E_CUDA;
+    }
+    net->owned.push_back(*p);
+    if (zero) {
+        e = cudaMemset(*p, 0, sizeof(T) * (n ? n : 1));
+        if (e != cudaSuccess) { pifpaf::set_error("cudaMemset failed: %s", cudaGetErrorString(e)); return PIFPAF_E_CUDA; }
+    }
+    return PIFPAF_OK;
+}
+
+template <typename T>
+int net_upload(pifpaf_net* net, T** p, const std::vector<T>& host) {
+    int rc = net_alloc(net, p, host.size(), false);
+    if (rc != PIFPAF_OK) return rc;
+    cudaError_t e = cudaMemcpy(*p, host.data(), sizeof(T) * host.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { pifpaf::set_error("cudaMemcpy failed: %s", cudaGetErrorString(e)); return PIFPAF_E_CUDA; }
+    return PIFPAF_OK;
+}
+
+inline int pad8(int v) { return (v + 7) & ~7; }
+inline int pad16(int v) { return (v + 15) & ~15; }
+
+// choose the UMMA N tile (<= 256, multiple of 16): the LARGEST tile whose padded work is within
+// 4 % of the minimum over all tilings
+void choose_block_n(int n_out, int* block_n, int* n_blocks) {
+    const int np = pad16(n_out);
+    long min_cost = -1;
+    for (int nb = 1; nb <= np / 16; nb++) {
+        const int bn = pad16((np + nb - 1) / nb);
+        if (bn > 256) continue;
+        const long cost = (long)bn * nb;
+        if (min_cost < 0 || cost < min_cost) min_cost = cost;
+    }
+    for (int nb = 1; nb <= np / 16; nb++) {
+        const int bn = pad16((np + nb - 1) / nb);
+        if (bn > 256) continue;
+        if ((long)bn * nb * 100 <= min_cost * 104) { *block_n = bn; *n_blocks = nb; return; }
+    }
+    *block_n = 16; *n_blocks = np / 16;
+}
+
+size_t gemm_smem_bytes(int block_n, int stages) {
+    return 1024 + (size_t)stages * (BM * BK * 2 + block_n * BK * 2) + (2 * stages + 4) * 8 + 16 +
+           4 * 32 * STAGE_WORDS * 4;
+}
+
+int choose_stages(int block_n, int num_k_blocks) {
+    const size_t budget = 200 * 1024;
+    int stages = 8;
+    while (stages > 2 && gemm_smem_bytes(block_n, stages) > budget) stages--;
+    (void)num_k_blocks;
+    return stages;
+}
+
+// common GEMM emit: weights [n_out][k_cols] f32 host -> bf16 [n_pad][k_pad8] device, bias padded
+int emit_gemm(pifpaf_net* net, Op& op, int in_tensor, int in_col_off, int k_cols, int n_out,
+              const float* weight, const float* bias) {
+    const Tensor& tin = net->tensors[in_tensor];
+    PIFPAF_CHECK_ARG(in_col_off % 8 == 0 && in_col_off >= 0 && in_col_off + k_cols <= tin.c,
+                     "conv1x1 input column window must be 16-byte aligned and inside the tensor");
+    int block_n, n_blocks;
+    choose_block_n(n_out, &block_n, &n_blocks);
+    const int n_pad = block_n * n_blocks;
+    const int k_pad = pad8(k_cols);
+    std::vector<__nv_bfloat16> w((size_t)n_pad * k_pad, __float2bfloat16(0.f));
+    for (int n = 0; n < n_out; n++)
+        for (int k = 0; k < k_cols; k++) w[(size_t)n * k_pad + k] = __float2bfloat16(weight[(size_t)n * k_cols + k]);
+    std::vector<float> b(n_pad, 0.f);
+    for (int n = 0; n < n_out; n++) b[n] = bias ? bias[n] : 0.f;
+    __nv_bfloat16* d_w = nullptr; float* d_b = nullptr;
+    int rc = net_upload(net, &d_w, w); if (rc != PIFPAF_OK) return rc;
+    rc = net_upload(net, &d_b, b); if (rc != PIFPAF_OK) return rc;
+
+    GemmArgs& g = op.g;
+    const size_t rows_max = (size_t)net->max_batch * tin.h * tin.w;
+    g.N = n_out; g.K = k_cols;
+    g.block_n = block_n; g.n_blocks = n_blocks;
+    g.num_k_blocks = (k_cols + BK - 1) / BK;
+    g.stages = choose_stages(block_n, g.num_k_blocks);
+    g.bias = d_b;
+    g.a = tin.data + in_col_off; g.lda = tin.c; g.wgt = d_w; g.ldw = k_pad;
+    op.a_tensor = in_tensor; op.rows_per_image = tin.h * tin.w;
+    op.smem = gemm_smem_bytes(block_n, g.stages);
+    op.flops_per_image = 2.0 * (double)op.rows_per_image * n_out * k_cols;
+    op.bytes_per_image = (double)op.rows_per_image * k_cols * 2.0;      // A read once (bf16); outputs added by the caller
+    op.weight_bytes = (double)n_out * k_cols * 2.0;
+    rc = make_tmap(&op.tmap_a, tin.data + in_col_off, rows_max, (uint64_t)k_cols, (uint64_t)tin.c, BM);
+    if (rc != PIFPAF_OK) return rc;
+    rc = make_tmap(&op.tmap_b, d_w, (uint64_t)n_pad, (uint64_t)k_pad, (uint64_t)k_pad, (uint32_t)block_n);
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pifpaf_net_create(pifpaf_net_t** out, int32_t device, int32_t max_batch) {
+    PIFPAF_CHECK_ARG(out != nullptr, "out is null");
+    *out = nullptr;
+    PIFPAF_CHECK_ARG(max_batch >= 1, "max_batch must be >= 1");
+    int n_dev = 0;
+    PIFPAF_CUDA_TRY(cudaGetDeviceCount(&n_dev));
+    PIFPAF_CHECK_ARG(device >= 0 && device < n_dev, "no such CUDA device");
+    PIFPAF_CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PIFPAF_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        pifpaf::set_error("libpifpaf_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+        return PIFPAF_E_CUDA;
+    }
+    pifpaf_net* net = new pifpaf_net();
+    net->device = device; net->max_batch = max_batch; net->n_sm = prop.multiProcessorCount;
+    PIFPAF_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    *out = net;
+    return PIFPAF_OK;
+}
+
+void pifpaf_net_destroy(pifpaf_net_t* net) {
+    if (!net) return;
+    cudaSetDevice(net->device);
+    for (void* p : net->owned) cudaFree(p);
+    delete net;
+}
+
+int pifpaf_net_tensor(pifpaf_net_t* net, int32_t h, int32_t w, int32_t c_phys, int32_t* id) {
+    PIFPAF_CHECK_ARG(net != nullptr && id != nullptr, "null argument");
+    PIFPAF_CHECK_ARG(h >= 1 && w >= 1 && c_phys >= 8 && c_phys % 8 == 0, "tensor shape: c_phys must be a multiple of 8");
+    PIFPAF_CUDA_TRY(cudaSetDevice(net->device));
+    Tensor t; t.h = h; t.w = w; t.c = c_phys; t.data = nullptr;
+    // + one tile of slack rows so that TMA boxes of the last partial M tile stay in mapped memory
+    int rc = net_alloc(net, &t.data, ((size_t)net->max_batch * h * w + BM) * c_phys, true);
+    if (rc != PIFPAF_OK) return rc;
+    net->tensors.push_back(t);
+    *id = (int)net->tensors.size() - 1;
+    return PIFPAF_OK;
+}
+
+int pifpaf_net_input_conv(pifpaf_net_t* net, int32_t in_h, int32_t in_w, int32_t kernel, int32_t stride,
+                          int32_t pad, int32_t c_out, const float* weight, const float* bias,
+                          int32_t relu, int32_t out_tensor) {
+    PIFPAF_CHECK_ARG(net != nullptr && weight != nullptr, "null argument");
+    PIFPAF_CHECK_ARG(out_tensor >= 0 && out_tensor < (int)net->tensors.size(), "bad tensor id");
+    const Tensor& to = net->tensors[out_tensor];
+    const int ho = (in_h + 2 * pad - kernel) / stride + 1, wo = (in_w + 2 * pad - kernel) / stride + 1;
+    PIFPAF_CHECK_ARG(to.h == ho && to.w == wo && to.c >= pad8(c_out), "output tensor shape mismatch");
+    PIFPAF_CUDA_TRY(cudaSetDevice(net->device));
+    const int C = pad8(c_out);
+    std::vector<float> w((size_t)3 * kernel * kernel * C, 0.f), b(C, 0.f);
+    for (int co = 0; co < c_out; co++) {
+        for (int ci = 0; ci < 3; ci++)
+            for (int ky = 0; ky < kernel; ky++)
+                for (int kx = 0; kx < kernel; kx++)
+                    w[(size_t)((ci * kernel + ky) * kernel + kx) * C + co] =
+                        weight[(((size_t)co * 3 + ci) * kernel + ky) * kernel + kx];
+        b[co] = bias ? bias[co] : 0.f;
+    }
+    Op op; op.kind = OP_INPUT_CONV;
+    float *d_w = nullptr, *d_b = nullptr;
+    int rc = net_upload(net, &d_w, w); if (rc != PIFPAF_OK) return rc;
+    rc = net_upload(net, &d_b, b); if (rc != PIFPAF_OK) return rc;
+    InConvArgs& a = op.ic;
+    a.in = nullptr; a.out = to.data; a.ld_out = to.c; a.weight = d_w; a.bias = d_b;
+    a.Hin = in_h; a.Win = in_w; a.Hout = ho; a.Wout = wo; a.C8 = C / 8;
+    a.kernel = kernel; a.stride = stride; a.pad = pad; a.relu = relu;
+    op.flops_per_image = 2.0 * ho * wo * c_out * 3.0 * kernel * kernel;
+    op.bytes_per_image = (double)in_h * in_w * 3 * 4.0 + (double)ho * wo * c_out * 2.0;
+    net->in_h = in_h; net->in_w = in_w;
+    net->ops.push_back(op);
+    return PIFPAF_OK;
+}
+
+int pifpaf_net_conv1x1(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off, int32_t k_cols,
+                       int32_t n_out, const float* weight, const float* bias, int32_t relu,
+                       int32_t out_tensor, int32_t out_col_off,
+                       int32_t shuffle_src_tensor, int32_t shuffle_src_col_off) {
+    PIFPAF_CHECK_ARG(net != nullptr && weight != nullptr, "null argument");
+    const int nt = (int)net->tensors.size();
+    PIFPAF_CHECK_ARG(in_tensor >= 0 && in_tensor < nt && out_tensor >= 0 && out_tensor < nt, "bad tensor id");
+    PIFPAF_CHECK_ARG(k_cols >= 1 && n_out >= 1, "bad conv size");
+    PIFPAF_CUDA_TRY(cudaSetDevice(net->device));
+    const Tensor& tin = net->tensors[in_tensor];
+    const Tensor& to = net->tensors[out_tensor];
+    PIFPAF_CHECK_ARG(tin.h == to.h && tin.w == to.w, "conv1x1 keeps the spatial shape");
+    Op op; op.kind = OP_GEMM;
+    int rc = emit_gemm(net, op, in_tensor, in_col_off, k_cols, n_out, weight, bias);
+    if (rc != PIFPAF_OK) return rc;
+    GemmArgs& g = op.g;
+    g.relu = relu; g.out = to.data; g.ldo = to.c; g.out_col_off = out_col_off;
+    // outputs: n_out bf16 per row; the fused shuffle also reads and re-writes the pass-through half
+    op.bytes_per_image += (double)op.rows_per_image * n_out * 2.0 * (shuffle_src_tensor >= 0 ? 3.0 : 1.0);
+    PIFPAF_CHECK_ARG(out_col_off % 8 == 0, "output column offset must be a multiple of 8");
+    if (shuffle_src_tensor < 0) {
+        g.mode = MODE_PLAIN;
+        PIFPAF_CHECK_ARG(out_col_off + pad8(n_out) <= to.c, "output window outside the tensor");
+    } else {
+        PIFPAF_CHECK_ARG(shuffle_src_tensor < nt, "bad shuffle source tensor");
+        const Tensor& ts = net->tensors[shuffle_src_tensor];
+        PIFPAF_CHECK_ARG(ts.h == to.h && ts.w == to.w, "shuffle source shape mismatch");
+        PIFPAF_CHECK_ARG(n_out % 2 == 0, "fused channel_shuffle needs an even branch width");
+        PIFPAF_CHECK_ARG(shuffle_src_col_off % 8 == 0 && shuffle_src_col_off + pad16(n_out) <= ts.c + 8,
+                         "shuffle source window");
+        PIFPAF_CHECK_ARG(out_col_off == 0 && to.c == 2 * pad8(n_out), "shuffle output tensor must be 2*pad8(n_out) wide");
+        g.mode = MODE_SHUFFLE;
+        g.src0 = ts.data; g.ld0 = ts.c; g.src0_col_off = shuffle_src_col_off;
+        g.half = n_out; g.gap = pad8(n_out) - n_out;
+    }
+    net->ops.push_back(op);
+    return PIFPAF_OK;
+}
+
+int pifpaf_net_dwconv(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off, int32_t channels,
+                      int32_t kernel, int32_t stride, int32_t pad, const float* weight, const float* bias,
+                      int32_t relu, int32_t out_tensor, int32_t out_col_off) {
+    PIFPAF_CHECK_ARG(net != nullptr && weight != nullptr, "null argument");
+    const int nt = (int)net->tensors.size();
+    PIFPAF_CHECK_ARG(in_tensor >= 0 && in_tensor < nt && out_tensor >= 0 && out_tensor < nt, "bad tensor id");
+    const Tensor& tin = net->tensors[in_tensor];
+    const Tensor& to = net->tensors[out_tensor];
+    const int ho = (tin.h + 2 * pad - kernel) / stride + 1, wo = (tin.w + 2 * pad - kernel) / stride + 1;
+    const int C = pad8(channels);
+    PIFPAF_CHECK_ARG(to.h == ho && to.w == wo, "dwconv output tensor shape mismatch");
+    PIFPAF_CHECK_ARG(in_col_off % 8 == 0 && out_col_off % 8 == 0 && in_col_off + C <= tin.c && out_col_off + C <= to.c,
+                     "dwconv column windows");
+    PIFPAF_CUDA_TRY(cudaSetDevice(net->device));
+    std::vector<float> w((size_t)kernel * kernel * C, 0.f), b(C, 0.f);
+    for (int c = 0; c < channels; c++) {
+        for (int t = 0; t < kernel * kernel; t++) w[(size_t)t * C + c] = weight[(size_t)c * kernel * kernel + t];
+        b[c] = bias ? bias[c] : 0.f;
+    }
+    Op op; op.kind = OP_DW;
+    float *d_w = nullptr, *d_b = nullptr;
+    int rc = net_upload(net, &d_w, w); if (rc != PIFPAF_OK) return rc;
+    rc = net_upload(net, &d_b, b); if (rc != PIFPAF_OK) return rc;
+    DwArgs& a = op.dw;
+    a.in = tin.data; a.ld_in = tin.c; a.in_col_off = in_col_off;
+    a.out = to.data; a.ld_out = to.c; a.out_col_off = out_col_off;
+    a.weight = d_w; a.bias = d_b;
+    a.Hin = tin.h; a.Win = tin.w; a.Hout = ho; a.Wout = wo; a.C8 = C / 8;
+    a.kernel = kernel; a.stride = stride; a.pad = pad; a.relu = relu;
+    op.flops_per_image = 2.0 * ho * wo * channels * (double)kernel * kernel;
+    op.bytes_per_image = ((double)tin.h * tin.w + (double)ho * wo) * channels * 2.0;
+    net->ops.push_back(op);
+    return PIFPAF_OK;
+}
+
+int pifpaf_net_heads(pifpaf_net_t* net, int32_t in_tensor, int32_t k_cols, int32_t n_heads,
+                     const int32_t* n_fields, const int32_t* n_comp, const int32_t* comp_ops,
+                     const float* weight, const float* bias) {
+    PIFPAF_CHECK_ARG(net != nullptr && weight != nullptr && n_fields && n_comp && comp_ops, "null argument");
+    PIFPAF_CHECK_ARG(n_heads >= 1 && n_heads <= 4, "1..4 heads supported");
+    PIFPAF_CHECK_ARG(in_tensor >= 0 && in_tensor < (int)net->tensors.size(), "bad tensor id");
+    PIFPAF_CUDA_TRY(cudaSetDevice(net->device));
+    const Tensor& tin = net->tensors[in_tensor];
+    int n_total = 0;
+    for (int i = 0; i < n_heads; i++) n_total += n_fields[i] * n_comp[i];
+    Op op; op.kind = OP_GEMM;
+    int rc = emit_gemm(net, op, in_tensor, 0, k_cols, n_total, weight, bias);
+    if (rc != PIFPAF_OK) return rc;
+    GemmArgs& g = op.g;
+    g.mode = MODE_HEADS; g.relu = 0;
+    op.bytes_per_image += (double)op.rows_per_image * n_total * 4.0;
+    std::vector<HeadCol> cols((size_t)g.block_n * g.n_blocks, HeadCol{0, 0, 0, 0});
+    int col = 0, op_off = 0;
+    for (int i = 0; i < n_heads; i++) {
+        for (int f = 0; f < n_fields[i]; f++)
+            for (int c = 0; c < n_comp[i]; c++) cols[col++] = HeadCol{i, f * n_comp[i] + c, comp_ops[op_off + c], 0};
+        op_off += n_comp[i];
+        net->head_fields[i] = n_fields[i]; net->head_comp[i] = n_comp[i];
+        rc = net_alloc(net, &net->head_out[i], (size_t)net->max_batch * n_fields[i] * n_comp[i] * tin.h * tin.w, true);
+        if (rc != PIFPAF_OK) return rc;
+        g.head_base[i] = net->head_out[i];
+        g.head_planes[i] = n_fields[i] * n_comp[i];
+    }
+    HeadCol* d_cols = nullptr;
+    rc = net_upload(net, &d_cols, cols); if (rc != PIFPAF_OK) return rc;
+    g.head_cols = d_cols;
+    g.hw = tin.h * tin.w; g.w = tin.w;
+    net->n_heads = n_heads; net->head_h = tin.h; net->head_w = tin.w;
+    net->ops.push_back(op);
+    return PIFPAF_OK;
+}
+
+int pifpaf_net_head_output(pifpaf_net_t* net, int32_t head, float** dev_ptr,
+                           int32_t* n_fields, int32_t* n_comp, int32_t* h, int32_t* w) {
+    PIFPAF_CHECK_ARG(net != nullptr && head >= 0 && head < net->n_heads, "bad head index");
+    if (dev_ptr) *dev_ptr = net->head_out[head];
+    if (n_fields) *n_fields = net->head_fields[head];
+    if (n_comp) *n_comp = net->head_comp[head];
+    if (h) *h = net->head_h;
+    if (w) *w = net->head_w;
+    return PIFPAF_OK;
+}
+
+static int net_forward_impl(pifpaf_net_t* net, const float* images_dev, int32_t batch, int32_t gemm_impl,
+                            cudaStream_t st, cudaEvent_t* events) {
+    PIFPAF_CHECK_ARG(net != nullptr, "null argument");
+    PIFPAF_CHECK_ARG(images_dev != nullptr || net->in_h == 0, "images pointer is null");
+    PIFPAF_CHECK_ARG(batch >= 1 && batch <= net->max_batch, "batch exceeds max_batch");
+    PIFPAF_CUDA_TRY(cudaSetDevice(net->device));
+    int op_index = 0;
+    for (Op& op : net->ops) {
+        if (events) PIFPAF_CUDA_TRY(cudaEventRecord(events[op_index], st));
+        op_index++;
+        if (op.kind == OP_INPUT_CONV) {
+            InConvArgs a = op.ic;
+            a.in = images_dev; a.B = batch;
+            const long long total = (long long)batch * a.Hout * a.Wout * a.C8;
+            const int grid = (int)std::min<long long>((total + 255) / 256, (long long)net->n_sm * 16);
+            const size_t smem = sizeof(float) * ((size_t)3 * a.kernel * a.kernel * a.C8 * 8 + a.C8 * 8);
+            k_input_conv<<<grid, 256, smem, st>>>(a);
+            PIFPAF_LAUNCH_CHECK();
+        } else if (op.kind == OP_DW) {
+            DwArgs a = op.dw;
+            a.B = batch;
+            const long long total = (long long)batch * a.Hout * a.Wout * a.C8;
+            const int grid = (int)std::min<long long>((total + 255) / 256, (long long)net->n_sm * 32);
+            k_dwconv<<<grid, 256, 0, st>>>(a);
+            PIFPAF_LAUNCH_CHECK();
+        } else {
+            GemmArgs g = op.g;
+            g.M = batch * op.rows_per_image;
+            g.m_blocks = (g.M + BM - 1) / BM;
+            if (gemm_impl == 1) {
+                const long long jobs = (long long)((g.M + 31) / 32) * (g.n_blocks * g.block_n / CHUNK);
+                const int grid = (int)std::min<long long>((jobs + 3) / 4, (long long)net->n_sm * 16);
+                k_gemm_simt<<<grid, 128, 0, st>>>(g);
+            } else {
+                const int tiles = g.m_blocks * g.n_blocks;
+                const int grid = std::min(tiles, net->n_sm);
+                k_gemm_tc<<<grid, GEMM_THREADS, op.smem, st>>>(op.tmap_a, op.tmap_b, g);
+            }
+            PIFPAF_LAUNCH_CHECK();
+        }
+    }
+    if (events) PIFPAF_CUDA_TRY(cudaEventRecord(events[op_index], st));
+    return PIFPAF_OK;
+}
+
+int pifpaf_net_forward(pifpaf_net_t* net, const float* images_dev, int32_t batch, int32_t gemm_impl,
+                       void* stream_v) {
+    return net_forward_impl(net, images_dev, batch, gemm_impl, reinterpret_cast<cudaStream_t>(stream_v), nullptr);
+}
+
+int pifpaf_net_forward_timed(pifpaf_net_t* net, const float* images_dev, int32_t batch, int32_t gemm_impl,
+                             void* stream_v, float* op_ms, int32_t* op_kind, double* op_flops, double* op_bytes) {
+    PIFPAF_CHECK_ARG(net != nullptr && op_ms != nullptr, "null argument");
+    PIFPAF_CUDA_TRY(cudaSetDevice(net->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
+    const size_t n = net->ops.size();
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) PIFPAF_CUDA_TRY(cudaEventCreate(&e));
+    int rc = net_forward_impl(net, images_dev, batch, gemm_impl, st, ev.data());
+    if (rc == PIFPAF_OK) {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { pifpaf::set_error("forward failed: %s", cudaGetErrorString(e)); rc = PIFPAF_E_CUDA; }
+    }
+    for (size_t i = 0; i < n && rc == PIFPAF_OK; i++) {
+        cudaEventElapsedTime(&op_ms[i], ev[i], ev[i + 1]);
+        const Op& op = net->ops[i];
+        if (op_kind) op_kind[i] = op.kind == OP_INPUT_CONV ? 0 : (op.kind == OP_GEMM ? 1 : 2);
+        if (op_flops) op_flops[i] = op.flops_per_image * batch;
+        if (op_bytes) op_bytes[i] = op.bytes_per_image * batch + op.weight_bytes;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return rc;
+}
+
+int pifpaf_net_tap_tensor(pifpaf_net_t* net, int32_t id, int32_t batch, float* out, int64_t out_elems) {
+    PIFPAF_CHECK_ARG(net != nullptr && id >= 0 && id < (int)net->tensors.size(), "bad tensor id");
+    const Tensor& t = net->tensors[id];
+    const long long n = (long long)batch * t.h * t.w * t.c;
+    PIFPAF_CHECK_ARG(out != nullptr && out_elems >= n && batch <= net->max_batch, "output buffer too small");
+    PIFPAF_CUDA_TRY(cudaSetDevice(net->device));
+    float* d_tmp = nullptr;
+    PIFPAF_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_tmp), sizeof(float) * n));
+    k_bf16_to_f32<<<1024, 256>>>(t.data, d_tmp, n);
+    pifpaf::count_launch();
+    cudaError_t e = cudaMemcpy(out, d_tmp, sizeof(float) * n, cudaMemcpyDeviceToHost);
+    cudaFree(d_tmp);
+    if (e != cudaSuccess) { pifpaf::set_error("tap copy failed: %s", cudaGetErrorString(e)); return PIFPAF_E_CUDA; }
+    return PIFPAF_OK;
+}
+
+int pifpaf_net_set_tensor(pifpaf_net_t* net, int32_t id, int32_t batch, const float* data, int64_t n_elems) {
+    PIFPAF_CHECK_ARG(net != nullptr && id >= 0 && id < (int)net->tensors.size(), "bad tensor id");
+    const Tensor& t = net->tensors[id];
+    const long long n = (long long)batch * t.h * t.w * t.c;
+    PIFPAF_CHECK_ARG(data != nullptr && n_elems == n && batch <= net->max_batch, "input size mismatch");
+    PIFPAF_CUDA_TRY(cudaSetDevice(net->device));
+    float* d_tmp = nullptr;
+    PIFPAF_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_tmp), sizeof(float) * n));
+    cudaError_t e = cudaMemcpy(d_tmp, data, sizeof(float) * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_f32_to_bf16<<<1024, 256>>>(d_tmp, t.data, n);
+        pifpaf::count_launch();
+        e = cudaDeviceSynchronize();
+    }
+    cudaFree(d_tmp);
+    if (e != cudaSuccess) { pifpaf::set_error("set_tensor failed: %s", cudaGetErrorString(e)); return PIFPAF_E_CUDA; }
+    return PIFPAF_OK;
+}
+
+double pifpaf_net_flops_per_image(pifpaf_net_t* net) {
+    if (!net) return 0.0;
+    double f = 0.0;
+    for (const Op& op : net->ops) f += op.flops_per_image;
+    return f;
+}
+
+int32_t pifpaf_net_num_ops(pifpaf_net_t* net) { return net ? (int32_t)net->ops.size() : 0; }
+
+}  // extern "C"

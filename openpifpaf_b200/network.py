@@ -1,0 +1,376 @@
+"""Host-side mirror of the reference network modules for the inference hot path.
+
+Reference (paths relative to /root/reference/src/openpifpaf/):
+  Shell.forward                       network/nets.py:35-48
+  ShuffleNetV2K / InvertedResidualK   network/basenetworks.py:186-355
+  CompositeField4 (eval)              network/heads.py:330-378
+
+`plan_from_shell(shell)` walks a reference-style ``Shell`` (duck-typed: the
+reference's own ``openpifpaf.network.nets.Shell`` or any module tree with the
+same attribute names), folds every eval-mode BatchNorm into its convolution and
+returns a plain "plan" of float32 numpy arrays.  `CompiledNet` turns a plan into
+a fused op list of libpifpaf_b200 (tcgen05 GEMMs for the 1x1 convolutions) and
+replays it.  torch.cat / chunk / channel_shuffle never run as kernels: they are
+folded into the physical channel placement computed here:
+
+  an activation with 2*half logical channels is stored as
+      [ half channels | gap | half channels | gap ],  gap = pad8(half) - half
+  so both halves start on 16-byte boundaries (TMA requirement); the last GEMM of
+  a block writes logical channel 2n <- pass-through[n], 2n+1 <- conv[n]
+  (== cat + channel_shuffle(groups=2), basenetworks.py:233-242) straight into
+  that layout, and the next block's chunk(2) is a column offset.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+OP_RAW, OP_SIGMOID, OP_ADD_X, OP_ADD_Y, OP_SOFTPLUS = 0, 1, 2, 3, 4
+
+SHUFFLENETV2K_CONFIGS = {     # network/factory.py:68-79
+    'shufflenetv2k16': ([4, 8, 4], [24, 348, 696, 1392, 1392]),
+    'shufflenetv2k20': ([5, 10, 5], [32, 512, 1024, 2048, 2048]),
+    'shufflenetv2k30': ([8, 16, 6], [32, 512, 1024, 2048, 2048]),
+}
+
+
+def pad8(v):
+    return (v + 7) // 8 * 8
+
+
+# ----------------------------------------------------------------------------- plans
+
+def _fold(conv, bn):
+    """conv (bias-free) followed by eval BatchNorm -> (weight, bias) float32 numpy."""
+    w = conv.weight.detach().double()
+    scale = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+    b = bn.bias.detach().double() - bn.running_mean.detach().double() * scale
+    if conv.bias is not None:
+        b = b + conv.bias.detach().double() * scale
+    w = w * scale.view(-1, 1, 1, 1)
+    return w.float().cpu().numpy(), b.float().cpu().numpy()
+
+
+def head_ops(n_confidences, n_vectors, n_scales, vector_offsets):
+    """Per-component epilogue of CompositeField4.forward in eval mode (heads.py:360-378)."""
+    ops = [OP_RAW] + [OP_SIGMOID] * n_confidences
+    for i in range(n_vectors):
+        ops += [OP_ADD_X, OP_ADD_Y] if vector_offsets[i] else [OP_RAW, OP_RAW]
+    ops += [OP_SOFTPLUS] * n_scales
+    return ops
+
+
+def plan_from_shell(shell):
+    """Extract a folded plan from a reference-style Shell with a ShuffleNetV2K base net."""
+    base = shell.base_net
+    if not all(hasattr(base, a) for a in ('input_block', 'stage2', 'stage3', 'stage4', 'conv5')):
+        raise RuntimeError(f'unsupported base network {type(base).__name__}: expected a ShuffleNetV2K')
+    if shell.training:
+        raise RuntimeError('the Shell must be in eval() mode (BatchNorm is folded)')
+    if len(base.input_block) != 1:
+        raise RuntimeError('input_conv2 variants are not supported')
+    conv, bn = base.input_block[0][0], base.input_block[0][1]
+    w, b = _fold(conv, bn)
+    plan = {'kind': 'shufflenetv2k',
+            'input': {'w': w, 'b': b, 'stride': int(conv.stride[0]), 'pad': int(conv.padding[0])},
+            'stages': [], 'heads': []}
+    for stage in (base.stage2, base.stage3, base.stage4):
+        blocks = []
+        for blk in stage:
+            b2 = blk.branch2
+            dw = b2[3]
+            if dw.dilation[0] != 1:
+                raise RuntimeError('dilated stages are not supported')
+            entry = {'first': blk.branch1 is not None, 'stride': int(dw.stride[0]),
+                     'kernel': int(dw.kernel_size[0]), 'pad': int(dw.padding[0])}
+            entry['b2_pw1'] = _fold(b2[0], b2[1])
+            entry['b2_dw'] = _fold(b2[3], b2[4])
+            entry['b2_pw2'] = _fold(b2[5], b2[6])
+            if blk.branch1 is not None:
+                entry['b1_dw'] = _fold(blk.branch1[0], blk.branch1[1])
+                entry['b1_pw'] = _fold(blk.branch1[2], blk.branch1[3])
+            blocks.append(entry)
+        plan['stages'].append(blocks)
+    if not isinstance(base.conv5[0], torch.nn.Conv2d):
+        raise RuntimeError('conv5_as_stage is not supported')
+    plan['conv5'] = _fold(base.conv5[0], base.conv5[1])
+    for hn in shell.head_nets:
+        m = hn.meta
+        if getattr(m, 'upsample_stride', 1) != 1:
+            raise RuntimeError('upsample_stride > 1 heads are not supported')
+        ncomp = 1 + m.n_confidences + m.n_vectors * 2 + m.n_scales
+        plan['heads'].append({
+            'w': hn.conv.weight.detach().float().cpu().numpy().reshape(m.n_fields * ncomp, -1),
+            'b': hn.conv.bias.detach().float().cpu().numpy(),
+            'n_fields': int(m.n_fields), 'n_comp': int(ncomp),
+            'ops': head_ops(m.n_confidences, m.n_vectors, m.n_scales, tuple(m.vector_offsets)),
+            'stride': int(base.stride)})
+    return plan
+
+
+def random_plan(base_name='shufflenetv2k16', heads=((17, 1, 1, 1), (19, 1, 2, 2)), seed=0):
+    """Random-init folded plan of the named architecture (no checkpoint can be downloaded here).
+    heads: (n_fields, n_confidences, n_vectors, n_scales) per head; vector offsets all True."""
+    repeats, ch = SHUFFLENETV2K_CONFIGS[base_name]
+    rng = np.random.Generator(np.random.PCG64(seed))
+
+    def conv(cout, cin, k=1, dw=False):
+        fan_in = (1 if dw else cin) * k * k
+        w = rng.standard_normal((cout, 1 if dw else cin, k, k)).astype(np.float32) * np.float32(np.sqrt(2.0 / fan_in))
+        b = (rng.standard_normal(cout) * 0.05).astype(np.float32)
+        return w, b
+
+    w, b = conv(ch[0], 3, 3)
+    plan = {'kind': 'shufflenetv2k', 'input': {'w': w, 'b': b, 'stride': 2, 'pad': 1}, 'stages': [], 'heads': []}
+    cin = ch[0]
+    for rep, cout in zip(repeats, ch[1:4]):
+        bf = cout // 2
+        blocks = []
+        for i in range(rep):
+            first = i == 0
+            e = {'first': first, 'stride': 2 if first else 1, 'kernel': 5, 'pad': 2}
+            e['b2_pw1'] = conv(bf, cin if first else bf)
+            e['b2_dw'] = conv(bf, bf, 5, dw=True)
+            e['b2_pw2'] = conv(bf, bf)
+            if first:
+                e['b1_dw'] = conv(cin, cin, 5, dw=True)
+                e['b1_pw'] = conv(bf, cin)
+            blocks.append(e)
+        plan['stages'].append(blocks)
+        cin = cout
+    plan['conv5'] = conv(ch[4], cin)
+    for (nf, nconf, nvec, nsc) in heads:
+        ncomp = 1 + nconf + 2 * nvec + nsc
+        w = (rng.standard_normal((nf * ncomp, ch[4])) * np.sqrt(1.0 / ch[4])).astype(np.float32)
+        b = (rng.standard_normal(nf * ncomp) * 0.1).astype(np.float32)
+        plan['heads'].append({'w': w, 'b': b, 'n_fields': nf, 'n_comp': ncomp,
+                              'ops': head_ops(nconf, nvec, nsc, (True,) * nvec), 'stride': 16})
+    return plan
+
+
+# ----------------------------------------------------------------------------- compiled net
+
+class _DevArray:
+    """Expose a raw device pointer to torch through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr, shape, typestr='<f4'):
+        self.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': typestr, 'data': (int(ptr), False),
+                                         'version': 2}
+
+
+class _Layout:
+    """Physical column placement of a logical channel vector."""
+
+    def __init__(self, channels, split):
+        self.channels = channels
+        self.split = split
+        if split:
+            self.half = channels // 2
+            self.hp = pad8(self.half)
+            self.width = 2 * self.hp
+        else:
+            self.width = pad8(channels)
+
+    def cols(self):
+        l = np.arange(self.channels)
+        if not self.split:
+            return l
+        return l + (l >= self.half) * (self.hp - self.half)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def build_ops(plan, in_h, in_w):
+    """Lower a plan to the op list of libpifpaf_b200 (pure Python; no GPU needed).
+
+    Returns (tensors, ops): tensors[i] = (h, w, c_phys); ops are dicts with a 'kind' in
+    {'input_conv', 'conv1x1', 'dwconv', 'heads'} whose fields are the C ABI arguments."""
+    if plan.get('kind') != 'shufflenetv2k':
+        raise RuntimeError('unsupported plan kind')
+    tensors, ops = [], []
+
+    def tensor(h, w, c):
+        tensors.append((h, w, c))
+        return len(tensors) - 1
+
+    def conv1x1(tin, in_off, in_cols, k_cols, wb, relu, tout, shuffle=None):
+        w, b = wb
+        w = w.reshape(w.shape[0], -1)
+        n, cin = w.shape
+        assert len(in_cols) == cin
+        wp = np.zeros((n, k_cols), dtype=np.float32)
+        wp[:, in_cols] = w
+        s_t, s_off = (-1, 0) if shuffle is None else shuffle
+        ops.append({'kind': 'conv1x1', 'in': tin, 'in_off': in_off, 'k_cols': k_cols, 'n_out': n,
+                    'w': wp, 'b': _f32(b), 'relu': int(relu), 'out': tout, 'out_off': 0,
+                    'shuffle_src': s_t, 'shuffle_off': s_off})
+
+    def dwconv(tin, cols, width, wb, kernel, stride, pad, tout):
+        w, b = wb
+        w = w.reshape(w.shape[0], kernel * kernel)
+        wp = np.zeros((width, kernel * kernel), dtype=np.float32)
+        bp = np.zeros((width,), dtype=np.float32)
+        wp[cols] = w
+        bp[cols] = b
+        ops.append({'kind': 'dwconv', 'in': tin, 'in_off': 0, 'channels': width, 'kernel': kernel,
+                    'stride': stride, 'pad': pad, 'w': wp, 'b': bp, 'relu': 0, 'out': tout, 'out_off': 0})
+
+    inp = plan['input']
+    k = inp['w'].shape[-1]
+    h = (in_h + 2 * inp['pad'] - k) // inp['stride'] + 1
+    w = (in_w + 2 * inp['pad'] - k) // inp['stride'] + 1
+    c0 = inp['w'].shape[0]
+    cur = tensor(h, w, pad8(c0))
+    ops.append({'kind': 'input_conv', 'in_h': in_h, 'in_w': in_w, 'kernel': k, 'stride': inp['stride'],
+                'pad': inp['pad'], 'c_out': c0, 'w': _f32(inp['w']), 'b': _f32(inp['b']), 'relu': 1, 'out': cur})
+    lay = _Layout(c0, split=False)
+    block_outputs = []
+    for blocks in plan['stages']:
+        for e in blocks:
+            bf = e['b2_pw2'][0].shape[0]
+            hp = pad8(bf)
+            kk, st, pd = e['kernel'], e['stride'], e['pad']
+            ho, wo = (h + 2 * pd - kk) // st + 1, (w + 2 * pd - kk) // st + 1
+            out_lay = _Layout(2 * bf, split=True)
+            t_out = tensor(ho, wo, out_lay.width)
+            if e['first']:
+                cols = lay.cols()
+                # branch1: dw (stride) -> 1x1   (basenetworks.py:200-212)
+                t_a = tensor(ho, wo, lay.width)
+                dwconv(cur, cols, lay.width, e['b1_dw'], kk, st, pd, t_a)
+                t_b = tensor(ho, wo, hp)
+                conv1x1(t_a, 0, cols, lay.width, e['b1_pw'], True, t_b)
+                # branch2: 1x1 -> dw (stride) -> 1x1   (basenetworks.py:214-226)
+                t_c = tensor(h, w, hp)
+                conv1x1(cur, 0, cols, lay.width, e['b2_pw1'], True, t_c)
+                t_d = tensor(ho, wo, hp)
+                dwconv(t_c, np.arange(bf), hp, e['b2_dw'], kk, st, pd, t_d)
+                conv1x1(t_d, 0, np.arange(bf), hp, e['b2_pw2'], True, t_out, shuffle=(t_b, 0))
+            else:
+                assert lay.split and lay.half == bf
+                # x1, x2 = x.chunk(2): x2 is the column window [hp, 2*hp)   (basenetworks.py:234-236)
+                t_c = tensor(h, w, hp)
+                conv1x1(cur, hp, np.arange(bf), bf, e['b2_pw1'], True, t_c)
+                t_d = tensor(ho, wo, hp)
+                dwconv(t_c, np.arange(bf), hp, e['b2_dw'], kk, st, pd, t_d)
+                conv1x1(t_d, 0, np.arange(bf), hp, e['b2_pw2'], True, t_out, shuffle=(cur, 0))
+            cur, lay, h, w = t_out, out_lay, ho, wo
+            block_outputs.append((cur, lay))
+    w5, b5 = plan['conv5']
+    c5 = w5.shape[0]
+    t5 = tensor(h, w, pad8(c5))
+    conv1x1(cur, 0, lay.cols(), lay.width, (w5, b5), True, t5)
+    heads = plan['heads']
+    ops.append({'kind': 'heads', 'in': t5, 'k_cols': c5,
+                'n_fields': [hd['n_fields'] for hd in heads], 'n_comp': [hd['n_comp'] for hd in heads],
+                'ops': [o for hd in heads for o in hd['ops']],
+                'w': _f32(np.concatenate([_f32(hd['w']) for hd in heads], axis=0)),
+                'b': _f32(np.concatenate([_f32(hd['b']) for hd in heads], axis=0))})
+    return tensors, ops, {'block_outputs': block_outputs, 'feature': (t5, _Layout(c5, split=False))}
+
+
+class CompiledNet:
+    """A plan compiled to libpifpaf_b200 ops for a fixed input size and maximum batch."""
+
+    def __init__(self, plan, in_h, in_w, max_batch, device=0):
+        self.lib = _lib.lib()
+        self.device = int(device)
+        self.max_batch = int(max_batch)
+        self.in_h, self.in_w = int(in_h), int(in_w)
+        self.tensor_shapes, ops, self.info = build_ops(plan, self.in_h, self.in_w)
+        self.handle = ctypes.c_void_p()
+        _lib.check(self.lib.pifpaf_net_create(ctypes.byref(self.handle), self.device, self.max_batch))
+        self._emit(ops)
+        self.flops_per_image = float(self.lib.pifpaf_net_flops_per_image(self.handle))
+        self.num_ops = int(self.lib.pifpaf_net_num_ops(self.handle))
+        self.heads = []
+        for i, h in enumerate(plan['heads']):
+            ptr = ctypes.c_void_p()
+            nf, nc, hh, ww = (ctypes.c_int32() for _ in range(4))
+            _lib.check(self.lib.pifpaf_net_head_output(self.handle, i, ctypes.byref(ptr), ctypes.byref(nf),
+                                                       ctypes.byref(nc), ctypes.byref(hh), ctypes.byref(ww)))
+            self.heads.append({'ptr': ptr.value, 'n_fields': nf.value, 'n_comp': nc.value,
+                               'h': hh.value, 'w': ww.value, 'stride': h['stride']})
+
+    def __del__(self):
+        h, self.handle = getattr(self, 'handle', None), None
+        if h:
+            try:
+                self.lib.pifpaf_net_destroy(h)
+            except Exception:
+                pass
+
+    def _emit(self, ops):
+        L, H = self.lib, self.handle
+        for (h, w, c) in self.tensor_shapes:
+            tid = ctypes.c_int32(-1)
+            _lib.check(L.pifpaf_net_tensor(H, h, w, c, ctypes.byref(tid)))
+        for o in ops:
+            if o['kind'] == 'input_conv':
+                _lib.check(L.pifpaf_net_input_conv(H, o['in_h'], o['in_w'], o['kernel'], o['stride'], o['pad'],
+                                                   o['c_out'], _ptr(o['w']), _ptr(o['b']), o['relu'], o['out']))
+            elif o['kind'] == 'conv1x1':
+                _lib.check(L.pifpaf_net_conv1x1(H, o['in'], o['in_off'], o['k_cols'], o['n_out'], _ptr(o['w']),
+                                                _ptr(o['b']), o['relu'], o['out'], o['out_off'],
+                                                o['shuffle_src'], o['shuffle_off']))
+            elif o['kind'] == 'dwconv':
+                _lib.check(L.pifpaf_net_dwconv(H, o['in'], o['in_off'], o['channels'], o['kernel'], o['stride'],
+                                               o['pad'], _ptr(o['w']), _ptr(o['b']), o['relu'], o['out'], o['out_off']))
+            elif o['kind'] == 'heads':
+                n = len(o['n_fields'])
+                nf = (ctypes.c_int32 * n)(*o['n_fields'])
+                nc = (ctypes.c_int32 * n)(*o['n_comp'])
+                ops_c = (ctypes.c_int32 * len(o['ops']))(*o['ops'])
+                _lib.check(L.pifpaf_net_heads(H, o['in'], o['k_cols'], n, nf, nc, ops_c, _ptr(o['w']), _ptr(o['b'])))
+            else:
+                raise RuntimeError(o['kind'])
+
+    # --- execution -----------------------------------------------------------
+    def forward(self, image_batch, *, gemm_impl=0, stream=None):
+        """Shell.forward: image_batch [B,3,H,W] float32 CUDA -> tuple of [B,F,comp,h,w] float32 CUDA views
+        (valid until the next forward)."""
+        if not image_batch.is_cuda or image_batch.dtype != torch.float32:
+            raise RuntimeError('image_batch must be a float32 CUDA tensor')
+        if image_batch.dim() != 4 or image_batch.shape[1] != 3 or tuple(image_batch.shape[2:]) != (self.in_h, self.in_w):
+            raise RuntimeError(f'expected [B,3,{self.in_h},{self.in_w}]')
+        b = int(image_batch.shape[0])
+        if b > self.max_batch:
+            raise RuntimeError('batch exceeds max_batch')
+        image_batch = image_batch.contiguous()
+        st = stream if stream is not None else torch.cuda.current_stream(image_batch.device)
+        _lib.check(self.lib.pifpaf_net_forward(self.handle, image_batch.data_ptr(), b, int(gemm_impl),
+                                               ctypes.c_void_p(st.cuda_stream)))
+        self._keepalive = image_batch
+        outs = []
+        for hd in self.heads:
+            arr = _DevArray(hd['ptr'], (b, hd['n_fields'], hd['n_comp'], hd['h'], hd['w']))
+            outs.append(torch.as_tensor(arr, device=f'cuda:{self.device}'))
+        return tuple(outs)
+
+    def forward_timed(self, image_batch, *, gemm_impl=0):
+        """Profiling pass: per-op (ms, kind, flops, bytes); kind 0 input conv, 1 tcgen05 GEMM, 2 depthwise."""
+        b, n = int(image_batch.shape[0]), self.num_ops
+        ms = np.zeros((n,), dtype=np.float32)
+        kind = np.zeros((n,), dtype=np.int32)
+        flops = np.zeros((n,), dtype=np.float64)
+        nbytes = np.zeros((n,), dtype=np.float64)
+        st = torch.cuda.current_stream(image_batch.device)
+        _lib.check(self.lib.pifpaf_net_forward_timed(self.handle, image_batch.contiguous().data_ptr(), b,
+                                                     int(gemm_impl), ctypes.c_void_p(st.cuda_stream),
+                                                     _ptr(ms), _ptr(kind), _ptr(flops), _ptr(nbytes)))
+        return ms, kind, flops, nbytes
+
+    def tap(self, tensor_id, batch):
+        """Debug: activation tensor as float32 numpy [B,h,w,c_phys]."""
+        h, w, c = self.tensor_shapes[tensor_id]
+        out = np.empty((batch, h, w, c), dtype=np.float32)
+        _lib.check(self.lib.pifpaf_net_tap_tensor(self.handle, tensor_id, batch, _ptr(out), out.size))
+        return out

@@ -1,0 +1,70 @@
+"""End-to-end batch API: images -> backbone+heads -> CifCaf decode -> annotations.
+
+Mirror of the reference's hot loop (paths relative to /root/reference/src/openpifpaf/):
+  Predictor.enumerated_dataloader   predictor.py:118-153
+  Decoder.batch / fields_batch      decoder/decoder.py:76-137
+
+Differences by design: the head tensors never leave the GPU (the reference does
+``heads.cpu()`` at decoder/decoder.py:98 and decodes on host cores); the whole
+batch is decoded by one batched launch sequence; only the final annotations
+(a few KB) are copied back.
+"""
+import time
+
+import torch
+
+from . import decoder as _decoder
+from . import network as _network
+
+
+class Predictor:
+    """:param net: `network.CompiledNet`
+    :param skeleton: 1-based skeleton of the CAF head (``headmeta.Caf.skeleton``)
+    :param n_keypoints: number of keypoints of the CIF head"""
+
+    def __init__(self, net, n_keypoints, skeleton, *, device=0):
+        self.net = net
+        self.device = torch.device('cuda', device)
+        sk = torch.as_tensor(skeleton, dtype=torch.int64).reshape(-1, 2) - 1     # decoder/cifcaf.py:121
+        self.decoder = _decoder.CifCaf(n_keypoints, sk, device=device)
+        self.cif_head, self.caf_head = 0, 1
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._dev_images = None
+        self.last_nn_time = 0.0
+        self.last_decoder_time = 0.0
+
+    def fields_batch(self, image_batch):
+        """decoder/decoder.py:76-112 without the .cpu(): returns device-resident head tensors."""
+        return self.net.forward(image_batch)
+
+    def batch_device(self, image_batch_dev):
+        """Device-resident images -> enqueue forward + decode on the current stream (no host sync)."""
+        heads = self.net.forward(image_batch_dev)
+        cif, caf = heads[self.cif_head], heads[self.caf_head]
+        self.decoder.decode_batch_async(cif, self.net.heads[self.cif_head]['stride'],
+                                        caf, self.net.heads[self.caf_head]['stride'])
+
+    def batch(self, image_batch_host):
+        """decoder/decoder.py:114-137: image batch (host, ideally pinned, float32 [B,3,H,W]) -> per-image
+        (annotations [N,K,4], ids [N]) CPU tensors.  H2D, forward, decode and D2H all inside."""
+        t0 = time.perf_counter()
+        with torch.cuda.stream(self.stream):
+            if self._dev_images is None or self._dev_images.shape != image_batch_host.shape:
+                self._dev_images = torch.empty(image_batch_host.shape, dtype=torch.float32, device=self.device)
+            self._dev_images.copy_(image_batch_host, non_blocking=True)
+            self.batch_device(self._dev_images)
+            result = self.decoder.fetch(stream=self.stream)
+        self.last_nn_time = self.last_decoder_time = time.perf_counter() - t0
+        return result
+
+
+def from_shell(shell, in_h, in_w, max_batch, *, device=0):
+    """Compile a reference-style Shell (network/nets.py:7-48) whose heads are (Cif, Caf) into a Predictor."""
+    plan = _network.plan_from_shell(shell)
+    net = _network.CompiledNet(plan, in_h, in_w, max_batch, device=device)
+    metas = shell.head_metas
+    cif_meta, caf_meta = metas[0], metas[1]
+    skeleton = getattr(caf_meta, 'skeleton', None)
+    if skeleton is None:
+        raise RuntimeError('CAF head meta has no skeleton')
+    return Predictor(net, cif_meta.n_fields, skeleton, device=device)

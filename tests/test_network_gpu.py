@@ -1,0 +1,94 @@
+"""GPU: backbone + heads kernels against the plain PyTorch fp32 reference of the same network, and the
+end-to-end Predictor path (network fields -> CUDA decoder) against the oracle decoder on the same fields."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+import ops_emulator
+from openpifpaf_b200 import constants, network, predictor
+from oracle import cifcaf as oc, net_oracle
+
+pytestmark = pytest.mark.gpu
+
+# bf16 activations / weights with f32 accumulation through ~57 fused ops, against fp32 PyTorch:
+# tolerance relative to the standard deviation of each field tensor (stated per BASELINE north_star 'bf16')
+FIELD_TOL_REL = 3e-2
+
+
+@pytest.fixture(scope='module')
+def small():
+    shell = net_oracle.make_shell('shufflenetv2k16', seed=1)
+    plan = network.plan_from_shell(shell)
+    return shell, plan
+
+
+def test_every_op_matches_bf16_emulation(small):
+    """each fused op against a CPU emulation that rounds to bf16 at the same points (tcgen05 and SIMT debug)."""
+    shell, plan = small
+    h, w, B = 97, 129, 2
+    x = torch.randn(B, 3, h, w, generator=torch.Generator().manual_seed(0))
+    tensors, ops, _ = network.build_ops(plan, h, w)
+    emu_heads, emu_acts = ops_emulator.run_ops(tensors, ops, x, bf16=True)
+    net = network.CompiledNet(plan, h, w, B)
+    for impl in (1, 0):
+        heads = net.forward(x.cuda(), gemm_impl=impl)
+        torch.cuda.synchronize()
+        for o in ops:
+            if o['kind'] == 'heads':
+                continue
+            got = net.tap(o['out'], B)
+            ref = emu_acts[o['out']].numpy()
+            scale = max(float(np.abs(ref).max()), 1e-6)
+            assert float(np.abs(got - ref).max()) / scale < 3e-2, (impl, o['kind'], o['out'])
+        for hg, he in zip(heads, emu_heads):
+            assert float((hg.cpu() - he).abs().max()) < 5e-2
+
+
+def test_fields_match_fp32_pytorch_full_size():
+    """BASELINE size: 641x641 (41x41 fields), batch 4, vs fp32 PyTorch (no TF32) on the same GPU."""
+    shell = net_oracle.make_shell('shufflenetv2k16', seed=2)
+    plan = network.plan_from_shell(shell)
+    net = network.CompiledNet(plan, 641, 641, 4)
+    x = torch.randn(4, 3, 641, 641, generator=torch.Generator().manual_seed(1)).cuda()
+    heads = net.forward(x)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        ref = shell.cuda()(x)
+    for hg, hr in zip(heads, ref):
+        assert hg.shape == hr.shape == (4, hr.shape[1], hr.shape[2], 41, 41)
+        err = float((hg - hr).abs().max())
+        assert err < FIELD_TOL_REL * float(hr.std()) + 1e-3, err
+
+
+def test_linearity_property_of_conv_path():
+    """size-independent property: with ReLU-free positive scaling, fields scale consistently --
+    forward(x) is deterministic and batch-position independent (image b alone == image b in a batch)."""
+    plan = network.random_plan('shufflenetv2k16', seed=4)
+    net = network.CompiledNet(plan, 161, 161, 8)
+    x = torch.randn(8, 3, 161, 161, generator=torch.Generator().manual_seed(2)).cuda()
+    full = [h.clone() for h in net.forward(x)]
+    again = [h.clone() for h in net.forward(x)]
+    for a, b in zip(full, again):
+        assert torch.equal(a, b)
+    for b in (0, 5, 7):
+        one = net.forward(x[b:b + 1].contiguous())
+        for hf, ho in zip(full, one):
+            assert torch.equal(hf[b], ho[0])
+
+
+def test_predictor_end_to_end_host_buffers():
+    """Predictor.batch on host images: CUDA decode of the network's fields == oracle decode of the same fields."""
+    plan = network.random_plan('shufflenetv2k16', seed=0)
+    net = network.CompiledNet(plan, 321, 321, 4)
+    pred = predictor.Predictor(net, constants.COCO_N_KEYPOINTS, constants.COCO_PERSON_SKELETON)
+    imgs = torch.randn(4, 3, 321, 321, generator=torch.Generator().manual_seed(3)).pin_memory()
+    res = pred.batch(imgs)
+    assert len(res) == 4
+    cif, caf = [h.cpu().numpy() for h in net.forward(imgs.cuda())]
+    sk = np.asarray(constants.COCO_PERSON_SKELETON, dtype=np.int64) - 1
+    p = oc.default_params(seed_sort_stable=1)
+    for b in range(4):
+        oa, _ = oc.decode(cif[b], 16, caf[b], 16, sk, 17, params=p)
+        helpers.assert_annotations_close(res[b][0].numpy(), oa, f'image {b}')

@@ -1,0 +1,108 @@
+"""CPU: (1) the oracle network equals the reference's own PyTorch modules (imported from /root/reference
+when present); (2) the product's host lowering (BN folding, physical channel placement, fused
+cat+channel_shuffle, head epilogue) reproduces the oracle network when its op list is interpreted on the CPU."""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import ops_emulator
+from openpifpaf_b200 import network
+from oracle import net_oracle
+
+REF_SRC = '/root/reference/src/openpifpaf'
+
+
+def _load_reference_modules():
+    """Load basenetworks / heads / headmeta of the reference by path, without running the package
+    __init__ (which needs the compiled extension and optional dependencies)."""
+    top = types.ModuleType('refpifpaf')
+    top.__path__ = [REF_SRC]
+    sys.modules['refpifpaf'] = top
+    net_pkg = types.ModuleType('refpifpaf.network')
+    net_pkg.__path__ = [os.path.join(REF_SRC, 'network')]
+    sys.modules['refpifpaf.network'] = net_pkg
+
+    def load(name, path):
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+        return mod
+
+    top.headmeta = load('refpifpaf.headmeta', os.path.join(REF_SRC, 'headmeta.py'))
+    base = load('refpifpaf.network.basenetworks', os.path.join(REF_SRC, 'network', 'basenetworks.py'))
+    heads = load('refpifpaf.network.heads', os.path.join(REF_SRC, 'network', 'heads.py'))
+    return top.headmeta, base, heads
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SRC), reason='/root/reference absent')
+def test_oracle_net_equals_reference_modules():
+    headmeta, base, heads = _load_reference_modules()
+    torch.manual_seed(0)
+    ref_base = base.ShuffleNetV2K('shufflenetv2k16', [4, 8, 4], [24, 348, 696, 1392, 1392])
+    kps = [str(i) for i in range(17)]
+    sk = [(1, 2)] * 19
+    cif = headmeta.Cif('cif', 'cocokp', keypoints=kps, sigmas=[0.1] * 17)
+    caf = headmeta.Caf('caf', 'cocokp', keypoints=kps, sigmas=[0.1] * 17, skeleton=sk)
+    ref_heads = [heads.CompositeField4(cif, 1392), heads.CompositeField4(caf, 1392)]
+    oracle = net_oracle.make_shell('shufflenetv2k16', seed=3)
+    # same parameter names -> load the oracle's (randomised) weights into the reference modules
+    ref_base.load_state_dict(oracle.base_net.state_dict())
+    for rh, oh in zip(ref_heads, oracle.head_nets):
+        rh.load_state_dict(oh.state_dict())
+        rh.eval()
+    net_oracle.model_defaults(ref_base)
+    ref_base.eval()
+    x = torch.randn(1, 3, 97, 113)
+    with torch.no_grad():
+        feat = ref_base(x)
+        want = [rh(feat) for rh in ref_heads]
+        got = oracle(x)
+    for w, g in zip(want, got):
+        assert w.shape == g.shape
+        torch.testing.assert_close(g, w, rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize('shape', [(97, 129), (65, 65)])
+def test_lowering_reproduces_oracle_net(shape):
+    h, w = shape
+    shell = net_oracle.make_shell('shufflenetv2k16', seed=1)
+    x = torch.randn(2, 3, h, w)
+    with torch.no_grad():
+        want = shell(x)
+    plan = network.plan_from_shell(shell)
+    tensors, ops, _ = network.build_ops(plan, h, w)
+    got, _ = ops_emulator.run_ops(tensors, ops, x)
+    for g, wnt in zip(got, want):
+        assert g.shape == wnt.shape
+        assert float((g - wnt).abs().max()) < 2e-5
+    # every activation window handed to TMA starts on a 16-byte boundary
+    for o in ops:
+        if o['kind'] in ('conv1x1', 'dwconv'):
+            assert o['in_off'] % 8 == 0 and o['out_off'] % 8 == 0
+    assert all(c % 8 == 0 for (_, _, c) in tensors)
+
+
+def test_random_plan_has_reference_architecture():
+    plan = network.random_plan('shufflenetv2k16')
+    assert [len(s) for s in plan['stages']] == [4, 8, 4]
+    assert plan['conv5'][0].shape[:2] == (1392, 1392)
+    assert [h['w'].shape[0] for h in plan['heads']] == [85, 152]
+    tensors, ops, _ = network.build_ops(plan, 641, 641)
+    gmac = 0.0
+    for o in ops:
+        hh, ww, _ = tensors[o['out']] if 'out' in o else tensors[o['in']]
+        if o['kind'] == 'conv1x1':
+            gmac += hh * ww * np.count_nonzero(o['w']) / 1e9
+        elif o['kind'] == 'heads':
+            gmac += hh * ww * o['w'].size / 1e9
+        elif o['kind'] == 'dwconv':
+            gmac += hh * ww * np.count_nonzero(o['w']) / 1e9
+        elif o['kind'] == 'input_conv':
+            gmac += hh * ww * o['w'].size / 1e9
+    assert abs(gmac - 36.58) < 0.2, gmac       # 36.58 GMAC / image @641
