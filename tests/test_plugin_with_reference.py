@@ -1,0 +1,58 @@
+"""CPU: the plugin registers with the UNMODIFIED reference package (staged from /root/reference with the
+compiled extension of oracle/_ref) and is selected by the reference's decoder factory.  Skipped when the
+reference is not available (e.g. on the GPU box)."""
+import os
+import shutil
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+REF = '/root/reference/src/openpifpaf'
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, 'oracle', '_ref', 'refcpp.so')
+
+
+@pytest.mark.skipif(not (os.path.isdir(REF) and os.path.exists(REF_SO)), reason='reference not available')
+def test_plugin_registers_and_is_selected(tmp_path):
+    stage = tmp_path / 'stage'
+    shutil.copytree(REF, stage / 'openpifpaf')
+    shutil.copy(REF_SO, stage / 'openpifpaf' / '_cpp.so')
+    (stage / 'pysparkling.py').write_text('class Context: pass\n')     # optional dependency stub
+    script = textwrap.dedent('''
+        import sys, warnings
+        warnings.filterwarnings('ignore')
+        import torch
+        torch.ops.load_library = torch.ops.load_library
+        import openpifpaf
+        from openpifpaf.plugins.coco.constants import COCO_KEYPOINTS, COCO_PERSON_SKELETON, COCO_PERSON_SIGMAS
+        assert 'openpifpaf_b200' in openpifpaf.plugin.REGISTERED, list(openpifpaf.plugin.REGISTERED)
+        names = sorted(d.__name__ for d in openpifpaf.DECODERS)
+        assert 'CifCafB200' in names, names
+        cif = openpifpaf.headmeta.Cif('cif', 'cocokp', keypoints=COCO_KEYPOINTS, sigmas=COCO_PERSON_SIGMAS)
+        caf = openpifpaf.headmeta.Caf('caf', 'cocokp', keypoints=COCO_KEYPOINTS, sigmas=COCO_PERSON_SIGMAS,
+                                      skeleton=COCO_PERSON_SKELETON)
+        cif.head_index, caf.head_index = 0, 1
+        cif.base_stride = caf.base_stride = 16
+        multi = openpifpaf.decoder.factory([cif, caf])
+        top = multi.decoders[0]
+        assert type(top).__name__ == 'CifCafB200', type(top).__name__
+        assert top.native.n_keypoints == 17 and tuple(top.native.skeleton.shape) == (19, 2)
+        # CLI flags of the reference reach the native statics
+        import argparse
+        parser = argparse.ArgumentParser()
+        openpifpaf.decoder.cli(parser)
+        args = parser.parse_args(['--force-complete-pose', '--seed-threshold=0.1'])
+        openpifpaf.decoder.configure(args)
+        from openpifpaf_b200 import decoder as d
+        p = d.CifCaf.params()
+        assert (p.force_complete, p.keypoint_threshold, p.keypoint_threshold_rel, p.seed_threshold,
+                p.nms_instance_threshold, p.nms_keypoint_threshold) == (1, 0.0, 0.0, 0.1, 0.0, 0.0), \\
+            (p.force_complete, p.keypoint_threshold, p.seed_threshold)
+        print('PLUGIN_OK')
+    ''')
+    env = dict(os.environ, PYTHONPATH=f'{stage}:{ROOT}')
+    r = subprocess.run([sys.executable, '-c', script], capture_output=True, text=True, env=env, cwd=str(tmp_path),
+                       timeout=300)
+    assert 'PLUGIN_OK' in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
