@@ -112,6 +112,16 @@ int pifpaf_decoder_decode_device(pifpaf_decoder_t* dec,
 int pifpaf_decoder_fetch(pifpaf_decoder_t* dec, int32_t* counts, float* ann, int64_t* ids,
                          int32_t ann_cap, void* stream);
 
+/* Split fetch for pipelining: fetch_begin enqueues ONE async D2H of the packed results of the last decode
+ * (header + up to 512 KB of records) on `stream` and returns at once; fetch_end waits for it and unpacks
+ * (same outputs as pifpaf_decoder_fetch).  Results are double buffered: a new decode may be enqueued
+ * between begin and end; at most two fetches may be outstanding, completed in order. */
+int pifpaf_decoder_fetch_begin(pifpaf_decoder_t* dec, void* stream);
+int pifpaf_decoder_fetch_end(pifpaf_decoder_t* dec, int32_t* counts, float* ann, int64_t* ids, int32_t ann_cap);
+/* Wait for the oldest outstanding fetch and report its per-image counts without consuming it
+ * (lets the caller size the buffers it passes to fetch_end). */
+int pifpaf_decoder_fetch_peek(pifpaf_decoder_t* dec, int32_t* counts);
+
 /* Single image, HOST buffers: the call the reference's binding makes.
  * Replaces CifCaf::call / call_with_initial_annotations
  * (csrc/src/cifcaf.cpp:116-262): cif [F][5][h][w], caf [C][8][h][w] on the host;

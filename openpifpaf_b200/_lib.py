@@ -44,6 +44,9 @@ SYMBOLS = {
     'pifpaf_decoder_decode_device': (ctypes.c_int, [VP, VP, VP, c_i32, c_i32, c_i32, c_i32, c_i32,
                                                     VP, VP, VP, c_i32, P(DecoderParams), VP]),
     'pifpaf_decoder_fetch': (ctypes.c_int, [VP, VP, VP, VP, c_i32, VP]),
+    'pifpaf_decoder_fetch_begin': (ctypes.c_int, [VP, VP]),
+    'pifpaf_decoder_fetch_end': (ctypes.c_int, [VP, VP, VP, VP, c_i32]),
+    'pifpaf_decoder_fetch_peek': (ctypes.c_int, [VP, VP]),
     'pifpaf_decoder_call': (ctypes.c_int, [VP, VP, c_i32, VP, c_i32, c_i32, c_i32, VP, VP, c_i32,
                                            P(DecoderParams), VP, VP, c_i32, P(c_i32)]),
     'pifpaf_decoder_tap_cifhr': (ctypes.c_int, [VP, c_i32, VP, c_i64]),

@@ -95,15 +95,27 @@ __device__ __forceinline__ float approx_exp(float x) {
     return x;
 }
 
-// src/cif_seeds.cpp:17-30 == src/caf_scored.cpp:15-26.  hr is the image base [F][H][Wp].
-__device__ __forceinline__ float cifhr_value(const float* __restrict__ hr, int F, int H, int W, int Wp,
-                                             double revision, long long f, float x, float y,
+// The CifHr map is SPARSE: only 32x32 tiles touched by a contributing cell are ever written; a tile is
+// valid for this call iff its epoch tag equals the call's epoch, otherwise every pixel of it reads as the
+// never-written 0.0 of a fresh reference buffer (src/cif_hr.cpp:97-114).
+struct HrView {
+    const float* hr;              // image base [F][H][Wp]
+    const unsigned* tile_epoch;   // image base [F][tiles]
+    unsigned epoch;
+    int F, H, W, Wp, tiles_x, tiles;
+};
+
+// src/cif_seeds.cpp:17-30 == src/caf_scored.cpp:15-26.
+__device__ __forceinline__ float cifhr_value(const HrView& v, double revision, long long f, float x, float y,
                                              float default_value) {
-    const float max_x = (float)((double)(float)W - 0.51);
-    const float max_y = (float)((double)(float)H - 0.51);
-    if (f >= F || (double)x < -0.49 || (double)y < -0.49 || x > max_x || y > max_y) return default_value;
+    const float max_x = (float)((double)(float)v.W - 0.51);
+    const float max_y = (float)((double)(float)v.H - 0.51);
+    if (f >= v.F || (double)x < -0.49 || (double)y < -0.49 || x > max_x || y > max_y) return default_value;
     const long long yi = (long long)((double)y + 0.5), xi = (long long)((double)x + 0.5);
-    const float value = (float)((double)hr[((size_t)f * H + yi) * Wp + xi] - revision);
+    const int tile = (int)(yi / TILE) * v.tiles_x + (int)(xi / TILE);
+    float stored = 0.0f;
+    if (v.tile_epoch[(size_t)f * v.tiles + tile] == v.epoch) stored = v.hr[((size_t)f * v.H + yi) * v.Wp + xi];
+    const float value = (float)((double)stored - revision);
     if ((double)value < 0.0) return default_value;
     return value;
 }
@@ -115,7 +127,9 @@ __global__ void __launch_bounds__(NT) k_cif_compact(const float* __restrict__ ci
                                                     double threshold, long long neighbors,
                                                     float min_scale_f, double factor,
                                                     float4* __restrict__ cells, int4* __restrict__ boxes,
-                                                    int* __restrict__ counts) {
+                                                    int* __restrict__ counts,
+                                                    unsigned* __restrict__ tile_epoch, unsigned epoch,
+                                                    int* __restrict__ worklist, int* __restrict__ work_count) {
     __shared__ int wc[NW];
     const int f = blockIdx.x, b = blockIdx.y;
     const float* cf = cif + ((size_t)(b * d.F + f) * 5) * d.hw;
@@ -147,6 +161,13 @@ __global__ void __launch_bounds__(NT) k_cif_compact(const float* __restrict__ ci
             const long long maxy = clamp_ll((long long)(y + truncate * sigma + 1.0f), miny + 1, d.H);
             out_c[pos] = make_float4(x, y, sigma, vn);
             out_b[pos] = make_int4((int)minx, (int)miny, (int)maxx, (int)maxy);
+            // first toucher of a tile in this call appends it to the worklist
+            const int tiles = d.tiles_x * d.tiles_y;
+            for (int ty = (int)miny / TILE; ty <= ((int)maxy - 1) / TILE; ty++)
+                for (int tx = (int)minx / TILE; tx <= ((int)maxx - 1) / TILE; tx++) {
+                    const int gid = (b * d.F + f) * tiles + ty * d.tiles_x + tx;
+                    if (atomicExch(&tile_epoch[gid], epoch) != epoch) worklist[atomicAdd(work_count, 1)] = gid;
+                }
         }
     }
     if (threadIdx.x == 0) counts[b * d.F + f] = base;
@@ -159,11 +180,18 @@ __global__ void __launch_bounds__(NT) k_cifhr_tiles(Dims d, double revision,
                                                     const float4* __restrict__ cells,
                                                     const int4* __restrict__ boxes,
                                                     const int* __restrict__ counts,
+                                                    const int* __restrict__ worklist,
+                                                    const int* __restrict__ work_count,
                                                     float* __restrict__ cifhr) {
     __shared__ int wc[NW];
     __shared__ float4 s_cell[NT];
     __shared__ int4 s_box[NT];
-    const int tile = blockIdx.x, f = blockIdx.y, b = blockIdx.z;
+    const int n_work = *work_count;
+    const int tiles = d.tiles_x * d.tiles_y;
+    for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+    const int gid = worklist[wi];
+    const int tile = gid % tiles, bf = gid / tiles;
+    const int f = bf % d.F, b = bf / d.F;
     const int tx0 = (tile % d.tiles_x) * TILE, ty0 = (tile / d.tiles_x) * TILE;
     const int px = tx0 + (threadIdx.x & 7) * 4;
     const int py = ty0 + (threadIdx.x >> 3);
@@ -218,19 +246,41 @@ __global__ void __launch_bounds__(NT) k_cifhr_tiles(Dims d, double revision,
         float4* dst = reinterpret_cast<float4*>(cifhr + ((size_t)(b * d.F + f) * d.H + py) * d.Wp + px);
         *dst = make_float4(acc[0], acc[1], acc[2], acc[3]);
     }
+    }   // worklist loop
+}
+
+// get_cifhr()/tap support: make image b's map dense by zero-filling the tiles not written in this call.
+__global__ void __launch_bounds__(NT) k_cifhr_materialize(Dims d, int b, unsigned* __restrict__ tile_epoch,
+                                                          unsigned epoch, float* __restrict__ cifhr) {
+    const int tile = blockIdx.x, f = blockIdx.y;
+    const int tiles = d.tiles_x * d.tiles_y;
+    const size_t gid = (size_t)(b * d.F + f) * tiles + tile;
+    if (tile_epoch[gid] == epoch) return;
+    const int px = (tile % d.tiles_x) * TILE + (threadIdx.x & 7) * 4;
+    const int py = (tile / d.tiles_x) * TILE + (threadIdx.x >> 3);
+    if (py < d.H)
+        *reinterpret_cast<float4*>(cifhr + ((size_t)(b * d.F + f) * d.H + py) * d.Wp + px) = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    if (threadIdx.x == 0) tile_epoch[gid] = epoch;
 }
 
 // ---------------------------------------------------------------------------
 // CifSeeds::fill (src/cif_seeds.cpp:33-66), per (image, field), order preserving.
 __global__ void __launch_bounds__(NT) k_seed_candidates(const float* __restrict__ cif, Dims d,
-                                                        const float* __restrict__ cifhr, double revision,
+                                                        const float* __restrict__ cifhr,
+                                                        const unsigned* __restrict__ tile_epoch, unsigned epoch,
+                                                        double revision,
                                                         double threshold, int ablation_nms, int no_rescore,
                                                         float* __restrict__ seg_v, float4* __restrict__ seg_xys,
                                                         int* __restrict__ seg_counts) {
     __shared__ int wc[NW];
     const int f = blockIdx.x, b = blockIdx.y;
     const float* cf = cif + ((size_t)(b * d.F + f) * 5) * d.hw;
-    const float* hr = cifhr + (size_t)b * d.F * d.H * d.Wp;
+    HrView hv;
+    hv.hr = cifhr + (size_t)b * d.F * d.H * d.Wp;
+    hv.tiles_x = d.tiles_x; hv.tiles = d.tiles_x * d.tiles_y;
+    hv.tile_epoch = tile_epoch + (size_t)b * d.F * hv.tiles; hv.epoch = epoch;
+    hv.F = d.F; hv.H = d.H; hv.W = d.W; hv.Wp = d.Wp;
     float* out_v = seg_v + (size_t)(b * d.F + f) * d.hw;
     float4* out_x = seg_xys + (size_t)(b * d.F + f) * d.hw;
     int base = 0, dummy = 0;
@@ -257,8 +307,8 @@ __global__ void __launch_bounds__(NT) k_seed_candidates(const float* __restrict_
                 x = cf[2 * d.hw + idx] * (float)d.cif_stride;
                 y = cf[3 * d.hw + idx] * (float)d.cif_stride;
                 if (!no_rescore) {
-                    const float hv = cifhr_value(hr, d.F, d.H, d.W, d.Wp, revision, f, x, y, -1.0f);
-                    c = (float)(0.9 * (double)hv + 0.1 * (double)c);
+                    const float hval = cifhr_value(hv, revision, f, x, y, -1.0f);
+                    c = (float)(0.9 * (double)hval + 0.1 * (double)c);
                 }
                 flag = !((double)c < threshold);
             }
@@ -405,13 +455,19 @@ __global__ void __launch_bounds__(SORT_NT) k_seed_sort(Dims d, const int* __rest
 // lists[(((b*C + c)*2 + dir)*7 + comp)*hw + pos], dir 0 = forward, 1 = backward.
 __global__ void __launch_bounds__(NT) k_caf_scored(const float* __restrict__ caf, Dims d,
                                                    const int* __restrict__ skeleton,
-                                                   const float* __restrict__ cifhr, double revision,
+                                                   const float* __restrict__ cifhr,
+                                                   const unsigned* __restrict__ tile_epoch, unsigned epoch,
+                                                   double revision,
                                                    double score_th, double cif_floor, int no_rescore,
                                                    float* __restrict__ lists, int* __restrict__ list_counts) {
     __shared__ int wc[NW];
     const int c = blockIdx.x, b = blockIdx.y;
     const float* cf = caf + ((size_t)(b * d.C + c) * 8) * d.hw;
-    const float* hr = cifhr + (size_t)b * d.F * d.H * d.Wp;
+    HrView hv;
+    hv.hr = cifhr + (size_t)b * d.F * d.H * d.Wp;
+    hv.tiles_x = d.tiles_x; hv.tiles = d.tiles_x * d.tiles_y;
+    hv.tile_epoch = tile_epoch + (size_t)b * d.F * hv.tiles; hv.epoch = epoch;
+    hv.F = d.F; hv.H = d.H; hv.W = d.W; hv.Wp = d.Wp;
     float* fw = lists + ((size_t)((b * d.C + c) * 2 + 0) * 7) * d.hw;
     float* bw = lists + ((size_t)((b * d.C + c) * 2 + 1) * 7) * d.hw;
     const long long kp_a = skeleton[2 * c], kp_b = skeleton[2 * c + 1];
@@ -429,8 +485,8 @@ __global__ void __launch_bounds__(NT) k_caf_scored(const float* __restrict__ caf
                 s1 = cf[6 * d.hw + idx] * st; s2 = cf[7 * d.hw + idx] * st;
                 cfw = cc; cbw = cc;
                 if (!no_rescore) {
-                    const float fhr = cifhr_value(hr, d.F, d.H, d.W, d.Wp, revision, kp_b, x2, y2, 0.0f);
-                    const float bhr = cifhr_value(hr, d.F, d.H, d.W, d.Wp, revision, kp_a, x1, y1, 0.0f);
+                    const float fhr = cifhr_value(hv, revision, kp_b, x2, y2, 0.0f);
+                    const float bhr = cifhr_value(hv, revision, kp_a, x1, y1, 0.0f);
                     cfw = (float)((double)cc * (cif_floor + (1.0 - cif_floor) * (double)fhr));
                     cbw = (float)((double)cc * (cif_floor + (1.0 - cif_floor) * (double)bhr));
                 }
@@ -996,26 +1052,43 @@ __global__ void __launch_bounds__(NT) k_nms(Dims d, GrowParams gp, Joint* __rest
     if (tid == 0) out_counts[b] = kept;
 }
 
-// pack every image's annotations contiguously for one small D2H copy
+// Pack the results of all images into ONE device buffer so that a single small D2H copy fetches them:
+//   int32 header: counts[B] | flags[B] | offsets[B+1]   (padded to 16 bytes)
+//   records     : total x (K+1) float4 -- K joints (v,x,y,s) then {id (int64 bits in .x,.y), 0, 0}
+__device__ __host__ inline size_t result_header_bytes(int B) { return ((size_t)(3 * B + 1) * 4 + 15) & ~(size_t)15; }
+
 __global__ void __launch_bounds__(NT) k_pack(Dims d, const float4* __restrict__ out_ann,
                                              const long long* __restrict__ out_ids,
-                                             const int* __restrict__ out_counts,
-                                             float4* __restrict__ packed_ann, long long* __restrict__ packed_ids,
-                                             int* __restrict__ offsets) {
+                                             const int* __restrict__ out_counts, const int* __restrict__ flags,
+                                             unsigned char* __restrict__ result) {
     __shared__ int s_off;
     const int b = blockIdx.x, tid = threadIdx.x;
+    int* hdr = reinterpret_cast<int*>(result);
     if (tid == 0) {
         int off = 0;
         for (int i = 0; i < b; i++) off += out_counts[i];
         s_off = off;
-        offsets[b] = off;
-        if (b == d.B - 1) offsets[d.B] = off + out_counts[b];
+        hdr[b] = out_counts[b];
+        hdr[d.B + b] = flags[b];
+        hdr[2 * d.B + b] = off;
+        if (b == d.B - 1) hdr[3 * d.B] = off + out_counts[b];
     }
     __syncthreads();
     const int off = s_off, n = out_counts[b];
+    float4* rec = reinterpret_cast<float4*>(result + result_header_bytes(d.B));
     const float4* src = out_ann + (size_t)b * d.max_ann * d.K;
-    for (int i = tid; i < n * d.K; i += NT) packed_ann[(size_t)off * d.K + i] = src[i];
-    for (int i = tid; i < n; i += NT) packed_ids[off + i] = out_ids[(size_t)b * d.max_ann + i];
+    const int R = d.K + 1;
+    for (int i = tid; i < n * R; i += NT) {
+        const int a = i / R, k = i - a * R;
+        float4 v;
+        if (k < d.K) {
+            v = src[(size_t)a * d.K + k];
+        } else {
+            const long long id = out_ids[(size_t)b * d.max_ann + a];
+            v = make_float4(__int_as_float((int)(id & 0xffffffffLL)), __int_as_float((int)(id >> 32)), 0.f, 0.f);
+        }
+        rec[(size_t)(off + a) * R + k] = v;
+    }
 }
 
 __global__ void k_blend_single(const float* __restrict__ L, int n, double x, double y, double s,
@@ -1047,6 +1120,8 @@ struct pifpaf_decoder {
     // workspace
     float* d_cifhr = nullptr;
     float4* d_cells = nullptr; int4* d_boxes = nullptr; int* d_cell_counts = nullptr;
+    unsigned* d_tile_epoch = nullptr; int* d_worklist = nullptr; int* d_work_count = nullptr;
+    unsigned hr_epoch = 0; size_t tile_epoch_elems = 0; int n_sm = 148;
     float* d_seg_v = nullptr; float4* d_seg_xys = nullptr; int* d_seg_counts = nullptr;
     unsigned *d_keys_a = nullptr, *d_vals_a = nullptr, *d_keys_b = nullptr, *d_vals_b = nullptr;
     int* d_seed_f = nullptr; float4* d_seed_vxys = nullptr; int* d_n_seeds = nullptr;
@@ -1054,13 +1129,18 @@ struct pifpaf_decoder {
     unsigned char* d_occ = nullptr; size_t occ_bytes = 0;
     Joint* d_anns = nullptr; long long* d_ann_ids = nullptr; int* d_n_anns = nullptr; int* d_flags = nullptr;
     float4* d_out_ann = nullptr; long long* d_out_ids = nullptr; int* d_out_counts = nullptr;
-    float4* d_packed_ann = nullptr; long long* d_packed_ids = nullptr; int* d_offsets = nullptr;
+    // packed results, double buffered (device + pinned host + event) so that a fetch can overlap the next decode
+    unsigned char* d_result[2] = {nullptr, nullptr};
+    unsigned char* h_result[2] = {nullptr, nullptr};
+    cudaEvent_t ev_result[2] = {nullptr, nullptr};
+    size_t result_bytes = 0, prefix_bytes = 0;
+    int cur_result = 0;          // buffer the next decode writes
+    int n_begun = 0, n_ended = 0;   // fetch_begin / fetch_end counters (at most 2 outstanding)
+    int slot_batch[2] = {0, 0};
     // single-image host path
     float *d_in_cif = nullptr, *d_in_caf = nullptr, *d_in_init = nullptr; long long* d_in_init_ids = nullptr;
     int* d_in_init_count = nullptr; int in_init_cap = 0;
     // pinned staging
-    int* h_meta = nullptr;            // counts[B], flags[B], offsets[B+1], n_anns[B]
-    float* h_packed_ann = nullptr; long long* h_packed_ids = nullptr;
     cudaStream_t own_stream = nullptr;
     unsigned epoch = 1;               // occupancy tags: epoch (seed loop), epoch+1 (NMS)
     Dims last{};
@@ -1116,16 +1196,18 @@ void pifpaf_decoder_destroy(pifpaf_decoder_t* dec) {
     if (!dec) return;
     cudaSetDevice(dec->device);
     void* dev_ptrs[] = {dec->d_skeleton, dec->d_adj_start, dec->d_adj_edge, dec->d_edge_lookup, dec->d_pair_id,
-        dec->d_cifhr, dec->d_cells, dec->d_boxes, dec->d_cell_counts, dec->d_seg_v, dec->d_seg_xys,
+        dec->d_cifhr, dec->d_cells, dec->d_boxes, dec->d_cell_counts, dec->d_tile_epoch, dec->d_worklist,
+        dec->d_work_count, dec->d_seg_v, dec->d_seg_xys,
         dec->d_seg_counts, dec->d_keys_a, dec->d_vals_a, dec->d_keys_b, dec->d_vals_b, dec->d_seed_f,
         dec->d_seed_vxys, dec->d_n_seeds, dec->d_lists, dec->d_list_counts, dec->d_occ, dec->d_anns,
         dec->d_ann_ids, dec->d_n_anns, dec->d_flags, dec->d_out_ann, dec->d_out_ids, dec->d_out_counts,
-        dec->d_packed_ann, dec->d_packed_ids, dec->d_offsets, dec->d_in_cif, dec->d_in_caf, dec->d_in_init,
+        dec->d_result[0], dec->d_result[1], dec->d_in_cif, dec->d_in_caf, dec->d_in_init,
         dec->d_in_init_ids, dec->d_in_init_count};
     for (void* p : dev_ptrs) if (p) cudaFree(p);
-    if (dec->h_meta) cudaFreeHost(dec->h_meta);
-    if (dec->h_packed_ann) cudaFreeHost(dec->h_packed_ann);
-    if (dec->h_packed_ids) cudaFreeHost(dec->h_packed_ids);
+    for (int i = 0; i < 2; i++) {
+        if (dec->h_result[i]) cudaFreeHost(dec->h_result[i]);
+        if (dec->ev_result[i]) cudaEventDestroy(dec->ev_result[i]);
+    }
     if (dec->own_stream) cudaStreamDestroy(dec->own_stream);
     delete dec;
 }
@@ -1211,6 +1293,16 @@ int pifpaf_decoder_create(pifpaf_decoder_t** out, int32_t device, int32_t n_keyp
     const size_t Wpm = (Wm + TILE - 1) / TILE * TILE;
     ALLOC(dec->d_cifhr, B * F * Hm * Wpm);
     ALLOC(dec->d_cells, B * F * hw); ALLOC(dec->d_boxes, B * F * hw); ALLOC(dec->d_cell_counts, B * F);
+    {
+        const size_t tiles_max = (Wpm / TILE) * ((Hm + TILE - 1) / TILE);
+        dec->tile_epoch_elems = B * F * tiles_max;
+        ALLOC(dec->d_tile_epoch, dec->tile_epoch_elems); ALLOC(dec->d_worklist, dec->tile_epoch_elems);
+        ALLOC(dec->d_work_count, 1);
+        TRY_D(cudaMemset(dec->d_tile_epoch, 0, sizeof(unsigned) * dec->tile_epoch_elems));
+        cudaDeviceProp prop;
+        TRY_D(cudaGetDeviceProperties(&prop, device));
+        dec->n_sm = prop.multiProcessorCount;
+    }
     ALLOC(dec->d_seg_v, B * F * hw); ALLOC(dec->d_seg_xys, B * F * hw); ALLOC(dec->d_seg_counts, B * F);
     ALLOC(dec->d_keys_a, B * F * hw); ALLOC(dec->d_vals_a, B * F * hw);
     ALLOC(dec->d_keys_b, B * F * hw); ALLOC(dec->d_vals_b, B * F * hw);
@@ -1223,13 +1315,17 @@ int pifpaf_decoder_create(pifpaf_decoder_t** out, int32_t device, int32_t n_keyp
     const size_t A = max_annotations;
     ALLOC(dec->d_anns, B * A * K); ALLOC(dec->d_ann_ids, B * A); ALLOC(dec->d_n_anns, B); ALLOC(dec->d_flags, B);
     ALLOC(dec->d_out_ann, B * A * K); ALLOC(dec->d_out_ids, B * A); ALLOC(dec->d_out_counts, B);
-    ALLOC(dec->d_packed_ann, B * A * K); ALLOC(dec->d_packed_ids, B * A); ALLOC(dec->d_offsets, B + 1);
+    dec->result_bytes = result_header_bytes((int)B) + B * A * (K + 1) * sizeof(float4);
+    // one async D2H copies the header and this much payload; the (rare) rest is fetched on demand
+    dec->prefix_bytes = std::min(dec->result_bytes, result_header_bytes((int)B) + (size_t)512 * 1024);
+    for (int i = 0; i < 2; i++) {
+        ALLOC(dec->d_result[i], dec->result_bytes);
+        TRY_D(cudaMallocHost(reinterpret_cast<void**>(&dec->h_result[i]), dec->result_bytes));
+        TRY_D(cudaEventCreateWithFlags(&dec->ev_result[i], cudaEventDisableTiming));
+    }
     ALLOC(dec->d_in_cif, (size_t)F * 5 * hw); ALLOC(dec->d_in_caf, (size_t)C * 8 * hw);
     dec->in_init_cap = max_annotations;
     ALLOC(dec->d_in_init, A * K * 4); ALLOC(dec->d_in_init_ids, A); ALLOC(dec->d_in_init_count, 1);
-    TRY_D(cudaMallocHost(reinterpret_cast<void**>(&dec->h_meta), sizeof(int) * (4 * B + 2)));
-    TRY_D(cudaMallocHost(reinterpret_cast<void**>(&dec->h_packed_ann), sizeof(float4) * B * A * K));
-    TRY_D(cudaMallocHost(reinterpret_cast<void**>(&dec->h_packed_ids), sizeof(long long) * B * A));
     TRY_D(cudaStreamCreateWithFlags(&dec->own_stream, cudaStreamNonBlocking));
 
     const size_t gs = grow_smem_bytes(K, C);
@@ -1280,20 +1376,27 @@ int pifpaf_decoder_decode_device(pifpaf_decoder_t* dec, const float* cif_dev, co
     gp.nms_keypoint_threshold = p.nms_keypoint_threshold;
     Graph gr{dec->d_skeleton, dec->d_adj_start, dec->d_adj_edge, dec->d_edge_lookup, dec->d_pair_id};
 
-    // CifHr (src/cifcaf.cpp:140-142: accumulate(cif, stride, min_scale 0.0, factor 1.0))
-    if (p.cifhr_ablation_skip) {
-        PIFPAF_CUDA_TRY(cudaMemsetAsync(dec->d_cifhr, 0, sizeof(float) * (size_t)d.B * d.F * d.H * d.Wp, st));
-    } else {
+    // CifHr (src/cifcaf.cpp:140-142: accumulate(cif, stride, min_scale 0.0, factor 1.0)).  A new epoch
+    // invalidates every tile (== the fresh zeroed buffer of a new reference instance) without touching memory.
+    if (++dec->hr_epoch == 0) {
+        PIFPAF_CUDA_TRY(cudaMemsetAsync(dec->d_tile_epoch, 0, sizeof(unsigned) * dec->tile_epoch_elems, st));
+        dec->hr_epoch = 1;
+    }
+    const unsigned hr_epoch = dec->hr_epoch;
+    if (!p.cifhr_ablation_skip) {
         const float min_scale_f = (float)(0.0 / (double)cif_stride);
+        PIFPAF_CUDA_TRY(cudaMemsetAsync(dec->d_work_count, 0, sizeof(int), st));
         k_cif_compact<<<dim3(d.F, d.B), NT, 0, st>>>(cif_dev, d, p.cifhr_threshold, (long long)p.cifhr_neighbors,
-                                                     min_scale_f, 1.0, dec->d_cells, dec->d_boxes, dec->d_cell_counts);
+                                                     min_scale_f, 1.0, dec->d_cells, dec->d_boxes, dec->d_cell_counts,
+                                                     dec->d_tile_epoch, hr_epoch, dec->d_worklist, dec->d_work_count);
         PIFPAF_LAUNCH_CHECK();
-        k_cifhr_tiles<<<dim3(d.tiles_x * d.tiles_y, d.F, d.B), NT, 0, st>>>(d, p.cifhr_revision, dec->d_cells,
-                                                                            dec->d_boxes, dec->d_cell_counts, dec->d_cifhr);
+        k_cifhr_tiles<<<dec->n_sm * 8, NT, 0, st>>>(d, p.cifhr_revision, dec->d_cells, dec->d_boxes,
+                                                    dec->d_cell_counts, dec->d_worklist, dec->d_work_count, dec->d_cifhr);
         PIFPAF_LAUNCH_CHECK();
     }
     // seeds (src/cifcaf.cpp:144-148)
-    k_seed_candidates<<<dim3(d.F, d.B), NT, 0, st>>>(cif_dev, d, dec->d_cifhr, p.cifhr_revision, p.seed_threshold,
+    k_seed_candidates<<<dim3(d.F, d.B), NT, 0, st>>>(cif_dev, d, dec->d_cifhr, dec->d_tile_epoch, hr_epoch,
+                                                     p.cifhr_revision, p.seed_threshold,
                                                      p.seeds_ablation_nms, p.seeds_ablation_no_rescore,
                                                      dec->d_seg_v, dec->d_seg_xys, dec->d_seg_counts);
     PIFPAF_LAUNCH_CHECK();
@@ -1304,8 +1407,8 @@ int pifpaf_decoder_decode_device(pifpaf_decoder_t* dec, const float* cif_dev, co
     PIFPAF_LAUNCH_CHECK();
     // caf scored (src/cifcaf.cpp:153-161: CafScored(cifhr, rev, -1.0, 0.1))
     if (d.C > 0) {
-        k_caf_scored<<<dim3(d.C, d.B), NT, 0, st>>>(caf_dev, d, dec->d_skeleton, dec->d_cifhr, p.cifhr_revision,
-                                                    p.caf_score_th, p.caf_cif_floor, p.caf_ablation_no_rescore,
+        k_caf_scored<<<dim3(d.C, d.B), NT, 0, st>>>(caf_dev, d, dec->d_skeleton, dec->d_cifhr, dec->d_tile_epoch,
+                                                    hr_epoch, p.cifhr_revision, p.caf_score_th, p.caf_cif_floor, p.caf_ablation_no_rescore,
                                                     dec->d_lists, dec->d_list_counts);
         PIFPAF_LAUNCH_CHECK();
     }
@@ -1318,8 +1421,8 @@ int pifpaf_decoder_decode_device(pifpaf_decoder_t* dec, const float* cif_dev, co
     if (p.force_complete && d.C > 0) {
         // src/cifcaf.cpp:414-426: CafScored(cifhr, rev, force_complete_caf_th, 0.1); score_th_ >= 0 ? it : default
         const double th = p.force_complete_caf_th >= 0.0 ? p.force_complete_caf_th : p.caf_score_th;
-        k_caf_scored<<<dim3(d.C, d.B), NT, 0, st>>>(caf_dev, d, dec->d_skeleton, dec->d_cifhr, p.cifhr_revision,
-                                                    th, 0.1, p.caf_ablation_no_rescore, dec->d_lists, dec->d_list_counts);
+        k_caf_scored<<<dim3(d.C, d.B), NT, 0, st>>>(caf_dev, d, dec->d_skeleton, dec->d_cifhr, dec->d_tile_epoch,
+                                                    hr_epoch, p.cifhr_revision, th, 0.1, p.caf_ablation_no_rescore, dec->d_lists, dec->d_list_counts);
         PIFPAF_LAUNCH_CHECK();
         k_force_complete<<<d.B, NT, gs, st>>>(d, gr, gp, dec->d_lists, dec->d_list_counts, dec->d_anns, dec->d_n_anns);
         PIFPAF_LAUNCH_CHECK();
@@ -1328,33 +1431,60 @@ int pifpaf_decoder_decode_device(pifpaf_decoder_t* dec, const float* cif_dev, co
     k_nms<<<d.B, NT, ns, st>>>(d, gp, dec->d_anns, dec->d_ann_ids, dec->d_n_anns, dec->d_occ, tag_nms,
                                dec->d_out_ann, dec->d_out_ids, dec->d_out_counts);
     PIFPAF_LAUNCH_CHECK();
-    k_pack<<<d.B, NT, 0, st>>>(d, dec->d_out_ann, dec->d_out_ids, dec->d_out_counts, dec->d_packed_ann,
-                               dec->d_packed_ids, dec->d_offsets);
+    k_pack<<<d.B, NT, 0, st>>>(d, dec->d_out_ann, dec->d_out_ids, dec->d_out_counts, dec->d_flags,
+                               dec->d_result[dec->cur_result]);
     PIFPAF_LAUNCH_CHECK();
     return PIFPAF_OK;
 }
 
-int pifpaf_decoder_fetch(pifpaf_decoder_t* dec, int32_t* counts, float* ann, int64_t* ids,
-                         int32_t ann_cap, void* stream_v) {
+int pifpaf_decoder_fetch_begin(pifpaf_decoder_t* dec, void* stream_v) {
     PIFPAF_CHECK_ARG(dec != nullptr && dec->has_last, "no decode to fetch");
-    PIFPAF_CHECK_ARG(counts != nullptr, "counts is null");
+    PIFPAF_CHECK_ARG(dec->n_begun - dec->n_ended < 2, "at most two fetches may be outstanding");
     PIFPAF_CUDA_TRY(cudaSetDevice(dec->device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
-    const Dims& d = dec->last;
-    const int B = d.B;
-    int* h_counts = dec->h_meta; int* h_flags = dec->h_meta + B; int* h_off = dec->h_meta + 2 * B;
-    PIFPAF_CUDA_TRY(cudaMemcpyAsync(h_counts, dec->d_out_counts, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
-    PIFPAF_CUDA_TRY(cudaMemcpyAsync(h_flags, dec->d_flags, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
-    PIFPAF_CUDA_TRY(cudaMemcpyAsync(h_off, dec->d_offsets, sizeof(int) * (B + 1), cudaMemcpyDeviceToHost, st));
-    PIFPAF_CUDA_TRY(cudaStreamSynchronize(st));
+    const int slot = dec->cur_result;
+    PIFPAF_CUDA_TRY(cudaMemcpyAsync(dec->h_result[slot], dec->d_result[slot], dec->prefix_bytes,
+                                    cudaMemcpyDeviceToHost, st));
+    PIFPAF_CUDA_TRY(cudaEventRecord(dec->ev_result[slot], st));
+    dec->slot_batch[slot] = dec->last.B;
+    dec->cur_result ^= 1;          // the next decode packs into the other buffer
+    dec->n_begun++;
+    return PIFPAF_OK;
+}
+
+int pifpaf_decoder_fetch_peek(pifpaf_decoder_t* dec, int32_t* counts) {
+    PIFPAF_CHECK_ARG(dec != nullptr && dec->n_begun > dec->n_ended, "fetch_peek without fetch_begin");
+    PIFPAF_CHECK_ARG(counts != nullptr, "counts is null");
+    PIFPAF_CUDA_TRY(cudaSetDevice(dec->device));
+    const int outstanding = dec->n_begun - dec->n_ended;
+    const int slot = (outstanding == 2) ? dec->cur_result : (dec->cur_result ^ 1);
+    PIFPAF_CUDA_TRY(cudaEventSynchronize(dec->ev_result[slot]));
+    const int* hdr = reinterpret_cast<const int*>(dec->h_result[slot]);
+    for (int b = 0; b < dec->slot_batch[slot]; b++) counts[b] = hdr[b];
+    return PIFPAF_OK;
+}
+
+int pifpaf_decoder_fetch_end(pifpaf_decoder_t* dec, int32_t* counts, float* ann, int64_t* ids, int32_t ann_cap) {
+    PIFPAF_CHECK_ARG(dec != nullptr && dec->n_begun > dec->n_ended, "fetch_end without fetch_begin");
+    PIFPAF_CHECK_ARG(counts != nullptr, "counts is null");
+    PIFPAF_CUDA_TRY(cudaSetDevice(dec->device));
+    // oldest outstanding slot: slots alternate, so it is cur_result when two are outstanding, else the other one
+    const int outstanding = dec->n_begun - dec->n_ended;
+    const int slot = (outstanding == 2) ? dec->cur_result : (dec->cur_result ^ 1);
+    PIFPAF_CUDA_TRY(cudaEventSynchronize(dec->ev_result[slot]));
+    dec->n_ended++;
+    const int B = dec->slot_batch[slot], K = dec->K;
+    const int* hdr = reinterpret_cast<const int*>(dec->h_result[slot]);
+    const int* h_counts = hdr; const int* h_flags = hdr + B; const int* h_off = hdr + 2 * B;
     const int total = h_off[B];
-    if (total > 0 && ann != nullptr) {
-        PIFPAF_CUDA_TRY(cudaMemcpyAsync(dec->h_packed_ann, dec->d_packed_ann, sizeof(float4) * (size_t)total * d.K,
-                                        cudaMemcpyDeviceToHost, st));
-        PIFPAF_CUDA_TRY(cudaMemcpyAsync(dec->h_packed_ids, dec->d_packed_ids, sizeof(long long) * (size_t)total,
-                                        cudaMemcpyDeviceToHost, st));
-        PIFPAF_CUDA_TRY(cudaStreamSynchronize(st));
+    const size_t hb = result_header_bytes(B), rec_bytes = (size_t)(K + 1) * sizeof(float4);
+    const size_t need = hb + (size_t)total * rec_bytes;
+    if (need > dec->prefix_bytes && ann != nullptr) {
+        PIFPAF_CUDA_TRY(cudaMemcpyAsync(dec->h_result[slot] + dec->prefix_bytes, dec->d_result[slot] + dec->prefix_bytes,
+                                        need - dec->prefix_bytes, cudaMemcpyDeviceToHost, dec->own_stream));
+        PIFPAF_CUDA_TRY(cudaStreamSynchronize(dec->own_stream));
     }
+    const unsigned char* recs = dec->h_result[slot] + hb;
     bool overflow = false;
     for (int b = 0; b < B; b++) {
         counts[b] = h_counts[b];
@@ -1362,16 +1492,25 @@ int pifpaf_decoder_fetch(pifpaf_decoder_t* dec, int32_t* counts, float* ann, int
         if (ann == nullptr) continue;
         int n = h_counts[b];
         if (n > ann_cap) { overflow = true; n = ann_cap; }
-        std::memcpy(ann + (size_t)b * ann_cap * d.K * 4, dec->h_packed_ann + (size_t)h_off[b] * d.K * 4,
-                    sizeof(float) * 4 * (size_t)n * d.K);
-        if (ids) std::memcpy(ids + (size_t)b * ann_cap, dec->h_packed_ids + h_off[b], sizeof(int64_t) * (size_t)n);
+        for (int a = 0; a < n; a++) {
+            const unsigned char* r = recs + (size_t)(h_off[b] + a) * rec_bytes;
+            std::memcpy(ann + ((size_t)b * ann_cap + a) * K * 4, r, sizeof(float) * 4 * (size_t)K);
+            if (ids) std::memcpy(ids + (size_t)b * ann_cap + a, r + sizeof(float4) * (size_t)K, sizeof(int64_t));
+        }
     }
     if (overflow) {
         pifpaf::set_error("annotation capacity exceeded (max_annotations=%d, ann_cap=%d): "
-                          "create the decoder with a larger max_annotations", d.max_ann, ann_cap);
+                          "create the decoder with a larger max_annotations", dec->max_ann, ann_cap);
         return PIFPAF_E_OVERFLOW;
     }
     return PIFPAF_OK;
+}
+
+int pifpaf_decoder_fetch(pifpaf_decoder_t* dec, int32_t* counts, float* ann, int64_t* ids,
+                         int32_t ann_cap, void* stream_v) {
+    int rc = pifpaf_decoder_fetch_begin(dec, stream_v);
+    if (rc != PIFPAF_OK) return rc;
+    return pifpaf_decoder_fetch_end(dec, counts, ann, ids, ann_cap);
 }
 
 int pifpaf_decoder_call(pifpaf_decoder_t* dec, const float* cif, int32_t cif_stride,
@@ -1415,6 +1554,9 @@ int pifpaf_decoder_tap_cifhr(pifpaf_decoder_t* dec, int32_t b, float* out, int64
     PIFPAF_CHECK_ARG(b >= 0 && b < d.B, "image index out of range");
     PIFPAF_CHECK_ARG(out != nullptr && out_elems >= (int64_t)d.F * d.H * d.W, "output buffer too small");
     PIFPAF_CUDA_TRY(cudaSetDevice(dec->device));
+    PIFPAF_CUDA_TRY(cudaDeviceSynchronize());
+    k_cifhr_materialize<<<dim3(d.tiles_x * d.tiles_y, d.F), NT>>>(d, b, dec->d_tile_epoch, dec->hr_epoch, dec->d_cifhr);
+    PIFPAF_LAUNCH_CHECK();
     PIFPAF_CUDA_TRY(cudaDeviceSynchronize());
     PIFPAF_CUDA_TRY(cudaMemcpy2D(out, sizeof(float) * d.W, dec->d_cifhr + (size_t)b * d.F * d.H * d.Wp,
                                  sizeof(float) * d.Wp, sizeof(float) * d.W, (size_t)d.F * d.H, cudaMemcpyDeviceToHost));

@@ -111,9 +111,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
 constexpr int BM = 128;          // UMMA M (cta_group::1): TMEM lane == tile row
 constexpr int BK = 64;           // one 128-byte swizzle atom of bf16 per smem row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;    // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
+constexpr int EPI_WARPS = 8;         // two warps per TMEM lane quadrant, each takes half of the columns
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;   // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..9 epilogue
 constexpr int CHUNK = 16;        // epilogue column chunk (one tcgen05.ld.32x32b.x16)
-constexpr int STAGE_WORDS = CHUNK + 1;   // padded staging row (words)
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 // start>>4 | LBO(ignored for swizzled K-major)=1 @16 | SBO = 1024 B (8 rows x 128 B) >>4 @32 | version 1 @46 | layout 2 @61
@@ -163,11 +163,42 @@ __device__ __forceinline__ float softplus_f(float x) {   // torch softplus beta=
 }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// store `cnt` (<= 16) consecutive 32-bit words from registers to p (4-byte aligned, LEAD words before the
+// first 16-byte boundary): scalar lead-in, 16-byte vectors, scalar tail.  Fully unrolled (no local memory).
+template <int LEAD>
+__device__ __forceinline__ void store_words(uint32_t* p, const uint32_t (&w)[CHUNK], int cnt) {
+#pragma unroll
+    for (int i = 0; i < LEAD; i++)
+        if (i < cnt) p[i] = w[i];
+#pragma unroll
+    for (int i = LEAD; i + 4 <= CHUNK; i += 4) {
+        if (i + 4 <= cnt) {
+            *reinterpret_cast<uint4*>(p + i) = make_uint4(w[i], w[i + 1], w[i + 2], w[i + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (i + j < cnt) p[i + j] = w[i + j];
+        }
+    }
+#pragma unroll
+    for (int i = LEAD + (CHUNK - LEAD) / 4 * 4; i < CHUNK; i++)
+        if (i < cnt) p[i] = w[i];
+}
+
 // Epilogue for one warp: 32 rows (lane == row) x CHUNK columns starting at GEMM column n0.
-// acc[] holds this lane's CHUNK accumulators.  stage: per-warp staging [32][STAGE_WORDS] words.
-__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, int m0, int n0, const float* acc,
-                                               uint32_t* stage, int lane) {
+// acc[] holds this lane's CHUNK accumulators.  Every lane writes its own row with 16-byte vector stores
+// (full 32-byte sectors), no shared-memory staging.
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, int m0, int n0, const float* acc, int lane) {
     const int m = m0 + lane;
+    float bv[CHUNK];
+    {
+        const float4* bp = reinterpret_cast<const float4*>(g.bias + n0);
+#pragma unroll
+        for (int j = 0; j < CHUNK / 4; j++) {
+            const float4 b4 = __ldg(bp + j);
+            bv[4 * j] = b4.x; bv[4 * j + 1] = b4.y; bv[4 * j + 2] = b4.z; bv[4 * j + 3] = b4.w;
+        }
+    }
     if (g.mode == MODE_HEADS) {
         if (m >= g.M) return;
         const int b = m / g.hw, pix = m - b * g.hw;
@@ -177,7 +208,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, int m0, int n0
             const int n = n0 + j;
             if (n >= g.N) break;
             const HeadCol hc = g.head_cols[n];
-            float v = acc[j] + g.bias[n];
+            float v = acc[j] + bv[j];
             if (hc.op == 1) v = sigmoid_f(v);
             else if (hc.op == 2) v += (float)x;
             else if (hc.op == 3) v += (float)y;
@@ -186,60 +217,53 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, int m0, int n0
         }
         return;
     }
-    uint32_t* my = stage + lane * STAGE_WORDS;
+    if (m >= g.M) return;
     if (g.mode == MODE_PLAIN) {
+        uint32_t w[CHUNK / 2];
 #pragma unroll
         for (int j = 0; j < CHUNK; j += 2) {
-            float a0 = acc[j] + g.bias[n0 + j], a1 = acc[j + 1] + g.bias[n0 + j + 1];
+            float a0 = acc[j] + bv[j], a1 = acc[j + 1] + bv[j + 1];
             if (g.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-            my[j >> 1] = pack_bf16(a0, a1);
+            w[j >> 1] = pack_bf16(a0, a1);
         }
-        __syncwarp();
-        // rows are CHUNK/2 = 8 words: 4 rows per warp store
-        uint32_t* outw = reinterpret_cast<uint32_t*>(g.out);
-        const int word0 = (g.out_col_off + n0) >> 1;
-        const int n_words = (min((g.N + 7) & ~7, n0 + CHUNK) - n0) >> 1;        // up to pad8(N)
-#pragma unroll
-        for (int it = 0; it < 8; it++) {
-            const int idx = it * 32 + lane;
-            const int r = idx >> 3, wd = idx & 7;
-            const int mr = m0 + r;
-            if (mr < g.M && wd < n_words && wd < (CHUNK >> 1))
-                outw[(size_t)mr * (g.ldo >> 1) + word0 + wd] = stage[r * STAGE_WORDS + wd];
-        }
-        __syncwarp();
+        // 16 bf16 = 32 bytes, 32-byte aligned (ldo % 8 == 0, out_col_off % 8 == 0, n0 % 16 == 0)
+        uint4* dst = reinterpret_cast<uint4*>(g.out + (size_t)m * g.ldo + g.out_col_off + n0);
+        const int n_pad8 = (g.N + 7) & ~7;
+        if (n0 < n_pad8) dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        if (n0 + 8 < n_pad8) dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
         return;
     }
     // MODE_SHUFFLE: word n = { src0[m][n] (logical channel 2n), conv[m][n] (logical 2n+1) }
-    {
-        uint4 s0 = make_uint4(0, 0, 0, 0), s1 = make_uint4(0, 0, 0, 0);
-        if (m < g.M) {
-            const uint4* sp = reinterpret_cast<const uint4*>(g.src0 + (size_t)m * g.ld0 + g.src0_col_off + n0);
-            s0 = sp[0];
-            s1 = sp[1];
-        }
-        const uint32_t sw[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const uint4* sp = reinterpret_cast<const uint4*>(g.src0 + (size_t)m * g.ld0 + g.src0_col_off + n0);
+    const uint4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+    const uint32_t sw[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    uint32_t w[CHUNK];
 #pragma unroll
-        for (int j = 0; j < CHUNK; j++) {
-            float a = acc[j] + g.bias[n0 + j];
-            if (g.relu) a = fmaxf(a, 0.f);
-            const uint32_t src_bits = (j & 1) ? (sw[j >> 1] >> 16) : (sw[j >> 1] & 0xffffu);
-            __nv_bfloat16 hb = __float2bfloat16_rn(a);
-            my[j] = src_bits | (static_cast<uint32_t>(*reinterpret_cast<unsigned short*>(&hb)) << 16);
+    for (int j = 0; j < CHUNK; j++) {
+        float a = acc[j] + bv[j];
+        if (g.relu) a = fmaxf(a, 0.f);
+        const uint32_t src_bits = (j & 1) ? (sw[j >> 1] >> 16) : (sw[j >> 1] & 0xffffu);
+        const __nv_bfloat16 hb = __float2bfloat16_rn(a);
+        w[j] = src_bits | (static_cast<uint32_t>(__bfloat16_as_ushort(hb)) << 16);
+    }
+    uint32_t* row = reinterpret_cast<uint32_t*>(g.out) + (size_t)m * (g.ldo >> 1) + (g.out_col_off >> 1);
+    const int cnt = min(CHUNK, g.N - n0);
+    const int shift = g.gap >> 1;                 // words inserted at the logical half boundary
+    const int n_split = (g.half + 1) >> 1;        // first n with 2n >= half
+    if (n0 + CHUNK <= n_split || shift == 0) {
+        store_words<0>(row + n0, w, cnt);
+    } else if (n0 >= n_split) {
+        uint32_t* p = row + n0 + shift;
+        switch (shift & 3) {                      // warp-uniform
+            case 0: store_words<0>(p, w, cnt); break;
+            case 1: store_words<3>(p, w, cnt); break;
+            case 2: store_words<2>(p, w, cnt); break;
+            default: store_words<1>(p, w, cnt); break;
         }
-        __syncwarp();
-        uint32_t* outw = reinterpret_cast<uint32_t*>(g.out);
+    } else {
 #pragma unroll
-        for (int it = 0; it < 16; it++) {
-            const int idx = it * 32 + lane;
-            const int r = idx >> 4, wd = idx & 15;
-            const int mr = m0 + r, n = n0 + wd;
-            if (mr < g.M && n < g.N) {
-                const int pw = n + ((2 * n >= g.half) ? (g.gap >> 1) : 0) + (g.out_col_off >> 1);
-                outw[(size_t)mr * (g.ldo >> 1) + pw] = stage[r * STAGE_WORDS + wd];
-            }
-        }
-        __syncwarp();
+        for (int j = 0; j < CHUNK; j++)
+            if (j < cnt) row[n0 + j + ((n0 + j) >= n_split ? shift : 0)] = w[j];
     }
 }
 
@@ -258,7 +282,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
     uint64_t* tmem_full = empty_bar + g.stages;                         // [2]
     uint64_t* tmem_empty = tmem_full + 2;                               // [2]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    uint32_t* staging = tmem_ptr + 4;                                   // [4 warps][32][STAGE_WORDS]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tmem_cols = (2 * g.block_n <= 32) ? 32 : (2 * g.block_n <= 64) ? 64 : (2 * g.block_n <= 128) ? 128
@@ -271,7 +294,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < g.stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-            for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+            for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], EPI_WARPS); }
             fence_barrier_init();
         }
         __syncwarp();
@@ -330,9 +353,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
             }
         }
     } else {
-        // ===== epilogue warps: TMEM lane quadrant = warp % 4 =====
+        // ===== epilogue warps: TMEM lane quadrant = warp % 4; warps 2..5 take the first half of the
+        // column chunks, warps 6..9 the second half =====
         const int q = warp & 3;
-        uint32_t* stage_w = staging + (warp - 2) * 32 * STAGE_WORDS;
+        const int n_chunks = g.block_n / CHUNK;
+        const int c_begin = (warp < 6) ? 0 : (n_chunks + 1) / 2;
+        const int c_end = (warp < 6) ? (n_chunks + 1) / 2 : n_chunks;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_blk = tile / g.n_blocks, n_blk = tile % g.n_blocks;
@@ -340,14 +366,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
             tcgen05_fence_after();
             const int m0 = m_blk * BM + q * 32;
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (uint32_t)(acc * g.block_n);
-            for (int c = 0; c < g.block_n; c += CHUNK) {
+            for (int ci = c_begin; ci < c_end; ci++) {
+                const int c = ci * CHUNK;
                 uint32_t v[CHUNK];
                 tmem_ld16(t_row + (uint32_t)c, v);
                 float accf[CHUNK];
 #pragma unroll
                 for (int j = 0; j < CHUNK; j++) accf[j] = __uint_as_float(v[j]);
                 const int n0 = n_blk * g.block_n + c;
-                if (n0 < ((g.N + 7) & ~7) || g.mode == MODE_HEADS) epilogue_chunk(g, m0, n0, accf, stage_w, lane);
+                if (n0 < ((g.N + 7) & ~7)) epilogue_chunk(g, m0, n0, accf, lane);
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -366,7 +393,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
 // ------------------------------------------------------------------ SIMT debug GEMM (tests only)
 // One warp per 32 rows x CHUNK columns; same epilogue as the tensor-core kernel.
 __global__ void __launch_bounds__(128) k_gemm_simt(GemmArgs g) {
-    __shared__ uint32_t staging[4 * 32 * STAGE_WORDS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_chunks = g.n_blocks * g.block_n / CHUNK;
     const long long total = (long long)((g.M + 31) / 32) * n_chunks;
@@ -388,8 +414,7 @@ __global__ void __launch_bounds__(128) k_gemm_simt(GemmArgs g) {
                 }
             }
         }
-        if (n0 < ((g.N + 7) & ~7) || g.mode == MODE_HEADS)
-            epilogue_chunk(g, m0, n0, acc, staging + warp * 32 * STAGE_WORDS, lane);
+        if (n0 < ((g.N + 7) & ~7)) epilogue_chunk(g, m0, n0, acc, lane);
     }
 }
 
@@ -402,6 +427,97 @@ struct DwArgs {
     int B, Hin, Win, Hout, Wout, C8, kernel, stride, pad, relu;
 };
 
+// bf16x2 word -> two floats (bf16 -> f32 is a 16-bit shift)
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+    f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+    f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+    f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
+    f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
+}
+
+// Register-tiled depthwise 5x5: one thread = 8 channels x DW_OX consecutive output pixels of one row.
+// Each input vector is loaded once and feeds every output/tap it touches; the 5x8 weights of a kernel row
+// stay in registers.  f32 accumulate.  (k == 5 only; other kernels take the generic path below.)
+constexpr int DW_OX = 4;
+constexpr int DW_OY = 8;
+
+template <int S>
+__global__ void __launch_bounds__(256) k_dwconv5(DwArgs a) {
+    constexpr int NCOL = (DW_OX - 1) * S + 5;
+    const int strips = (a.Wout + DW_OX - 1) / DW_OX;
+    const int ytiles = (a.Hout + DW_OY - 1) / DW_OY;
+    const long long total = (long long)a.B * ytiles * strips * DW_OY * a.C8;
+    const int C = a.C8 * 8;
+    // thread order: channels fastest (coalesced 16-byte vectors), then DW_OY vertically adjacent rows of the
+    // same strip (their 5-row input windows overlap -> L1 hits), then strips, row tiles, images
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(t % a.C8);
+        long long p = t / a.C8;
+        const int yl = (int)(p % DW_OY); p /= DW_OY;
+        const int sx = (int)(p % strips); p /= strips;
+        const int oy = (int)(p % ytiles) * DW_OY + yl;
+        const int b = (int)(p / ytiles);
+        if (oy >= a.Hout) continue;
+        const int ox0 = sx * DW_OX;
+        const int ix0 = ox0 * S - a.pad;
+        float acc[DW_OX][8];
+        {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + c8 * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + c8 * 8 + 4));
+#pragma unroll
+            for (int o = 0; o < DW_OX; o++) {
+                acc[o][0] = b0.x; acc[o][1] = b0.y; acc[o][2] = b0.z; acc[o][3] = b0.w;
+                acc[o][4] = b1.x; acc[o][5] = b1.y; acc[o][6] = b1.z; acc[o][7] = b1.w;
+            }
+        }
+#pragma unroll
+        for (int ky = 0; ky < 5; ky++) {
+            const int iy = oy * S - a.pad + ky;
+            if (iy < 0 || iy >= a.Hin) continue;
+            float w[5][8];
+#pragma unroll
+            for (int kx = 0; kx < 5; kx++) {
+                const float* wp = a.weight + (size_t)(ky * 5 + kx) * C + c8 * 8;
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
+                const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
+                w[kx][0] = w0.x; w[kx][1] = w0.y; w[kx][2] = w0.z; w[kx][3] = w0.w;
+                w[kx][4] = w1.x; w[kx][5] = w1.y; w[kx][6] = w1.z; w[kx][7] = w1.w;
+            }
+            const __nv_bfloat16* rowp = a.in + ((size_t)(b * a.Hin + iy) * a.Win) * a.ld_in + a.in_col_off + c8 * 8;
+#pragma unroll
+            for (int col = 0; col < NCOL; col++) {
+                const int ix = ix0 + col;
+                if (ix < 0 || ix >= a.Win) continue;
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(rowp + (size_t)ix * a.ld_in));
+                float f[8];
+                unpack8(v, f);
+#pragma unroll
+                for (int o = 0; o < DW_OX; o++) {
+                    const int kx = col - o * S;       // compile-time after unrolling
+                    if (kx < 0 || kx >= 5) continue;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) acc[o][j] = fmaf(f[j], w[kx][j], acc[o][j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < DW_OX; o++) {
+            const int ox = ox0 + o;
+            if (ox >= a.Wout) continue;
+            if (a.relu) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[o][j] = fmaxf(acc[o][j], 0.f);
+            }
+            uint4 ov;
+            ov.x = pack_bf16(acc[o][0], acc[o][1]); ov.y = pack_bf16(acc[o][2], acc[o][3]);
+            ov.z = pack_bf16(acc[o][4], acc[o][5]); ov.w = pack_bf16(acc[o][6], acc[o][7]);
+            *reinterpret_cast<uint4*>(a.out + ((size_t)(b * a.Hout + oy) * a.Wout + ox) * a.ld_out + a.out_col_off + c8 * 8) = ov;
+        }
+    }
+}
+
+// generic depthwise kxk (any kernel/stride): one output pixel x 8 channels per thread
 __global__ void __launch_bounds__(256) k_dwconv(DwArgs a) {
     const long long total = (long long)a.B * a.Hout * a.Wout * a.C8;
     const int C = a.C8 * 8;
@@ -631,12 +747,11 @@ void choose_block_n(int n_out, int* block_n, int* n_blocks) {
 }
 
 size_t gemm_smem_bytes(int block_n, int stages) {
-    return 1024 + (size_t)stages * (BM * BK * 2 + block_n * BK * 2) + (2 * stages + 4) * 8 + 16 +
-           4 * 32 * STAGE_WORDS * 4;
+    return 1024 + (size_t)stages * (BM * BK * 2 + block_n * BK * 2) + (2 * stages + 4) * 8 + 64;
 }
 
 int choose_stages(int block_n, int num_k_blocks) {
-    const size_t budget = 200 * 1024;
+    const size_t budget = 210 * 1024;
     int stages = 8;
     while (stages > 2 && gemm_smem_bytes(block_n, stages) > budget) stages--;
     (void)num_k_blocks;
@@ -903,9 +1018,17 @@ static int net_forward_impl(pifpaf_net_t* net, const float* images_dev, int32_t 
         } else if (op.kind == OP_DW) {
             DwArgs a = op.dw;
             a.B = batch;
-            const long long total = (long long)batch * a.Hout * a.Wout * a.C8;
-            const int grid = (int)std::min<long long>((total + 255) / 256, (long long)net->n_sm * 32);
-            k_dwconv<<<grid, 256, 0, st>>>(a);
+            if (a.kernel == 5 && (a.stride == 1 || a.stride == 2)) {
+                const long long total = (long long)batch * ((a.Hout + DW_OY - 1) / DW_OY) * DW_OY *
+                                        ((a.Wout + DW_OX - 1) / DW_OX) * a.C8;
+                const int grid = (int)std::min<long long>((total + 255) / 256, (long long)net->n_sm * 64);
+                if (a.stride == 1) k_dwconv5<1><<<grid, 256, 0, st>>>(a);
+                else k_dwconv5<2><<<grid, 256, 0, st>>>(a);
+            } else {
+                const long long total = (long long)batch * a.Hout * a.Wout * a.C8;
+                const int grid = (int)std::min<long long>((total + 255) / 256, (long long)net->n_sm * 32);
+                k_dwconv<<<grid, 256, 0, st>>>(a);
+            }
             PIFPAF_LAUNCH_CHECK();
         } else {
             GemmArgs g = op.g;

@@ -249,14 +249,26 @@ class CifCaf(metaclass=_Statics):
 
     def fetch(self, *, stream=None):
         """Wait for the last decode_batch_async and return its per-image results."""
-        B, K, cap = self._last_batch, self.n_keypoints, self.max_annotations
+        self.fetch_begin(stream=stream)
+        return self.fetch_end()
+
+    def fetch_begin(self, *, stream=None):
+        """Enqueue the (single, small) async D2H of the last decode's packed results; pair with fetch_end().
+        A further decode_batch_async may be enqueued in between (results are double buffered)."""
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        _lib.check(_lib.lib().pifpaf_decoder_fetch_begin(self._handle, ctypes.c_void_p(st.cuda_stream)))
+        self._begun = getattr(self, '_begun', [])
+        self._begun.append(self._last_batch)
+
+    def fetch_end(self):
+        B, K = self._begun.pop(0), self.n_keypoints
         counts = np.zeros((B,), dtype=np.int32)
+        _lib.check(_lib.lib().pifpaf_decoder_fetch_peek(self._handle, counts.ctypes.data))
+        cap = max(int(counts.max()) if B else 0, 1)
         ann = np.empty((B, cap, K, 4), dtype=np.float32)
         ids = np.empty((B, cap), dtype=np.int64)
-        _lib.check(_lib.lib().pifpaf_decoder_fetch(
-            self._handle, counts.ctypes.data, ann.ctypes.data, ids.ctypes.data, cap,
-            ctypes.c_void_p(st.cuda_stream)))
+        _lib.check(_lib.lib().pifpaf_decoder_fetch_end(
+            self._handle, counts.ctypes.data, ann.ctypes.data, ids.ctypes.data, cap))
         return [(torch.from_numpy(ann[b, :counts[b]].copy()), torch.from_numpy(ids[b, :counts[b]].copy()))
                 for b in range(B)]
 

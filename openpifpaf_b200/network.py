@@ -110,9 +110,12 @@ def plan_from_shell(shell):
     return plan
 
 
-def random_plan(base_name='shufflenetv2k16', heads=((17, 1, 1, 1), (19, 1, 2, 2)), seed=0):
+def random_plan(base_name='shufflenetv2k16', heads=((17, 1, 1, 1), (19, 1, 2, 2)), seed=0, confidence_bias=-4.0):
     """Random-init folded plan of the named architecture (no checkpoint can be downloaded here).
-    heads: (n_fields, n_confidences, n_vectors, n_scales) per head; vector offsets all True."""
+    heads: (n_fields, n_confidences, n_vectors, n_scales) per head; vector offsets all True.
+    confidence_bias is added to the bias of the confidence channels so that a random-init head emits a
+    sparse confidence map (sigmoid(-4) ~ 0.02) like a trained network's background; with a zero bias every
+    cell sits near 0.5 and passes every decoder threshold, which no trained model produces."""
     repeats, ch = SHUFFLENETV2K_CONFIGS[base_name]
     rng = np.random.Generator(np.random.PCG64(seed))
 
@@ -145,6 +148,7 @@ def random_plan(base_name='shufflenetv2k16', heads=((17, 1, 1, 1), (19, 1, 2, 2)
         ncomp = 1 + nconf + 2 * nvec + nsc
         w = (rng.standard_normal((nf * ncomp, ch[4])) * np.sqrt(1.0 / ch[4])).astype(np.float32)
         b = (rng.standard_normal(nf * ncomp) * 0.1).astype(np.float32)
+        b.reshape(nf, ncomp)[:, 1:1 + nconf] += np.float32(confidence_bias)
         plan['heads'].append({'w': w, 'b': b, 'n_fields': nf, 'n_comp': ncomp,
                               'ops': head_ops(nconf, nvec, nsc, (True,) * nvec), 'stride': 16})
     return plan

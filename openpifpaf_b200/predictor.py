@@ -29,6 +29,7 @@ class Predictor:
         self.decoder = _decoder.CifCaf(n_keypoints, sk, device=device)
         self.cif_head, self.caf_head = 0, 1
         self.stream = torch.cuda.Stream(device=self.device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
         self._dev_images = None
         self.last_nn_time = 0.0
         self.last_decoder_time = 0.0
@@ -56,6 +57,38 @@ class Predictor:
             result = self.decoder.fetch(stream=self.stream)
         self.last_nn_time = self.last_decoder_time = time.perf_counter() - t0
         return result
+
+
+    def batches(self, host_batches):
+        """Pipelined variant of `batch` over an iterable of host image batches (what Predictor.dataloader /
+        enumerated_dataloader does in the reference, predictor.py:118-153): the H2D copy of batch i+1 runs on a
+        copy stream under the forward+decode of batch i, and the (tiny) result D2H of batch i is waited for
+        only after batch i+1 has been enqueued.  Yields per-batch results in order."""
+        dev, copied, consumed = [None, None], [None, None], [None, None]
+        outstanding = 0
+        for i, host in enumerate(host_batches):
+            s = i % 2
+            if dev[s] is None or dev[s].shape != host.shape:
+                dev[s] = torch.empty(host.shape, dtype=torch.float32, device=self.device)
+                copied[s], consumed[s] = torch.cuda.Event(), None
+            with torch.cuda.stream(self.copy_stream):
+                if consumed[s] is not None:
+                    self.copy_stream.wait_event(consumed[s])
+                dev[s].copy_(host, non_blocking=True)
+                copied[s].record(self.copy_stream)
+            with torch.cuda.stream(self.stream):
+                self.stream.wait_event(copied[s])
+                self.batch_device(dev[s])
+                consumed[s] = torch.cuda.Event()
+                consumed[s].record(self.stream)
+                self.decoder.fetch_begin(stream=self.stream)
+            outstanding += 1
+            if outstanding == 2:
+                yield self.decoder.fetch_end()
+                outstanding -= 1
+        while outstanding:
+            yield self.decoder.fetch_end()
+            outstanding -= 1
 
 
 def from_shell(shell, in_h, in_w, max_batch, *, device=0):

@@ -92,3 +92,18 @@ def test_predictor_end_to_end_host_buffers():
     for b in range(4):
         oa, _ = oc.decode(cif[b], 16, caf[b], 16, sk, 17, params=p)
         helpers.assert_annotations_close(res[b][0].numpy(), oa, f'image {b}')
+
+
+def test_pipelined_batches_equal_sequential():
+    """Predictor.batches (H2D / compute overlap, double-buffered results) yields what Predictor.batch yields."""
+    plan = network.random_plan('shufflenetv2k16', seed=0, confidence_bias=0.0)
+    net = network.CompiledNet(plan, 161, 161, 3)
+    pred = predictor.Predictor(net, constants.COCO_N_KEYPOINTS, constants.COCO_PERSON_SKELETON)
+    g = torch.Generator().manual_seed(5)
+    hosts = [torch.randn(3, 3, 161, 161, generator=g).pin_memory() for _ in range(5)]
+    want = [pred.batch(h) for h in hosts]
+    got = list(pred.batches(iter(hosts)))
+    assert len(got) == len(want) == 5
+    for rw, rg in zip(want, got):
+        for (aw, iw), (ag, ig) in zip(rw, rg):
+            assert torch.equal(aw, ag) and torch.equal(iw, ig)
