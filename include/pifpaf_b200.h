@@ -188,6 +188,15 @@ int pifpaf_net_conv1x1(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off,
                        int32_t out_tensor, int32_t out_col_off,
                        int32_t shuffle_src_tensor, int32_t shuffle_src_col_off);
 
+/* Dense kxk conv (k <= 7, stride 1 or 2) as an implicit GEMM on tensor cores (torchvision ResNet blocks behind
+ * basenetworks.py:71-150): reads channels [in_col_off, in_col_off+c_in) of in_tensor through a 4-D TMA map
+ * (zero padding by out-of-bounds fill); weight [n_out][c_in][k][k] (torch layout); + bias (folded BN);
+ * optional residual add (residual_tensor >= 0) BEFORE the optional ReLU (BasicBlock / Bottleneck tail). */
+int pifpaf_net_conv(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off, int32_t c_in,
+                    int32_t kernel, int32_t stride, int32_t pad, int32_t n_out, const float* weight,
+                    const float* bias, int32_t relu, int32_t out_tensor, int32_t out_col_off,
+                    int32_t residual_tensor, int32_t residual_col_off);
+
 /* Depthwise kxk conv (basenetworks.py:228-231), weight [channels][k][k], + bias (folded BN) (+ReLU). */
 int pifpaf_net_dwconv(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off, int32_t channels,
                       int32_t kernel, int32_t stride, int32_t pad, const float* weight, const float* bias,

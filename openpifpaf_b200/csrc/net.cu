@@ -70,6 +70,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)),
+          "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
@@ -146,13 +154,35 @@ struct GemmArgs {
     // plain / shuffle
     __nv_bfloat16* out; int ldo; int out_col_off;
     const __nv_bfloat16* src0; int ld0; int src0_col_off; int half; int gap;
+    int src_tma;                 // pass-through tile arrives by TMA in shared memory (else read from global)
     // heads
     const HeadCol* head_cols;    // [n_blocks * block_n]
     float* head_base[4]; int head_planes[4];
     int hw, w;                   // pixels per image, field width
+    // implicit-GEMM convolution (conv_k > 0): one M tile = a PH x PW patch of output pixels of one image;
+    // K blocks run over taps x 64-channel blocks; A comes from a 4-D tensor map {C, W, H, B}
+    int conv_k, conv_stride, conv_pad, conv_cblocks;
+    int Hi, Wi, Ho, Wo, tiles_x, tiles_y;
+    // residual add before the ReLU (torchvision BasicBlock / Bottleneck): res[m][res_col_off + n]
+    const __nv_bfloat16* res; int ld_res; int res_col_off;
     // debug (SIMT) operand views
     const __nv_bfloat16* a; int lda; const __nv_bfloat16* wgt; int ldw;
 };
+
+constexpr int PH = 8, PW = 16;     // conv output patch per M tile (PH * PW == BM)
+
+// tile row (== TMEM lane) -> output row index m, or -1 if outside the tensor
+__device__ __forceinline__ int tile_row_to_m(const GemmArgs& g, int m_blk, int row) {
+    if (g.conv_k == 0) {
+        const int m = m_blk * BM + row;
+        return m < g.M ? m : -1;
+    }
+    const int per_img = g.tiles_x * g.tiles_y;
+    const int b = m_blk / per_img, t = m_blk - b * per_img;
+    const int oy = (t / g.tiles_x) * PH + row / PW, ox = (t % g.tiles_x) * PW + row % PW;
+    if (oy >= g.Ho || ox >= g.Wo) return -1;
+    return (b * g.Ho + oy) * g.Wo + ox;
+}
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -188,19 +218,22 @@ __device__ __forceinline__ void store_words(uint32_t* p, const uint32_t (&w)[CHU
 // Epilogue for one warp: 32 rows (lane == row) x CHUNK columns starting at GEMM column n0.
 // acc[] holds this lane's CHUNK accumulators.  Every lane writes its own row with 16-byte vector stores
 // (full 32-byte sectors), no shared-memory staging.
-__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, int m0, int n0, const float* acc, int lane) {
-    const int m = m0 + lane;
+// bias: pointer to this chunk's CHUNK biases (shared memory in the tensor-core kernel, global in the debug
+// kernel).  src_row: this lane's row of the pass-through tile at the chunk's first column (shared memory, filled
+// by TMA) or nullptr to read it from global memory.
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, int m, int n0, const float* acc,
+                                               const float* bias, const __nv_bfloat16* src_row) {
     float bv[CHUNK];
     {
-        const float4* bp = reinterpret_cast<const float4*>(g.bias + n0);
+        const float4* bp = reinterpret_cast<const float4*>(bias);
 #pragma unroll
         for (int j = 0; j < CHUNK / 4; j++) {
-            const float4 b4 = __ldg(bp + j);
+            const float4 b4 = bp[j];
             bv[4 * j] = b4.x; bv[4 * j + 1] = b4.y; bv[4 * j + 2] = b4.z; bv[4 * j + 3] = b4.w;
         }
     }
+    if (m < 0) return;
     if (g.mode == MODE_HEADS) {
-        if (m >= g.M) return;
         const int b = m / g.hw, pix = m - b * g.hw;
         const int y = pix / g.w, x = pix - y * g.w;
 #pragma unroll
@@ -217,12 +250,25 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, int m0, int n0
         }
         return;
     }
-    if (m >= g.M) return;
     if (g.mode == MODE_PLAIN) {
         uint32_t w[CHUNK / 2];
+        float rv[CHUNK];
+        if (g.res != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(g.res + (size_t)m * g.ld_res + g.res_col_off + n0);
+            const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+            const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                rv[2 * j] = __uint_as_float(rw[j] << 16);
+                rv[2 * j + 1] = __uint_as_float(rw[j] & 0xffff0000u);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < CHUNK; j++) rv[j] = 0.f;
+        }
 #pragma unroll
         for (int j = 0; j < CHUNK; j += 2) {
-            float a0 = acc[j] + bv[j], a1 = acc[j + 1] + bv[j + 1];
+            float a0 = acc[j] + bv[j] + rv[j], a1 = acc[j + 1] + bv[j + 1] + rv[j + 1];
             if (g.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
             w[j >> 1] = pack_bf16(a0, a1);
         }
@@ -234,8 +280,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, int m0, int n0
         return;
     }
     // MODE_SHUFFLE: word n = { src0[m][n] (logical channel 2n), conv[m][n] (logical 2n+1) }
-    const uint4* sp = reinterpret_cast<const uint4*>(g.src0 + (size_t)m * g.ld0 + g.src0_col_off + n0);
-    const uint4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+    const uint4* sp = src_row != nullptr
+        ? reinterpret_cast<const uint4*>(src_row)
+        : reinterpret_cast<const uint4*>(g.src0 + (size_t)m * g.ld0 + g.src0_col_off + n0);
+    const uint4 s0 = sp[0], s1 = sp[1];
     const uint32_t sw[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
     uint32_t w[CHUNK];
 #pragma unroll
@@ -269,19 +317,25 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, int m0, int n0
 
 // ------------------------------------------------------------------ tcgen05 GEMM
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmArgs g) {
+k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+          const __grid_constant__ CUtensorMap tmap_src, GemmArgs g) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // carve: [stages][A 16 KB | B block_n*128 B] then barriers, tmem ptr, staging
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int a_bytes = BM * BK * 2;
     const int b_bytes = g.block_n * BK * 2;
     const int stage_bytes = a_bytes + b_bytes;
-    unsigned char* tail = smem + (size_t)g.stages * stage_bytes;
+    // pass-through tiles of the fused shuffle: [2 accumulator stages][BM rows][block_n] bf16, filled by TMA
+    const int src_bytes = g.src_tma ? BM * g.block_n * 2 : 0;
+    unsigned char* src_tiles = smem + (size_t)g.stages * stage_bytes;
+    float* bias_s = reinterpret_cast<float*>(src_tiles + 2 * (size_t)src_bytes);   // [n_blocks * block_n]
+    unsigned char* tail = reinterpret_cast<unsigned char*>(bias_s + g.n_blocks * g.block_n);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);            // [stages]
     uint64_t* empty_bar = full_bar + g.stages;                          // [stages]
     uint64_t* tmem_full = empty_bar + g.stages;                         // [2]
     uint64_t* tmem_empty = tmem_full + 2;                               // [2]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* src_full = tmem_empty + 2;                                // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(src_full + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tmem_cols = (2 * g.block_n <= 32) ? 32 : (2 * g.block_n <= 64) ? 64 : (2 * g.block_n <= 128) ? 128
@@ -290,11 +344,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
+        if (g.src_tma) tma_prefetch_desc(&tmap_src);
     }
+    for (int i = threadIdx.x; i < g.n_blocks * g.block_n; i += GEMM_THREADS) bias_s[i] = g.bias[i];
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < g.stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-            for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], EPI_WARPS); }
+            for (int a = 0; a < 2; a++) {
+                mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], EPI_WARPS); mbar_init(&src_full[a], 1);
+            }
             fence_barrier_init();
         }
         __syncwarp();
@@ -311,16 +369,40 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
         // ===== TMA producer (one elected lane) =====
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
+            int sacc = 0; uint32_t sacc_phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m_blk = tile / g.n_blocks, n_blk = tile % g.n_blocks;
+                int cb = 0, cy = 0, cx = 0, cimg = 0;
+                if (g.conv_k > 0) {
+                    const int per_img = g.tiles_x * g.tiles_y;
+                    cimg = m_blk / per_img;
+                    const int t = m_blk - cimg * per_img;
+                    cy = (t / g.tiles_x) * PH * g.conv_stride - g.conv_pad;
+                    cx = (t % g.tiles_x) * PW * g.conv_stride - g.conv_pad;
+                }
                 for (int kb = 0; kb < g.num_k_blocks; kb++) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char* sa = smem + (size_t)stage * stage_bytes;
                     unsigned char* sb = sa + a_bytes;
                     mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-                    tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+                    if (g.conv_k > 0) {
+                        const int tap = kb / g.conv_cblocks;
+                        cb = kb - tap * g.conv_cblocks;
+                        tma_load_4d(sa, &tmap_a, &full_bar[stage], cb * BK, cx + tap % g.conv_k, cy + tap / g.conv_k, cimg);
+                    } else {
+                        tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+                    }
                     tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * g.block_n);
                     if (++stage == g.stages) { stage = 0; phase ^= 1; }
+                }
+                if (g.src_tma) {
+                    // pass-through tile of this output tile; its buffer is free once the epilogue that used this
+                    // accumulator stage two tiles ago has released it
+                    mbar_wait(&tmem_empty[sacc], sacc_phase ^ 1);
+                    mbar_expect_tx(&src_full[sacc], (uint32_t)src_bytes);
+                    tma_load_2d(src_tiles + (size_t)sacc * src_bytes, &tmap_src, &src_full[sacc],
+                                n_blk * g.block_n, m_blk * BM);
+                    if (++sacc == 2) { sacc = 0; sacc_phase ^= 1; }
                 }
             }
         }
@@ -364,7 +446,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
             const int m_blk = tile / g.n_blocks, n_blk = tile % g.n_blocks;
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
-            const int m0 = m_blk * BM + q * 32;
+            if (g.src_tma) mbar_wait(&src_full[acc], acc_phase);
+            const int m = tile_row_to_m(g, m_blk, q * 32 + lane);
+            const __nv_bfloat16* src_tile_row = reinterpret_cast<const __nv_bfloat16*>(
+                src_tiles + (size_t)acc * src_bytes) + (size_t)(q * 32 + lane) * g.block_n;
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (uint32_t)(acc * g.block_n);
             for (int ci = c_begin; ci < c_end; ci++) {
                 const int c = ci * CHUNK;
@@ -374,7 +459,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
 #pragma unroll
                 for (int j = 0; j < CHUNK; j++) accf[j] = __uint_as_float(v[j]);
                 const int n0 = n_blk * g.block_n + c;
-                if (n0 < ((g.N + 7) & ~7)) epilogue_chunk(g, m0, n0, accf, lane);
+                if (n0 < ((g.N + 7) & ~7))
+                    epilogue_chunk(g, m, n0, accf, bias_s + n0, g.src_tma ? src_tile_row + c : nullptr);
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -395,26 +481,48 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
 __global__ void __launch_bounds__(128) k_gemm_simt(GemmArgs g) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_chunks = g.n_blocks * g.block_n / CHUNK;
-    const long long total = (long long)((g.M + 31) / 32) * n_chunks;
+    const long long total = (long long)g.m_blocks * 4 * n_chunks;        // 4 row quarters per M tile
     for (long long job = (long long)blockIdx.x * 4 + warp; job < total; job += (long long)gridDim.x * 4) {
-        const int mb = (int)(job / n_chunks), ch = (int)(job % n_chunks);
-        const int m0 = mb * 32, n0 = ch * CHUNK;
-        const int m = m0 + lane;
+        const int ch = (int)(job % n_chunks);
+        const int mq = (int)(job / n_chunks);
+        const int m_blk = mq >> 2, row = (mq & 3) * 32 + lane;
+        const int n0 = ch * CHUNK;
+        const int m = tile_row_to_m(g, m_blk, row);
         float acc[CHUNK];
 #pragma unroll
         for (int j = 0; j < CHUNK; j++) acc[j] = 0.f;
-        if (m < g.M) {
-            for (int k = 0; k < g.K; k++) {
-                const float a = __bfloat162float(g.a[(size_t)m * g.lda + k]);
+        if (m >= 0) {
+            if (g.conv_k == 0) {
+                for (int k = 0; k < g.K; k++) {
+                    const float a = __bfloat162float(g.a[(size_t)m * g.lda + k]);
 #pragma unroll
-                for (int j = 0; j < CHUNK; j++) {
-                    const int n = n0 + j;
-                    const float wv = (n < g.N) ? __bfloat162float(g.wgt[(size_t)n * g.ldw + k]) : 0.f;
-                    acc[j] = fmaf(a, wv, acc[j]);
+                    for (int j = 0; j < CHUNK; j++) {
+                        const int n = n0 + j;
+                        const float wv = (n < g.N) ? __bfloat162float(g.wgt[(size_t)n * g.ldw + k]) : 0.f;
+                        acc[j] = fmaf(a, wv, acc[j]);
+                    }
+                }
+            } else {
+                const int ox = m % g.Wo, oy = (m / g.Wo) % g.Ho, b = m / (g.Wo * g.Ho);
+                for (int tap = 0; tap < g.conv_k * g.conv_k; tap++) {
+                    const int iy = oy * g.conv_stride - g.conv_pad + tap / g.conv_k;
+                    const int ix = ox * g.conv_stride - g.conv_pad + tap % g.conv_k;
+                    if (iy < 0 || iy >= g.Hi || ix < 0 || ix >= g.Wi) continue;
+                    const __nv_bfloat16* ap = g.a + ((size_t)(b * g.Hi + iy) * g.Wi + ix) * g.lda;
+                    for (int k = 0; k < g.K; k++) {
+                        const float a = __bfloat162float(ap[k]);
+#pragma unroll
+                        for (int j = 0; j < CHUNK; j++) {
+                            const int n = n0 + j;
+                            const float wv = (n < g.N)
+                                ? __bfloat162float(g.wgt[(size_t)n * g.ldw + (size_t)tap * g.conv_cblocks * BK + k]) : 0.f;
+                            acc[j] = fmaf(a, wv, acc[j]);
+                        }
+                    }
                 }
             }
         }
-        if (n0 < ((g.N + 7) & ~7)) epilogue_chunk(g, m0, n0, acc, lane);
+        if (n0 < ((g.N + 7) & ~7)) epilogue_chunk(g, m, n0, acc, g.bias + n0, nullptr);
     }
 }
 
@@ -513,6 +621,124 @@ __global__ void __launch_bounds__(256) k_dwconv5(DwArgs a) {
             ov.x = pack_bf16(acc[o][0], acc[o][1]); ov.y = pack_bf16(acc[o][2], acc[o][3]);
             ov.z = pack_bf16(acc[o][4], acc[o][5]); ov.w = pack_bf16(acc[o][6], acc[o][7]);
             *reinterpret_cast<uint4*>(a.out + ((size_t)(b * a.Hout + oy) * a.Wout + ox) * a.ld_out + a.out_col_off + c8 * 8) = ov;
+        }
+    }
+}
+
+// Depthwise 5x5 with TMA-staged input tiles: a persistent CTA walks (channel block, image, tile) work items; one
+// elected thread streams the (TH*S+4-S+1) x (TW*S+4-S+1) x 64-channel input window of the NEXT items into a
+// double-buffered shared-memory ring (4-D tensor map, out-of-bounds zero fill == the conv padding) while the
+// 256 threads (8 channel groups x 32 pixel lanes) compute OX outputs x 8 channels each from shared memory.
+template <int S, int OX, int TH, int TW>
+struct DwTile {
+    static constexpr int IH = (TH - 1) * S + 5, IW = (TW - 1) * S + 5;
+    static constexpr int BYTES = IH * IW * 64 * 2;
+    static constexpr int NCOL = (OX - 1) * S + 5;
+    static_assert(TH * (TW / OX) == 32, "32 pixel lanes");
+};
+
+template <int S, int OX, int TH, int TW>
+__global__ void __launch_bounds__(256, 2) k_dwconv5_tma(const __grid_constant__ CUtensorMap tmap_in, DwArgs a) {
+    using T = DwTile<S, OX, TH, TW>;
+    extern __shared__ __align__(128) unsigned char dsm_raw[];
+    unsigned char* dsm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dsm_raw) + 127) & ~uintptr_t(127));
+    __shared__ uint64_t full[2];
+    const int tid = threadIdx.x;
+    const int tiles_x = (a.Wout + TW - 1) / TW, tiles_y = (a.Hout + TH - 1) / TH;
+    const int cblks = (a.C8 + 7) / 8;
+    const int per_c = a.B * tiles_y * tiles_x;
+    const int total = per_c * cblks;
+    const int C = a.C8 * 8;
+
+    if (tid == 0) {
+        mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tmap_in);
+    }
+    __syncthreads();
+
+    auto issue = [&](int w, int buf) {
+        const int cblk = w / per_c; int r = w - cblk * per_c;
+        const int b = r / (tiles_y * tiles_x); r -= b * tiles_y * tiles_x;
+        const int ty = r / tiles_x, tx = r - ty * tiles_x;
+        mbar_expect_tx(&full[buf], (uint32_t)T::BYTES);
+        tma_load_4d(dsm + (size_t)buf * T::BYTES, &tmap_in, &full[buf], cblk * 64, tx * TW * S - a.pad,
+                    ty * TH * S - a.pad, b);
+    };
+
+    if (tid == 0) {
+        if ((int)blockIdx.x < total) issue(blockIdx.x, 0);
+        if ((int)(blockIdx.x + gridDim.x) < total) issue(blockIdx.x + gridDim.x, 1);
+    }
+    const int cg = tid & 7, pl = tid >> 3;            // channel group, pixel lane
+    const int yl = pl / (TW / OX), sx = pl % (TW / OX);
+    uint32_t phase[2] = {0, 0};
+    int it = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, it++) {
+        const int buf = it & 1;
+        const int cblk = w / per_c; int r = w - cblk * per_c;
+        const int b = r / (tiles_y * tiles_x); r -= b * tiles_y * tiles_x;
+        const int ty = r / tiles_x, tx = r - ty * tiles_x;
+        const int c0 = cblk * 64 + cg * 8;
+        mbar_wait(&full[buf], phase[buf]);
+        phase[buf] ^= 1;
+        const int oy = ty * TH + yl, ox0 = tx * TW + sx * OX;
+        if (c0 < C && oy < a.Hout && ox0 < a.Wout) {
+            const unsigned char* tile = dsm + (size_t)buf * T::BYTES;
+            float acc[OX][8];
+            {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + c0));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + c0 + 4));
+#pragma unroll
+                for (int o = 0; o < OX; o++) {
+                    acc[o][0] = b0.x; acc[o][1] = b0.y; acc[o][2] = b0.z; acc[o][3] = b0.w;
+                    acc[o][4] = b1.x; acc[o][5] = b1.y; acc[o][6] = b1.z; acc[o][7] = b1.w;
+                }
+            }
+#pragma unroll
+            for (int ky = 0; ky < 5; ky++) {
+                float wv[5][8];
+#pragma unroll
+                for (int kx = 0; kx < 5; kx++) {
+                    const float* wp = a.weight + (size_t)(ky * 5 + kx) * C + c0;
+                    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
+                    const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
+                    wv[kx][0] = w0.x; wv[kx][1] = w0.y; wv[kx][2] = w0.z; wv[kx][3] = w0.w;
+                    wv[kx][4] = w1.x; wv[kx][5] = w1.y; wv[kx][6] = w1.z; wv[kx][7] = w1.w;
+                }
+                const unsigned char* rowp = tile + ((size_t)(yl * S + ky) * T::IW + sx * OX * S) * 128 + cg * 16;
+#pragma unroll
+                for (int col = 0; col < T::NCOL; col++) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(rowp + (size_t)col * 128);
+                    float f[8];
+                    unpack8(v, f);
+#pragma unroll
+                    for (int o = 0; o < OX; o++) {
+                        const int kx = col - o * S;
+                        if (kx < 0 || kx >= 5) continue;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) acc[o][j] = fmaf(f[j], wv[kx][j], acc[o][j]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < OX; o++) {
+                const int ox = ox0 + o;
+                if (ox >= a.Wout) continue;
+                if (a.relu) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) acc[o][j] = fmaxf(acc[o][j], 0.f);
+                }
+                uint4 ov;
+                ov.x = pack_bf16(acc[o][0], acc[o][1]); ov.y = pack_bf16(acc[o][2], acc[o][3]);
+                ov.z = pack_bf16(acc[o][4], acc[o][5]); ov.w = pack_bf16(acc[o][6], acc[o][7]);
+                *reinterpret_cast<uint4*>(a.out + ((size_t)(b * a.Hout + oy) * a.Wout + ox) * a.ld_out + a.out_col_off + c0) = ov;
+            }
+        }
+        __syncthreads();                                // everyone is done with this buffer
+        if (tid == 0) {
+            const int wn = w + 2 * gridDim.x;
+            if (wn < total) issue(wn, buf);
         }
     }
 }
@@ -663,6 +889,69 @@ int make_tmap(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, 
     return PIFPAF_OK;
 }
 
+// 2-D bf16 row-major view, un-swizzled box [box_rows][box_cols] (dense rows in shared memory)
+int make_tmap_plain(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                    uint32_t box_cols, uint32_t box_rows) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (!fn) { pifpaf::set_error("cuTensorMapEncodeTiled entry point not available"); return PIFPAF_E_CUDA; }
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {ld * 2};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        pifpaf::set_error("cuTensorMapEncodeTiled (plain) failed (%d): rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r,
+                          (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols);
+        return PIFPAF_E_CUDA;
+    }
+    return PIFPAF_OK;
+}
+
+// 4-D bf16 NHWC activation view {C, W, H, B} for implicit-GEMM convolutions: box = 64 channels x the
+// input window of a PH x PW output patch, traversed with the conv stride
+int make_tmap_conv(CUtensorMap* map, const void* base, uint64_t c, uint64_t w, uint64_t h, uint64_t b, uint64_t ld,
+                   int stride) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (!fn) { pifpaf::set_error("cuTensorMapEncodeTiled entry point not available"); return PIFPAF_E_CUDA; }
+    const cuuint64_t dims[4] = {c, w, h, b};
+    const cuuint64_t strides[3] = {ld * 2, w * ld * 2, h * w * ld * 2};
+    const cuuint32_t box[4] = {BK, (cuuint32_t)((PW - 1) * stride + 1), (cuuint32_t)((PH - 1) * stride + 1), 1};
+    const cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        pifpaf::set_error("cuTensorMapEncodeTiled (conv) failed (%d): c=%llu w=%llu h=%llu b=%llu ld=%llu stride=%d",
+                          (int)r, (unsigned long long)c, (unsigned long long)w, (unsigned long long)h,
+                          (unsigned long long)b, (unsigned long long)ld, stride);
+        return PIFPAF_E_CUDA;
+    }
+    return PIFPAF_OK;
+}
+
+// 4-D bf16 NHWC view {C, W, H, B}, dense (un-swizzled) box of 64 channels x box_w x box_h pixels
+int make_tmap_dw(CUtensorMap* map, const void* base, uint64_t c, uint64_t w, uint64_t h, uint64_t b, uint64_t ld,
+                 uint32_t box_w, uint32_t box_h) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (!fn) { pifpaf::set_error("cuTensorMapEncodeTiled entry point not available"); return PIFPAF_E_CUDA; }
+    const cuuint64_t dims[4] = {c, w, h, b};
+    const cuuint64_t strides[3] = {ld * 2, w * ld * 2, h * w * ld * 2};
+    const cuuint32_t box[4] = {64, box_w, box_h, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        pifpaf::set_error("cuTensorMapEncodeTiled (dw) failed (%d): c=%llu w=%llu h=%llu b=%llu ld=%llu box=%ux%u", (int)r,
+                          (unsigned long long)c, (unsigned long long)w, (unsigned long long)h, (unsigned long long)b,
+                          (unsigned long long)ld, box_w, box_h);
+        return PIFPAF_E_CUDA;
+    }
+    return PIFPAF_OK;
+}
+
 struct Tensor { int h, w, c; __nv_bfloat16* data; };
 
 enum OpKind { OP_INPUT_CONV, OP_GEMM, OP_DW };
@@ -671,11 +960,12 @@ struct Op {
     OpKind kind;
     // gemm
     GemmArgs g{};
-    CUtensorMap tmap_a{}, tmap_b{};
-    int a_tensor = -1; int rows_per_image = 0;
+    CUtensorMap tmap_a{}, tmap_b{}, tmap_src{};
+    int a_tensor = -1; int rows_per_image = 0; int tiles_per_image = 0;
     size_t smem = 0;
     // dw
     DwArgs dw{};
+    CUtensorMap tmap_dw{}; bool dw_tma = false;
     // input conv
     InConvArgs ic{};
     int n_out_pixels = 0;
@@ -746,15 +1036,15 @@ void choose_block_n(int n_out, int* block_n, int* n_blocks) {
     *block_n = 16; *n_blocks = np / 16;
 }
 
-size_t gemm_smem_bytes(int block_n, int stages) {
-    return 1024 + (size_t)stages * (BM * BK * 2 + block_n * BK * 2) + (2 * stages + 4) * 8 + 64;
+size_t gemm_smem_bytes(int block_n, int n_blocks, int stages, bool shuffle) {
+    return 1024 + (size_t)stages * (BM * BK * 2 + block_n * BK * 2) + (shuffle ? 2 * (size_t)BM * block_n * 2 : 0) +
+           (size_t)n_blocks * block_n * 4 + (2 * stages + 6) * 8 + 64;
 }
 
-int choose_stages(int block_n, int num_k_blocks) {
-    const size_t budget = 210 * 1024;
-    int stages = 8;
-    while (stages > 2 && gemm_smem_bytes(block_n, stages) > budget) stages--;
-    (void)num_k_blocks;
+int choose_stages(int block_n, int n_blocks, int num_k_blocks, bool shuffle) {
+    const size_t budget = 222 * 1024;
+    int stages = std::min(8, std::max(2, num_k_blocks * 2));
+    while (stages > 2 && gemm_smem_bytes(block_n, n_blocks, stages, shuffle) > budget) stages--;
     return stages;
 }
 
@@ -782,11 +1072,11 @@ int emit_gemm(pifpaf_net* net, Op& op, int in_tensor, int in_col_off, int k_cols
     g.N = n_out; g.K = k_cols;
     g.block_n = block_n; g.n_blocks = n_blocks;
     g.num_k_blocks = (k_cols + BK - 1) / BK;
-    g.stages = choose_stages(block_n, g.num_k_blocks);
+    g.stages = choose_stages(block_n, n_blocks, g.num_k_blocks, false);
     g.bias = d_b;
     g.a = tin.data + in_col_off; g.lda = tin.c; g.wgt = d_w; g.ldw = k_pad;
     op.a_tensor = in_tensor; op.rows_per_image = tin.h * tin.w;
-    op.smem = gemm_smem_bytes(block_n, g.stages);
+    op.smem = gemm_smem_bytes(block_n, n_blocks, g.stages, false);
     op.flops_per_image = 2.0 * (double)op.rows_per_image * n_out * k_cols;
     op.bytes_per_image = (double)op.rows_per_image * k_cols * 2.0;      // A read once (bf16); outputs added by the caller
     op.weight_bytes = (double)n_out * k_cols * 2.0;
@@ -816,7 +1106,11 @@ int pifpaf_net_create(pifpaf_net_t** out, int32_t device, int32_t max_batch) {
     }
     pifpaf_net* net = new pifpaf_net();
     net->device = device; net->max_batch = max_batch; net->n_sm = prop.multiProcessorCount;
-    PIFPAF_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    PIFPAF_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    PIFPAF_CUDA_TRY(cudaFuncSetAttribute(k_dwconv5_tma<1, 4, 8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         2 * DwTile<1, 4, 8, 16>::BYTES + 128));
+    PIFPAF_CUDA_TRY(cudaFuncSetAttribute(k_dwconv5_tma<2, 2, 4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         2 * DwTile<2, 2, 4, 16>::BYTES + 128));
     *out = net;
     return PIFPAF_OK;
 }
@@ -909,7 +1203,80 @@ int pifpaf_net_conv1x1(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off,
         g.mode = MODE_SHUFFLE;
         g.src0 = ts.data; g.ld0 = ts.c; g.src0_col_off = shuffle_src_col_off;
         g.half = n_out; g.gap = pad8(n_out) - n_out;
+        g.src_tma = gemm_smem_bytes(g.block_n, g.n_blocks, 2, true) <= 222 * 1024 ? 1 : 0;
+        g.stages = choose_stages(g.block_n, g.n_blocks, g.num_k_blocks, g.src_tma != 0);
+        op.smem = gemm_smem_bytes(g.block_n, g.n_blocks, g.stages, g.src_tma != 0);
+        // pass-through tile [BM rows][block_n cols], dense rows in shared memory (no swizzle)
+        rc = make_tmap_plain(&op.tmap_src, ts.data + shuffle_src_col_off, (uint64_t)net->max_batch * ts.h * ts.w,
+                             (uint64_t)std::min(ts.c - shuffle_src_col_off, pad16(n_out)), (uint64_t)ts.c,
+                             (uint32_t)g.block_n, BM);
+        if (rc != PIFPAF_OK) return rc;
     }
+    net->ops.push_back(op);
+    return PIFPAF_OK;
+}
+
+int pifpaf_net_conv(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off, int32_t c_in,
+                    int32_t kernel, int32_t stride, int32_t pad, int32_t n_out, const float* weight,
+                    const float* bias, int32_t relu, int32_t out_tensor, int32_t out_col_off,
+                    int32_t residual_tensor, int32_t residual_col_off) {
+    PIFPAF_CHECK_ARG(net != nullptr && weight != nullptr, "null argument");
+    const int nt = (int)net->tensors.size();
+    PIFPAF_CHECK_ARG(in_tensor >= 0 && in_tensor < nt && out_tensor >= 0 && out_tensor < nt, "bad tensor id");
+    PIFPAF_CHECK_ARG(kernel >= 1 && kernel <= 7 && stride >= 1 && stride <= 2 && pad >= 0, "unsupported conv geometry");
+    PIFPAF_CHECK_ARG(c_in >= 1 && n_out >= 1, "bad conv size");
+    PIFPAF_CUDA_TRY(cudaSetDevice(net->device));
+    const Tensor& tin = net->tensors[in_tensor];
+    const Tensor& to = net->tensors[out_tensor];
+    const int ho = (tin.h + 2 * pad - kernel) / stride + 1, wo = (tin.w + 2 * pad - kernel) / stride + 1;
+    PIFPAF_CHECK_ARG(to.h == ho && to.w == wo, "conv output tensor shape mismatch");
+    PIFPAF_CHECK_ARG(in_col_off % 8 == 0 && in_col_off + c_in <= tin.c, "conv input column window");
+    PIFPAF_CHECK_ARG(out_col_off % 8 == 0 && out_col_off + pad8(n_out) <= to.c, "conv output column window");
+    Op op; op.kind = OP_GEMM;
+    int block_n, n_blocks;
+    choose_block_n(n_out, &block_n, &n_blocks);
+    const int n_pad = block_n * n_blocks;
+    const int taps = kernel * kernel, cblocks = (c_in + BK - 1) / BK;
+    const int k_total = taps * cblocks * BK;
+    // torch weight [n_out][c_in][k][k] -> bf16 [n_pad][tap][cblocks*64]
+    std::vector<__nv_bfloat16> w((size_t)n_pad * k_total, __float2bfloat16(0.f));
+    for (int n = 0; n < n_out; n++)
+        for (int c = 0; c < c_in; c++)
+            for (int t = 0; t < taps; t++)
+                w[(size_t)n * k_total + (size_t)t * cblocks * BK + c] = __float2bfloat16(weight[((size_t)n * c_in + c) * taps + t]);
+    std::vector<float> b(n_pad, 0.f);
+    for (int n = 0; n < n_out; n++) b[n] = bias ? bias[n] : 0.f;
+    __nv_bfloat16* d_w = nullptr; float* d_b = nullptr;
+    int rc = net_upload(net, &d_w, w); if (rc != PIFPAF_OK) return rc;
+    rc = net_upload(net, &d_b, b); if (rc != PIFPAF_OK) return rc;
+    GemmArgs& g = op.g;
+    g.N = n_out; g.K = c_in;
+    g.block_n = block_n; g.n_blocks = n_blocks;
+    g.num_k_blocks = taps * cblocks;
+    g.stages = choose_stages(block_n, n_blocks, g.num_k_blocks, false);
+    g.bias = d_b; g.mode = MODE_PLAIN; g.relu = relu;
+    g.out = to.data; g.ldo = to.c; g.out_col_off = out_col_off;
+    g.conv_k = kernel; g.conv_stride = stride; g.conv_pad = pad; g.conv_cblocks = cblocks;
+    g.Hi = tin.h; g.Wi = tin.w; g.Ho = ho; g.Wo = wo;
+    g.tiles_x = (wo + PW - 1) / PW; g.tiles_y = (ho + PH - 1) / PH;
+    g.a = tin.data + in_col_off; g.lda = tin.c; g.wgt = d_w; g.ldw = k_total;
+    if (residual_tensor >= 0) {
+        PIFPAF_CHECK_ARG(residual_tensor < nt, "bad residual tensor");
+        const Tensor& tr = net->tensors[residual_tensor];
+        PIFPAF_CHECK_ARG(tr.h == ho && tr.w == wo && residual_col_off % 8 == 0 && residual_col_off + n_out <= tr.c,
+                         "residual tensor shape mismatch");
+        g.res = tr.data; g.ld_res = tr.c; g.res_col_off = residual_col_off;
+    }
+    op.a_tensor = in_tensor; op.rows_per_image = ho * wo; op.tiles_per_image = g.tiles_x * g.tiles_y;
+    op.smem = gemm_smem_bytes(block_n, n_blocks, g.stages, false);
+    op.flops_per_image = 2.0 * (double)ho * wo * n_out * c_in * taps;
+    op.bytes_per_image = (double)tin.h * tin.w * c_in * 2.0 + (double)ho * wo * n_out * 2.0 * (residual_tensor >= 0 ? 2.0 : 1.0);
+    op.weight_bytes = (double)n_out * c_in * taps * 2.0;
+    rc = make_tmap_conv(&op.tmap_a, tin.data + in_col_off, (uint64_t)c_in, (uint64_t)tin.w, (uint64_t)tin.h,
+                        (uint64_t)net->max_batch, (uint64_t)tin.c, stride);
+    if (rc != PIFPAF_OK) return rc;
+    rc = make_tmap(&op.tmap_b, d_w, (uint64_t)n_pad, (uint64_t)k_total, (uint64_t)k_total, (uint32_t)block_n);
+    if (rc != PIFPAF_OK) return rc;
     net->ops.push_back(op);
     return PIFPAF_OK;
 }
@@ -945,6 +1312,14 @@ int pifpaf_net_dwconv(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off, 
     a.kernel = kernel; a.stride = stride; a.pad = pad; a.relu = relu;
     op.flops_per_image = 2.0 * ho * wo * channels * (double)kernel * kernel;
     op.bytes_per_image = ((double)tin.h * tin.w + (double)ho * wo) * channels * 2.0;
+    if (kernel == 5 && (stride == 1 || stride == 2)) {
+        const uint32_t bw = stride == 1 ? DwTile<1, 4, 8, 16>::IW : DwTile<2, 2, 4, 16>::IW;
+        const uint32_t bh = stride == 1 ? DwTile<1, 4, 8, 16>::IH : DwTile<2, 2, 4, 16>::IH;
+        rc = make_tmap_dw(&op.tmap_dw, tin.data + in_col_off, (uint64_t)C, (uint64_t)tin.w, (uint64_t)tin.h,
+                          (uint64_t)net->max_batch, (uint64_t)tin.c, bw, bh);
+        if (rc != PIFPAF_OK) return rc;
+        op.dw_tma = true;
+    }
     net->ops.push_back(op);
     return PIFPAF_OK;
 }
@@ -1018,7 +1393,20 @@ static int net_forward_impl(pifpaf_net_t* net, const float* images_dev, int32_t 
         } else if (op.kind == OP_DW) {
             DwArgs a = op.dw;
             a.B = batch;
-            if (a.kernel == 5 && (a.stride == 1 || a.stride == 2)) {
+            if (op.dw_tma && gemm_impl == 0) {
+                const int cblks = (a.C8 + 7) / 8;
+                if (a.stride == 1) {
+                    using T = DwTile<1, 4, 8, 16>;
+                    const long long total = (long long)batch * ((a.Hout + 7) / 8) * ((a.Wout + 15) / 16) * cblks;
+                    const int grid = (int)std::min<long long>(total, (long long)net->n_sm * 3);
+                    k_dwconv5_tma<1, 4, 8, 16><<<grid, 256, 2 * T::BYTES + 128, st>>>(op.tmap_dw, a);
+                } else {
+                    using T = DwTile<2, 2, 4, 16>;
+                    const long long total = (long long)batch * ((a.Hout + 3) / 4) * ((a.Wout + 15) / 16) * cblks;
+                    const int grid = (int)std::min<long long>(total, (long long)net->n_sm * 2);
+                    k_dwconv5_tma<2, 2, 4, 16><<<grid, 256, 2 * T::BYTES + 128, st>>>(op.tmap_dw, a);
+                }
+            } else if (a.kernel == 5 && (a.stride == 1 || a.stride == 2)) {
                 const long long total = (long long)batch * ((a.Hout + DW_OY - 1) / DW_OY) * DW_OY *
                                         ((a.Wout + DW_OX - 1) / DW_OX) * a.C8;
                 const int grid = (int)std::min<long long>((total + 255) / 256, (long long)net->n_sm * 64);
@@ -1033,15 +1421,16 @@ static int net_forward_impl(pifpaf_net_t* net, const float* images_dev, int32_t 
         } else {
             GemmArgs g = op.g;
             g.M = batch * op.rows_per_image;
-            g.m_blocks = (g.M + BM - 1) / BM;
+            g.m_blocks = g.conv_k > 0 ? batch * op.tiles_per_image : (g.M + BM - 1) / BM;
             if (gemm_impl == 1) {
-                const long long jobs = (long long)((g.M + 31) / 32) * (g.n_blocks * g.block_n / CHUNK);
+                const long long jobs = (long long)g.m_blocks * 4 * (g.n_blocks * g.block_n / CHUNK);
                 const int grid = (int)std::min<long long>((jobs + 3) / 4, (long long)net->n_sm * 16);
                 k_gemm_simt<<<grid, 128, 0, st>>>(g);
             } else {
                 const int tiles = g.m_blocks * g.n_blocks;
                 const int grid = std::min(tiles, net->n_sm);
-                k_gemm_tc<<<grid, GEMM_THREADS, op.smem, st>>>(op.tmap_a, op.tmap_b, g);
+                k_gemm_tc<<<grid, GEMM_THREADS, op.smem, st>>>(op.tmap_a, op.tmap_b,
+                                                                g.src_tma ? op.tmap_src : op.tmap_a, g);
             }
             PIFPAF_LAUNCH_CHECK();
         }

@@ -62,13 +62,59 @@ def head_ops(n_confidences, n_vectors, n_scales, vector_offsets):
     return ops
 
 
-def plan_from_shell(shell):
-    """Extract a folded plan from a reference-style Shell with a ShuffleNetV2K base net."""
+def _heads_plan(shell, base):
+    heads = []
+    for hn in shell.head_nets:
+        m = hn.meta
+        if getattr(m, 'upsample_stride', 1) != 1:
+            raise RuntimeError('upsample_stride > 1 heads are not supported')
+        ncomp = 1 + m.n_confidences + m.n_vectors * 2 + m.n_scales
+        heads.append({
+            'w': hn.conv.weight.detach().float().cpu().numpy().reshape(m.n_fields * ncomp, -1),
+            'b': hn.conv.bias.detach().float().cpu().numpy(),
+            'n_fields': int(m.n_fields), 'n_comp': int(ncomp),
+            'ops': head_ops(m.n_confidences, m.n_vectors, m.n_scales, tuple(m.vector_offsets)),
+            'stride': int(base.stride)})
+    return heads
+
+
+def _plan_from_resnet(shell):
+    """basenetworks.py:71-150: torchvision ResNet without the max-pool (input_block = conv1, bn1, relu;
+    block2..block5 = layer1..layer4 of BasicBlock / Bottleneck)."""
     base = shell.base_net
-    if not all(hasattr(base, a) for a in ('input_block', 'stage2', 'stage3', 'stage4', 'conv5')):
-        raise RuntimeError(f'unsupported base network {type(base).__name__}: expected a ShuffleNetV2K')
+    if len(base.input_block) != 3:
+        raise RuntimeError('only the default Resnet input block (conv, bn, relu; pool0_stride=0) is supported')
+    conv, bn = base.input_block[0], base.input_block[1]
+    w, b = _fold(conv, bn)
+    plan = {'kind': 'resnet',
+            'input': {'w': w, 'b': b, 'stride': int(conv.stride[0]), 'pad': int(conv.padding[0])},
+            'blocks': [], 'heads': _heads_plan(shell, base)}
+
+    def conv_entry(c, n):
+        if c.dilation[0] != 1 or c.groups != 1:
+            raise RuntimeError('dilated / grouped ResNet convolutions are not supported')
+        w_, b_ = _fold(c, n)
+        return {'w': w_, 'b': b_, 'kernel': int(c.kernel_size[0]), 'stride': int(c.stride[0]), 'pad': int(c.padding[0])}
+
+    for stage in (base.block2, base.block3, base.block4, base.block5):
+        for blk in stage:
+            e = {'convs': [conv_entry(blk.conv1, blk.bn1), conv_entry(blk.conv2, blk.bn2)]}
+            if hasattr(blk, 'conv3'):
+                e['convs'].append(conv_entry(blk.conv3, blk.bn3))
+            e['downsample'] = None if blk.downsample is None else conv_entry(blk.downsample[0], blk.downsample[1])
+            plan['blocks'].append(e)
+    return plan
+
+
+def plan_from_shell(shell):
+    """Extract a folded plan from a reference-style Shell (ShuffleNetV2K or Resnet base net)."""
+    base = shell.base_net
     if shell.training:
         raise RuntimeError('the Shell must be in eval() mode (BatchNorm is folded)')
+    if all(hasattr(base, a) for a in ('input_block', 'block2', 'block3', 'block4', 'block5')):
+        return _plan_from_resnet(shell)
+    if not all(hasattr(base, a) for a in ('input_block', 'stage2', 'stage3', 'stage4', 'conv5')):
+        raise RuntimeError(f'unsupported base network {type(base).__name__}: expected ShuffleNetV2K or Resnet')
     if len(base.input_block) != 1:
         raise RuntimeError('input_conv2 variants are not supported')
     conv, bn = base.input_block[0][0], base.input_block[0][1]
@@ -96,17 +142,7 @@ def plan_from_shell(shell):
     if not isinstance(base.conv5[0], torch.nn.Conv2d):
         raise RuntimeError('conv5_as_stage is not supported')
     plan['conv5'] = _fold(base.conv5[0], base.conv5[1])
-    for hn in shell.head_nets:
-        m = hn.meta
-        if getattr(m, 'upsample_stride', 1) != 1:
-            raise RuntimeError('upsample_stride > 1 heads are not supported')
-        ncomp = 1 + m.n_confidences + m.n_vectors * 2 + m.n_scales
-        plan['heads'].append({
-            'w': hn.conv.weight.detach().float().cpu().numpy().reshape(m.n_fields * ncomp, -1),
-            'b': hn.conv.bias.detach().float().cpu().numpy(),
-            'n_fields': int(m.n_fields), 'n_comp': int(ncomp),
-            'ops': head_ops(m.n_confidences, m.n_vectors, m.n_scales, tuple(m.vector_offsets)),
-            'stride': int(base.stride)})
+    plan['heads'] = _heads_plan(shell, base)
     return plan
 
 
@@ -154,6 +190,23 @@ def random_plan(base_name='shufflenetv2k16', heads=((17, 1, 1, 1), (19, 1, 2, 2)
     return plan
 
 
+def calibrate_random_heads(plan, device=0, seed=0):
+    """Give a random-init plan trained-network-like head statistics: measure the RMS of the backbone features
+    on a small random batch (on the GPU, through the product kernels) and rescale the head weights so that the
+    head pre-activations have unit scale.  Together with random_plan's confidence bias this yields sparse
+    confidence maps (a few cells per image above the decoder thresholds) instead of saturated noise."""
+    net = CompiledNet(plan, 161, 161, 2, device=device)
+    x = torch.randn((2, 3, 161, 161), generator=torch.Generator().manual_seed(seed)).to(f'cuda:{device}')
+    net.forward(x)
+    torch.cuda.synchronize()
+    t, lay = net.info['feature']
+    feat = net.tap(t, 2)[..., lay.cols()]
+    rms = float(np.sqrt(np.mean(np.square(feat, dtype=np.float64))))
+    for hd in plan['heads']:
+        hd['w'] = (hd['w'] / np.float32(max(rms, 1e-6))).astype(np.float32)
+    return rms
+
+
 # ----------------------------------------------------------------------------- compiled net
 
 class _DevArray:
@@ -197,6 +250,8 @@ def build_ops(plan, in_h, in_w):
 
     Returns (tensors, ops): tensors[i] = (h, w, c_phys); ops are dicts with a 'kind' in
     {'input_conv', 'conv1x1', 'dwconv', 'heads'} whose fields are the C ABI arguments."""
+    if plan.get('kind') == 'resnet':
+        return _build_ops_resnet(plan, in_h, in_w)
     if plan.get('kind') != 'shufflenetv2k':
         raise RuntimeError('unsupported plan kind')
     tensors, ops = [], []
@@ -281,6 +336,64 @@ def build_ops(plan, in_h, in_w):
     return tensors, ops, {'block_outputs': block_outputs, 'feature': (t5, _Layout(c5, split=False))}
 
 
+def _heads_op(heads, t_in, k_cols):
+    return {'kind': 'heads', 'in': t_in, 'k_cols': k_cols,
+            'n_fields': [hd['n_fields'] for hd in heads], 'n_comp': [hd['n_comp'] for hd in heads],
+            'ops': [o for hd in heads for o in hd['ops']],
+            'w': _f32(np.concatenate([_f32(hd['w']) for hd in heads], axis=0)),
+            'b': _f32(np.concatenate([_f32(hd['b']) for hd in heads], axis=0))}
+
+
+def _build_ops_resnet(plan, in_h, in_w):
+    """torchvision BasicBlock / Bottleneck (eval): every conv+BN is one implicit-GEMM conv op; the residual
+    add and the final ReLU of a block are fused into the epilogue of its last conv."""
+    tensors, ops = [], []
+
+    def tensor(h, w, c):
+        tensors.append((h, w, c))
+        return len(tensors) - 1
+
+    def conv(tin, e, relu, tout, residual=-1):
+        ops.append({'kind': 'conv', 'in': tin, 'in_off': 0, 'c_in': e['w'].shape[1], 'kernel': e['kernel'],
+                    'stride': e['stride'], 'pad': e['pad'], 'n_out': e['w'].shape[0], 'w': _f32(e['w']),
+                    'b': _f32(e['b']), 'relu': int(relu), 'out': tout, 'out_off': 0,
+                    'residual': residual, 'residual_off': 0})
+
+    def out_hw(h, w, e):
+        return ((h + 2 * e['pad'] - e['kernel']) // e['stride'] + 1, (w + 2 * e['pad'] - e['kernel']) // e['stride'] + 1)
+
+    inp = plan['input']
+    k = inp['w'].shape[-1]
+    h = (in_h + 2 * inp['pad'] - k) // inp['stride'] + 1
+    w = (in_w + 2 * inp['pad'] - k) // inp['stride'] + 1
+    c0 = inp['w'].shape[0]
+    cur = tensor(h, w, pad8(c0))
+    ops.append({'kind': 'input_conv', 'in_h': in_h, 'in_w': in_w, 'kernel': k, 'stride': inp['stride'],
+                'pad': inp['pad'], 'c_out': c0, 'w': _f32(inp['w']), 'b': _f32(inp['b']), 'relu': 1, 'out': cur})
+    c_cur = c0
+    block_outputs = []
+    for e in plan['blocks']:
+        identity = cur
+        hh, ww = h, w
+        t_in = cur
+        if e['downsample'] is not None:
+            ds = e['downsample']
+            dh, dw_ = out_hw(h, w, ds)
+            identity = tensor(dh, dw_, pad8(ds['w'].shape[0]))
+            conv(cur, ds, False, identity)
+        n_convs = len(e['convs'])
+        for ci, ce in enumerate(e['convs']):
+            oh, ow = out_hw(hh, ww, ce)
+            t_out = tensor(oh, ow, pad8(ce['w'].shape[0]))
+            last = ci == n_convs - 1
+            conv(t_in, ce, True, t_out, residual=identity if last else -1)
+            t_in, hh, ww = t_out, oh, ow
+        cur, h, w, c_cur = t_in, hh, ww, e['convs'][-1]['w'].shape[0]
+        block_outputs.append((cur, _Layout(c_cur, split=False)))
+    ops.append(_heads_op(plan['heads'], cur, c_cur))
+    return tensors, ops, {'block_outputs': block_outputs, 'feature': (cur, _Layout(c_cur, split=False))}
+
+
 class CompiledNet:
     """A plan compiled to libpifpaf_b200 ops for a fixed input size and maximum batch."""
 
@@ -290,6 +403,7 @@ class CompiledNet:
         self.max_batch = int(max_batch)
         self.in_h, self.in_w = int(in_h), int(in_w)
         self.tensor_shapes, ops, self.info = build_ops(plan, self.in_h, self.in_w)
+        self.op_desc = [{k: v for k, v in o.items() if not isinstance(v, np.ndarray)} for o in ops]
         self.handle = ctypes.c_void_p()
         _lib.check(self.lib.pifpaf_net_create(ctypes.byref(self.handle), self.device, self.max_batch))
         self._emit(ops)
@@ -325,6 +439,10 @@ class CompiledNet:
                 _lib.check(L.pifpaf_net_conv1x1(H, o['in'], o['in_off'], o['k_cols'], o['n_out'], _ptr(o['w']),
                                                 _ptr(o['b']), o['relu'], o['out'], o['out_off'],
                                                 o['shuffle_src'], o['shuffle_off']))
+            elif o['kind'] == 'conv':
+                _lib.check(L.pifpaf_net_conv(H, o['in'], o['in_off'], o['c_in'], o['kernel'], o['stride'], o['pad'],
+                                             o['n_out'], _ptr(o['w']), _ptr(o['b']), o['relu'], o['out'],
+                                             o['out_off'], o['residual'], o['residual_off']))
             elif o['kind'] == 'dwconv':
                 _lib.check(L.pifpaf_net_dwconv(H, o['in'], o['in_off'], o['channels'], o['kernel'], o['stride'],
                                                o['pad'], _ptr(o['w']), _ptr(o['b']), o['relu'], o['out'], o['out_off']))

@@ -93,6 +93,39 @@ class ShuffleNetV2K(torch.nn.Module):
         return self.conv5(x)
 
 
+class Resnet(torch.nn.Module):
+    """basenetworks.py:71-150 in its default configuration: torchvision ResNet with the max-pool removed
+    (pool0_stride = 0 -> stride 16), no dilation, all four blocks."""
+
+    def __init__(self, name, torchvision_resnet, out_features=2048):
+        super().__init__()
+        modules = list(torchvision_resnet(weights=None).children())
+        self.name = name
+        self.stride = 16
+        self.out_features = out_features
+        self.input_block = torch.nn.Sequential(*modules[:3])       # conv1, bn1, relu (max-pool popped, :86-93)
+        self.block2, self.block3, self.block4, self.block5 = modules[4], modules[5], modules[6], modules[7]
+
+    def forward(self, x):
+        x = self.input_block(x)
+        x = self.block2(x)
+        x = self.block3(x)
+        x = self.block4(x)
+        return self.block5(x)
+
+
+def make_base(base_name):
+    import torchvision
+    if base_name in SHUFFLENETV2K_CONFIGS:
+        repeats, channels = SHUFFLENETV2K_CONFIGS[base_name]
+        return ShuffleNetV2K(base_name, repeats, channels)
+    if base_name == 'resnet18':
+        return Resnet('resnet18', torchvision.models.resnet18, 512)          # network/factory.py:57
+    if base_name == 'resnet50':
+        return Resnet('resnet50', torchvision.models.resnet50)               # network/factory.py:58
+    raise ValueError(base_name)
+
+
 class HeadMeta:
     """The subset of headmeta.Cif / headmeta.Caf (headmeta.py:12-113) the forward pass needs."""
 
@@ -181,8 +214,7 @@ def make_shell(base_name='shufflenetv2k16', n_keypoints=17, n_connections=19, se
     layers non-trivial running statistics/affine parameters so that BN folding is actually exercised."""
     g = torch.Generator().manual_seed(seed)
     torch.manual_seed(seed)
-    repeats, channels = SHUFFLENETV2K_CONFIGS[base_name]
-    base = ShuffleNetV2K(base_name, repeats, channels)
+    base = make_base(base_name)
     heads = [CompositeField4(HeadMeta.cif(n_keypoints), base.out_features),
              CompositeField4(HeadMeta.caf(n_connections), base.out_features)]
     shell = Shell(base, heads)

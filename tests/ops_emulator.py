@@ -44,6 +44,15 @@ def run_ops(tensors, ops, images, bf16=False):
                 logical[..., 1::2] = y
                 l = np.arange(2 * n)
                 out[..., l + (l >= half) * gap] = logical
+        elif kind == 'conv':
+            a = acts[o['in']][..., o['in_off']:o['in_off'] + o['c_in']].permute(0, 3, 1, 2)
+            y = F.conv2d(a, q(torch.from_numpy(o['w'])), torch.from_numpy(o['b']), o['stride'], o['pad'])
+            y = y.permute(0, 2, 3, 1)
+            if o['residual'] >= 0:
+                y = y + acts[o['residual']][..., o['residual_off']:o['residual_off'] + o['n_out']]
+            if o['relu']:
+                y = F.relu(y)
+            acts[o['out']][..., o['out_off']:o['out_off'] + o['n_out']] = q(y)
         elif kind == 'dwconv':
             c = o['channels']
             a = acts[o['in']][..., o['in_off']:o['in_off'] + c].permute(0, 3, 1, 2)

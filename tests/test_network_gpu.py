@@ -107,3 +107,30 @@ def test_pipelined_batches_equal_sequential():
     for rw, rg in zip(want, got):
         for (aw, iw), (ag, ig) in zip(rw, rg):
             assert torch.equal(aw, ag) and torch.equal(iw, ig)
+
+
+@pytest.mark.parametrize('name,size,batch', [('resnet18', 161, 1), ('resnet50', 129, 2)])
+def test_resnet_implicit_gemm_matches_emulation_and_fp32(name, size, batch):
+    """configs[0] (resnet18, 161x161, single image) and the resnet50 family: 3x3 / strided convs as tcgen05
+    implicit GEMMs with the fused residual epilogue, per op vs the bf16 emulation and end-to-end vs fp32 PyTorch."""
+    shell = net_oracle.make_shell(name, seed=4)
+    plan = network.plan_from_shell(shell)
+    x = torch.randn(batch, 3, size, size, generator=torch.Generator().manual_seed(6))
+    tensors, ops, _ = network.build_ops(plan, size, size)
+    emu_heads, emu_acts = ops_emulator.run_ops(tensors, ops, x, bf16=True)
+    net = network.CompiledNet(plan, size, size, batch)
+    for impl in (1, 0):
+        heads = net.forward(x.cuda(), gemm_impl=impl)
+        torch.cuda.synchronize()
+        for o in ops:
+            if o['kind'] == 'heads':
+                continue
+            got = net.tap(o['out'], batch)
+            ref = emu_acts[o['out']].numpy()
+            scale = max(float(np.abs(ref).max()), 1e-6)
+            assert float(np.abs(got - ref).max()) / scale < 3e-2, (impl, o['kind'], o['out'], o.get('kernel'), o.get('stride'))
+    with torch.no_grad():
+        want = shell(x)
+    for hg, hw_ in zip(net.forward(x.cuda()), want):
+        assert hg.shape == hw_.shape
+        assert float((hg.cpu() - hw_).abs().max()) < FIELD_TOL_REL * float(hw_.std()) + 1e-3

@@ -106,3 +106,38 @@ def test_random_plan_has_reference_architecture():
         elif o['kind'] == 'input_conv':
             gmac += hh * ww * o['w'].size / 1e9
     assert abs(gmac - 36.58) < 0.2, gmac       # 36.58 GMAC / image @641
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SRC), reason='/root/reference absent')
+def test_oracle_resnet_equals_reference_module():
+    """the oracle Resnet wrapper == reference basenetworks.Resnet (max-pool removed, stride 16)."""
+    import torchvision
+    _, base, _ = _load_reference_modules()
+    base.Resnet.pretrained = False
+    ref = base.Resnet('resnet18', lambda pretrained: torchvision.models.resnet18(weights=None), 512)
+    assert ref.stride == 16
+    oracle = net_oracle.make_base('resnet18')
+    ref.load_state_dict(oracle.state_dict())
+    ref.eval(); oracle.eval()
+    x = torch.randn(1, 3, 161, 161)
+    with torch.no_grad():
+        torch.testing.assert_close(oracle(x), ref(x), rtol=0, atol=1e-5)
+    assert tuple(oracle(x).shape) == (1, 512, 11, 11)
+
+
+@pytest.mark.parametrize('name,shape', [('resnet18', (161, 161)), ('resnet50', (97, 113))])
+def test_resnet_lowering_reproduces_oracle_net(name, shape):
+    h, w = shape
+    shell = net_oracle.make_shell(name, seed=1)
+    x = torch.randn(2, 3, h, w)
+    with torch.no_grad():
+        want = shell(x)
+    plan = network.plan_from_shell(shell)
+    assert plan['kind'] == 'resnet'
+    tensors, ops, _ = network.build_ops(plan, h, w)
+    got, _ = ops_emulator.run_ops(tensors, ops, x)
+    for g, wnt in zip(got, want):
+        assert g.shape == wnt.shape
+        assert float((g - wnt).abs().max()) < 1e-5 * max(1.0, float(wnt.abs().max()))
+    n_conv = sum(o['kind'] == 'conv' for o in ops)
+    assert n_conv == (20 if name == 'resnet18' else 53) - 1       # all convs but the stem (SURVEY appendix A)

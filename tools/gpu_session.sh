@@ -12,7 +12,7 @@ tail -30 gpurun_out/diag_net.log
 echo "== decoder perf"; timeout 600 python tools/diag_decoder_perf.py > gpurun_out/decoder_perf.log 2>&1; echo "rc=$?"
 tail -8 gpurun_out/decoder_perf.log
 echo "== smoke"; timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/smoke.log
-echo "== bench"; timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2>&1; echo "rc=$?"
+echo "== bench"; timeout 900 python bench.py --steps 10 --warmup 3 --dump-ops gpurun_out/per_op.json > gpurun_out/bench.log 2>&1; echo "rc=$?"
 tail -5 gpurun_out/bench.log
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1; echo "rc=$?"
 tail -2 gpurun_out/bench_ref.log
@@ -22,7 +22,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --c
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_decoder.csv \
    python tools/diag_decoder_perf.py 2 > gpurun_out/decoder_under_ncu.log 2>&1; echo "rc=$?"
 echo "== ncu full"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_gemm_tc|k_dwconv5' -s 60 -c 10 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_gemm_tc|k_dwconv5' -s 70 -c 12 \
    -o gpurun_out/prof_net -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_net.log 2>&1; echo "rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_grow|k_cifhr_tiles|k_nms|k_seed_sort|k_caf_scored' -s 40 -c 10 \
    -o gpurun_out/prof_dec -f python tools/diag_decoder_perf.py 2 > gpurun_out/ncu_full_dec.log 2>&1; echo "rc=$?"
