@@ -219,8 +219,8 @@ def run_b200(args):
                               'shuffle': o.get('shuffle_src', -1) >= 0 if 'shuffle_src' in o else None,
                               'ms': round(float(ms_op[i]), 4), 'gflops': round(float(flops[i]) / 1e9, 2),
                               'gbytes': round(float(nbytes[i]) / 1e9, 4),
-                              'tflops': round(float(flops[i]) / ms_op[i] / 1e9, 1),
-                              'gbs': round(float(nbytes[i]) / ms_op[i] / 1e6, 0)})
+                              'tflops': round(float(flops[i]) / float(ms_op[i]) / 1e9, 1),
+                              'gbs': round(float(nbytes[i]) / float(ms_op[i]) / 1e6, 0)})
             with open(args.dump_ops, 'w') as f:
                 json.dump({'batch': B, 'ops': table}, f, indent=1)
         out = {

@@ -104,6 +104,25 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
+// asynchronous TMEM load of 16 columns; results are valid only after tmem_ld_wait(v)
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+// wait for all outstanding tcgen05.ld of this thread; the registers are in/out operands so that no use of them
+// can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait(uint32_t* v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -119,7 +138,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
 constexpr int BM = 128;          // UMMA M (cta_group::1): TMEM lane == tile row
 constexpr int BK = 64;           // one 128-byte swizzle atom of bf16 per smem row
 constexpr int UMMA_K = 16;
-constexpr int EPI_WARPS = 8;         // two warps per TMEM lane quadrant, each takes half of the columns
+constexpr int EPI_WARPS = 16;        // four warps per TMEM lane quadrant, each takes a quarter of the columns
 constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;   // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..9 epilogue
 constexpr int CHUNK = 16;        // epilogue column chunk (one tcgen05.ld.32x32b.x16)
 
@@ -435,12 +454,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
             }
         }
     } else {
-        // ===== epilogue warps: TMEM lane quadrant = warp % 4; warps 2..5 take the first half of the
-        // column chunks, warps 6..9 the second half =====
+        // ===== epilogue warps: TMEM lane quadrant = warp % 4; the EPI_WARPS/4 warps of a quadrant split the
+        // column chunks evenly =====
         const int q = warp & 3;
         const int n_chunks = g.block_n / CHUNK;
-        const int c_begin = (warp < 6) ? 0 : (n_chunks + 1) / 2;
-        const int c_end = (warp < 6) ? (n_chunks + 1) / 2 : n_chunks;
+        const int part = (warp - 2) >> 2, parts = EPI_WARPS / 4;
+        const int c_begin = n_chunks * part / parts;
+        const int c_end = n_chunks * (part + 1) / parts;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_blk = tile / g.n_blocks, n_blk = tile % g.n_blocks;
@@ -451,16 +471,27 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
             const __nv_bfloat16* src_tile_row = reinterpret_cast<const __nv_bfloat16*>(
                 src_tiles + (size_t)acc * src_bytes) + (size_t)(q * 32 + lane) * g.block_n;
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (uint32_t)(acc * g.block_n);
-            for (int ci = c_begin; ci < c_end; ci++) {
+            // software-pipelined TMEM reads: the load of chunk ci+1 is in flight while chunk ci is processed
+            uint32_t va[CHUNK], vb[CHUNK];
+            auto process = [&](int ci, const uint32_t* v) {
                 const int c = ci * CHUNK;
-                uint32_t v[CHUNK];
-                tmem_ld16(t_row + (uint32_t)c, v);
                 float accf[CHUNK];
 #pragma unroll
                 for (int j = 0; j < CHUNK; j++) accf[j] = __uint_as_float(v[j]);
                 const int n0 = n_blk * g.block_n + c;
                 if (n0 < ((g.N + 7) & ~7))
                     epilogue_chunk(g, m, n0, accf, bias_s + n0, g.src_tma ? src_tile_row + c : nullptr);
+            };
+            if (c_begin < c_end) tmem_ld16_async(t_row + (uint32_t)(c_begin * CHUNK), va);
+            for (int ci = c_begin; ci < c_end; ci += 2) {
+                tmem_ld_wait(va);
+                if (ci + 1 < c_end) tmem_ld16_async(t_row + (uint32_t)((ci + 1) * CHUNK), vb);
+                process(ci, va);
+                if (ci + 1 < c_end) {
+                    tmem_ld_wait(vb);
+                    if (ci + 2 < c_end) tmem_ld16_async(t_row + (uint32_t)((ci + 2) * CHUNK), va);
+                    process(ci + 1, vb);
+                }
             }
             tcgen05_fence_before();
             __syncwarp();

@@ -3,9 +3,9 @@
 set +e
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
-echo "== diag_gemm"; timeout 420 python tools/diag_gemm.py > gpurun_out/diag_gemm.log 2>&1; echo "rc=$?"
+echo "== diag_gemm"; timeout -k 10 420 python tools/diag_gemm.py > gpurun_out/diag_gemm.log 2>&1; echo "rc=$?"
 grep -E "DIAG_GEMM|BAD|EXCEPTION" gpurun_out/diag_gemm.log | head -20
-echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?"
+echo "== pytest -m gpu (all but resnet)"; timeout -k 10 1500 python -m pytest tests -m gpu -q -k "not resnet" > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?"
 tail -25 gpurun_out/pytest_gpu.log
 echo "== diag_net"; timeout 600 python tools/diag_net.py > gpurun_out/diag_net.log 2>&1; echo "rc=$?"
 tail -30 gpurun_out/diag_net.log
@@ -16,6 +16,8 @@ echo "== bench"; timeout 900 python bench.py --steps 10 --warmup 3 --dump-ops gp
 tail -5 gpurun_out/bench.log
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1; echo "rc=$?"
 tail -2 gpurun_out/bench_ref.log
+echo "== pytest resnet"; timeout -k 10 600 python -m pytest tests -m gpu -q -k "resnet" > gpurun_out/pytest_resnet.log 2>&1; echo "rc=$?"
+tail -25 gpurun_out/pytest_resnet.log
 echo "== ncu launch lists"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches_bench.csv \
    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1; echo "rc=$?"
