@@ -168,7 +168,7 @@ int pifpaf_net_create(pifpaf_net_t** out, int32_t device, int32_t max_batch);
 void pifpaf_net_destroy(pifpaf_net_t* net);
 
 /* Activation tensor NHWC bf16 [max_batch][h][w][c_phys] (zero-initialised;
- * c_phys % 8 == 0).  *id receives its handle. */
+ * c_phys % 16 == 0: rows start on 32-byte boundaries).  *id receives its handle. */
 int pifpaf_net_tensor(pifpaf_net_t* net, int32_t h, int32_t w, int32_t c_phys, int32_t* id);
 
 /* Input block conv (basenetworks.py:275-280; torchvision resnet conv1): dense kxk conv on the
@@ -181,8 +181,8 @@ int pifpaf_net_input_conv(pifpaf_net_t* net, int32_t in_h, int32_t in_w, int32_t
  * of in_tensor; weight [n_out][k_cols] in the same physical column order; + bias (+ReLU).
  * shuffle_src_tensor < 0: plain output at columns [out_col_off, out_col_off+n_out) of out_tensor.
  * shuffle_src_tensor >= 0: fused cat + channel_shuffle(2) (basenetworks.py:233-242): output logical
- *   channel 2n <- shuffle_src[n], 2n+1 <- this conv[n]; out_tensor holds the two logical halves each
- *   padded to a multiple of 8 channels (c_phys == 2*pad8(n_out)). */
+ *   channel 2n <- shuffle_src[n], 2n+1 <- this conv[n], written contiguously (physical == logical order);
+ *   in_col_off may be any column: the next block's x.chunk(2) is the TMA coordinate n_out. */
 int pifpaf_net_conv1x1(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off, int32_t k_cols,
                        int32_t n_out, const float* weight, const float* bias, int32_t relu,
                        int32_t out_tensor, int32_t out_col_off,

@@ -167,6 +167,7 @@ struct HeadCol { int head; int plane; int op; int pad; };   // per GEMM output c
 
 struct GemmArgs {
     int M, N, K;                 // rows, real output channels, k extent (columns of the A view)
+    int a_col0;                  // first column of the A view inside its tensor (TMA coordinate; any value)
     int block_n, n_blocks, m_blocks, num_k_blocks, stages;
     int mode, relu;
     const float* bias;           // [n_blocks * block_n], zero padded
@@ -211,6 +212,13 @@ __device__ __forceinline__ float softplus_f(float x) {   // torch softplus beta=
     return x > 20.0f ? x : log1pf(expf(x));
 }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// Blackwell 256-bit global store (STG.E.256): p must be 32-byte aligned
+__device__ __forceinline__ void st_global_256(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d,
+                                              uint32_t e, uint32_t f, uint32_t g, uint32_t h) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f), "r"(g), "r"(h) : "memory");
+}
 
 // store `cnt` (<= 16) consecutive 32-bit words from registers to p (4-byte aligned, LEAD words before the
 // first 16-byte boundary): scalar lead-in, 16-byte vectors, scalar tail.  Fully unrolled (no local memory).
@@ -291,11 +299,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, int m, int n0,
             if (g.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
             w[j >> 1] = pack_bf16(a0, a1);
         }
-        // 16 bf16 = 32 bytes, 32-byte aligned (ldo % 8 == 0, out_col_off % 8 == 0, n0 % 16 == 0)
+        // 16 bf16 = 32 bytes, 32-byte aligned (ldo % 16 == 0, out_col_off % 16 == 0, n0 % 16 == 0)
         uint4* dst = reinterpret_cast<uint4*>(g.out + (size_t)m * g.ldo + g.out_col_off + n0);
         const int n_pad8 = (g.N + 7) & ~7;
-        if (n0 < n_pad8) dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-        if (n0 + 8 < n_pad8) dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        if (n0 + 8 < n_pad8) {
+            st_global_256(dst, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+        } else if (n0 < n_pad8) {
+            dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
         return;
     }
     // MODE_SHUFFLE: word n = { src0[m][n] (logical channel 2n), conv[m][n] (logical 2n+1) }
@@ -313,24 +324,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, int m, int n0,
         const __nv_bfloat16 hb = __float2bfloat16_rn(a);
         w[j] = src_bits | (static_cast<uint32_t>(__bfloat16_as_ushort(hb)) << 16);
     }
-    uint32_t* row = reinterpret_cast<uint32_t*>(g.out) + (size_t)m * (g.ldo >> 1) + (g.out_col_off >> 1);
+    // logical channel 2n, 2n+1 == physical word n (gap-free layout): 64 bytes per lane, 64-byte aligned
+    uint32_t* row = reinterpret_cast<uint32_t*>(g.out) + (size_t)m * (g.ldo >> 1) + (g.out_col_off >> 1) + n0;
     const int cnt = min(CHUNK, g.N - n0);
-    const int shift = g.gap >> 1;                 // words inserted at the logical half boundary
-    const int n_split = (g.half + 1) >> 1;        // first n with 2n >= half
-    if (n0 + CHUNK <= n_split || shift == 0) {
-        store_words<0>(row + n0, w, cnt);
-    } else if (n0 >= n_split) {
-        uint32_t* p = row + n0 + shift;
-        switch (shift & 3) {                      // warp-uniform
-            case 0: store_words<0>(p, w, cnt); break;
-            case 1: store_words<3>(p, w, cnt); break;
-            case 2: store_words<2>(p, w, cnt); break;
-            default: store_words<1>(p, w, cnt); break;
-        }
+    if (cnt == CHUNK) {
+        st_global_256(row, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+        st_global_256(row + 8, w[8], w[9], w[10], w[11], w[12], w[13], w[14], w[15]);
     } else {
-#pragma unroll
-        for (int j = 0; j < CHUNK; j++)
-            if (j < cnt) row[n0 + j + ((n0 + j) >= n_split ? shift : 0)] = w[j];
+        store_words<0>(row, w, cnt);
     }
 }
 
@@ -409,7 +410,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
                         cb = kb - tap * g.conv_cblocks;
                         tma_load_4d(sa, &tmap_a, &full_bar[stage], cb * BK, cx + tap % g.conv_k, cy + tap / g.conv_k, cimg);
                     } else {
-                        tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+                        tma_load_2d(sa, &tmap_a, &full_bar[stage], g.a_col0 + kb * BK, m_blk * BM);
                     }
                     tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * g.block_n);
                     if (++stage == g.stages) { stage = 0; phase ^= 1; }
@@ -1083,8 +1084,7 @@ int choose_stages(int block_n, int n_blocks, int num_k_blocks, bool shuffle) {
 int emit_gemm(pifpaf_net* net, Op& op, int in_tensor, int in_col_off, int k_cols, int n_out,
               const float* weight, const float* bias) {
     const Tensor& tin = net->tensors[in_tensor];
-    PIFPAF_CHECK_ARG(in_col_off % 8 == 0 && in_col_off >= 0 && in_col_off + k_cols <= tin.c,
-                     "conv1x1 input column window must be 16-byte aligned and inside the tensor");
+    PIFPAF_CHECK_ARG(in_col_off >= 0 && in_col_off + k_cols <= tin.c, "conv1x1 input column window outside the tensor");
     int block_n, n_blocks;
     choose_block_n(n_out, &block_n, &n_blocks);
     const int n_pad = block_n * n_blocks;
@@ -1100,7 +1100,7 @@ int emit_gemm(pifpaf_net* net, Op& op, int in_tensor, int in_col_off, int k_cols
 
     GemmArgs& g = op.g;
     const size_t rows_max = (size_t)net->max_batch * tin.h * tin.w;
-    g.N = n_out; g.K = k_cols;
+    g.N = n_out; g.K = k_cols; g.a_col0 = in_col_off;
     g.block_n = block_n; g.n_blocks = n_blocks;
     g.num_k_blocks = (k_cols + BK - 1) / BK;
     g.stages = choose_stages(block_n, n_blocks, g.num_k_blocks, false);
@@ -1111,7 +1111,9 @@ int emit_gemm(pifpaf_net* net, Op& op, int in_tensor, int in_col_off, int k_cols
     op.flops_per_image = 2.0 * (double)op.rows_per_image * n_out * k_cols;
     op.bytes_per_image = (double)op.rows_per_image * k_cols * 2.0;      // A read once (bf16); outputs added by the caller
     op.weight_bytes = (double)n_out * k_cols * 2.0;
-    rc = make_tmap(&op.tmap_a, tin.data + in_col_off, rows_max, (uint64_t)k_cols, (uint64_t)tin.c, BM);
+    // the map covers the whole tensor; the view's first column is a TMA coordinate (no alignment needed).
+    // Columns past the view multiply zero weight rows (B is zero padded), columns past the tensor are zero filled.
+    rc = make_tmap(&op.tmap_a, tin.data, rows_max, (uint64_t)tin.c, (uint64_t)tin.c, BM);
     if (rc != PIFPAF_OK) return rc;
     rc = make_tmap(&op.tmap_b, d_w, (uint64_t)n_pad, (uint64_t)k_pad, (uint64_t)k_pad, (uint32_t)block_n);
     return rc;
@@ -1155,7 +1157,7 @@ void pifpaf_net_destroy(pifpaf_net_t* net) {
 
 int pifpaf_net_tensor(pifpaf_net_t* net, int32_t h, int32_t w, int32_t c_phys, int32_t* id) {
     PIFPAF_CHECK_ARG(net != nullptr && id != nullptr, "null argument");
-    PIFPAF_CHECK_ARG(h >= 1 && w >= 1 && c_phys >= 8 && c_phys % 8 == 0, "tensor shape: c_phys must be a multiple of 8");
+    PIFPAF_CHECK_ARG(h >= 1 && w >= 1 && c_phys >= 16 && c_phys % 16 == 0, "tensor shape: c_phys must be a multiple of 16");
     PIFPAF_CUDA_TRY(cudaSetDevice(net->device));
     Tensor t; t.h = h; t.w = w; t.c = c_phys; t.data = nullptr;
     // + one tile of slack rows so that TMA boxes of the last partial M tile stay in mapped memory
@@ -1219,7 +1221,7 @@ int pifpaf_net_conv1x1(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off,
     g.relu = relu; g.out = to.data; g.ldo = to.c; g.out_col_off = out_col_off;
     // outputs: n_out bf16 per row; the fused shuffle also reads and re-writes the pass-through half
     op.bytes_per_image += (double)op.rows_per_image * n_out * 2.0 * (shuffle_src_tensor >= 0 ? 3.0 : 1.0);
-    PIFPAF_CHECK_ARG(out_col_off % 8 == 0, "output column offset must be a multiple of 8");
+    PIFPAF_CHECK_ARG(out_col_off % 16 == 0, "output column offset must be a multiple of 16");
     if (shuffle_src_tensor < 0) {
         g.mode = MODE_PLAIN;
         PIFPAF_CHECK_ARG(out_col_off + pad8(n_out) <= to.c, "output window outside the tensor");
@@ -1230,10 +1232,10 @@ int pifpaf_net_conv1x1(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off,
         PIFPAF_CHECK_ARG(n_out % 2 == 0, "fused channel_shuffle needs an even branch width");
         PIFPAF_CHECK_ARG(shuffle_src_col_off % 8 == 0 && shuffle_src_col_off + pad16(n_out) <= ts.c + 8,
                          "shuffle source window");
-        PIFPAF_CHECK_ARG(out_col_off == 0 && to.c == 2 * pad8(n_out), "shuffle output tensor must be 2*pad8(n_out) wide");
+        PIFPAF_CHECK_ARG(out_col_off == 0 && to.c >= 2 * n_out, "shuffle output tensor must hold 2*n_out channels");
         g.mode = MODE_SHUFFLE;
         g.src0 = ts.data; g.ld0 = ts.c; g.src0_col_off = shuffle_src_col_off;
-        g.half = n_out; g.gap = pad8(n_out) - n_out;
+        g.half = n_out; g.gap = 0;
         g.src_tma = gemm_smem_bytes(g.block_n, g.n_blocks, 2, true) <= 222 * 1024 ? 1 : 0;
         g.stages = choose_stages(g.block_n, g.n_blocks, g.num_k_blocks, g.src_tma != 0);
         op.smem = gemm_smem_bytes(g.block_n, g.n_blocks, g.stages, g.src_tma != 0);
@@ -1262,7 +1264,7 @@ int pifpaf_net_conv(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off, in
     const int ho = (tin.h + 2 * pad - kernel) / stride + 1, wo = (tin.w + 2 * pad - kernel) / stride + 1;
     PIFPAF_CHECK_ARG(to.h == ho && to.w == wo, "conv output tensor shape mismatch");
     PIFPAF_CHECK_ARG(in_col_off % 8 == 0 && in_col_off + c_in <= tin.c, "conv input column window");
-    PIFPAF_CHECK_ARG(out_col_off % 8 == 0 && out_col_off + pad8(n_out) <= to.c, "conv output column window");
+    PIFPAF_CHECK_ARG(out_col_off % 16 == 0 && out_col_off + pad8(n_out) <= to.c, "conv output column window");
     Op op; op.kind = OP_GEMM;
     int block_n, n_blocks;
     choose_block_n(n_out, &block_n, &n_blocks);

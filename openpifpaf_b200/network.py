@@ -13,12 +13,11 @@ a fused op list of libpifpaf_b200 (tcgen05 GEMMs for the 1x1 convolutions) and
 replays it.  torch.cat / chunk / channel_shuffle never run as kernels: they are
 folded into the physical channel placement computed here:
 
-  an activation with 2*half logical channels is stored as
-      [ half channels | gap | half channels | gap ],  gap = pad8(half) - half
-  so both halves start on 16-byte boundaries (TMA requirement); the last GEMM of
-  a block writes logical channel 2n <- pass-through[n], 2n+1 <- conv[n]
-  (== cat + channel_shuffle(groups=2), basenetworks.py:233-242) straight into
-  that layout, and the next block's chunk(2) is a column offset.
+  activations are stored in logical channel order (rows padded to 16 channels);
+  the last GEMM of a block writes logical channel 2n <- pass-through[n],
+  2n+1 <- conv[n] (== cat + channel_shuffle(groups=2), basenetworks.py:233-242)
+  with aligned 256-bit stores, and the next block's x.chunk(2) is just the TMA
+  start coordinate `half` of its A operand (TMA needs no alignment there).
 """
 import ctypes
 
@@ -38,6 +37,10 @@ SHUFFLENETV2K_CONFIGS = {     # network/factory.py:68-79
 
 def pad8(v):
     return (v + 7) // 8 * 8
+
+
+def pad16(v):
+    return (v + 15) // 16 * 16
 
 
 # ----------------------------------------------------------------------------- plans
@@ -218,23 +221,19 @@ class _DevArray:
 
 
 class _Layout:
-    """Physical column placement of a logical channel vector."""
+    """Physical column placement of a logical channel vector: physical == logical order, rows padded to a
+    multiple of 16 channels (32-byte aligned rows for 256-bit stores).  `split` marks tensors whose two
+    logical halves are consumed separately (x.chunk(2)): the second half starts at column `half`, which TMA
+    takes as a plain coordinate (no alignment requirement)."""
 
     def __init__(self, channels, split):
         self.channels = channels
         self.split = split
-        if split:
-            self.half = channels // 2
-            self.hp = pad8(self.half)
-            self.width = 2 * self.hp
-        else:
-            self.width = pad8(channels)
+        self.half = channels // 2 if split else None
+        self.width = pad16(channels)
 
     def cols(self):
-        l = np.arange(self.channels)
-        if not self.split:
-            return l
-        return l + (l >= self.half) * (self.hp - self.half)
+        return np.arange(self.channels)
 
 
 def _f32(a):
@@ -287,7 +286,7 @@ def build_ops(plan, in_h, in_w):
     h = (in_h + 2 * inp['pad'] - k) // inp['stride'] + 1
     w = (in_w + 2 * inp['pad'] - k) // inp['stride'] + 1
     c0 = inp['w'].shape[0]
-    cur = tensor(h, w, pad8(c0))
+    cur = tensor(h, w, pad16(c0))
     ops.append({'kind': 'input_conv', 'in_h': in_h, 'in_w': in_w, 'kernel': k, 'stride': inp['stride'],
                 'pad': inp['pad'], 'c_out': c0, 'w': _f32(inp['w']), 'b': _f32(inp['b']), 'relu': 1, 'out': cur})
     lay = _Layout(c0, split=False)
@@ -295,7 +294,7 @@ def build_ops(plan, in_h, in_w):
     for blocks in plan['stages']:
         for e in blocks:
             bf = e['b2_pw2'][0].shape[0]
-            hp = pad8(bf)
+            hp = pad16(bf)
             kk, st, pd = e['kernel'], e['stride'], e['pad']
             ho, wo = (h + 2 * pd - kk) // st + 1, (w + 2 * pd - kk) // st + 1
             out_lay = _Layout(2 * bf, split=True)
@@ -315,9 +314,9 @@ def build_ops(plan, in_h, in_w):
                 conv1x1(t_d, 0, np.arange(bf), hp, e['b2_pw2'], True, t_out, shuffle=(t_b, 0))
             else:
                 assert lay.split and lay.half == bf
-                # x1, x2 = x.chunk(2): x2 is the column window [hp, 2*hp)   (basenetworks.py:234-236)
+                # x1, x2 = x.chunk(2): x2 is the column window [bf, 2*bf)   (basenetworks.py:234-236)
                 t_c = tensor(h, w, hp)
-                conv1x1(cur, hp, np.arange(bf), bf, e['b2_pw1'], True, t_c)
+                conv1x1(cur, bf, np.arange(bf), bf, e['b2_pw1'], True, t_c)
                 t_d = tensor(ho, wo, hp)
                 dwconv(t_c, np.arange(bf), hp, e['b2_dw'], kk, st, pd, t_d)
                 conv1x1(t_d, 0, np.arange(bf), hp, e['b2_pw2'], True, t_out, shuffle=(cur, 0))
@@ -325,7 +324,7 @@ def build_ops(plan, in_h, in_w):
             block_outputs.append((cur, lay))
     w5, b5 = plan['conv5']
     c5 = w5.shape[0]
-    t5 = tensor(h, w, pad8(c5))
+    t5 = tensor(h, w, pad16(c5))
     conv1x1(cur, 0, lay.cols(), lay.width, (w5, b5), True, t5)
     heads = plan['heads']
     ops.append({'kind': 'heads', 'in': t5, 'k_cols': c5,
@@ -367,7 +366,7 @@ def _build_ops_resnet(plan, in_h, in_w):
     h = (in_h + 2 * inp['pad'] - k) // inp['stride'] + 1
     w = (in_w + 2 * inp['pad'] - k) // inp['stride'] + 1
     c0 = inp['w'].shape[0]
-    cur = tensor(h, w, pad8(c0))
+    cur = tensor(h, w, pad16(c0))
     ops.append({'kind': 'input_conv', 'in_h': in_h, 'in_w': in_w, 'kernel': k, 'stride': inp['stride'],
                 'pad': inp['pad'], 'c_out': c0, 'w': _f32(inp['w']), 'b': _f32(inp['b']), 'relu': 1, 'out': cur})
     c_cur = c0
@@ -379,12 +378,12 @@ def _build_ops_resnet(plan, in_h, in_w):
         if e['downsample'] is not None:
             ds = e['downsample']
             dh, dw_ = out_hw(h, w, ds)
-            identity = tensor(dh, dw_, pad8(ds['w'].shape[0]))
+            identity = tensor(dh, dw_, pad16(ds['w'].shape[0]))
             conv(cur, ds, False, identity)
         n_convs = len(e['convs'])
         for ci, ce in enumerate(e['convs']):
             oh, ow = out_hw(hh, ww, ce)
-            t_out = tensor(oh, ow, pad8(ce['w'].shape[0]))
+            t_out = tensor(oh, ow, pad16(ce['w'].shape[0]))
             last = ci == n_convs - 1
             conv(t_in, ce, True, t_out, residual=identity if last else -1)
             t_in, hh, ww = t_out, oh, ow

@@ -38,12 +38,8 @@ def run_ops(tensors, ops, images, bf16=False):
                 out[..., o['out_off']:o['out_off'] + n] = y
             else:
                 src = acts[o['shuffle_src']][..., o['shuffle_off']:o['shuffle_off'] + n]
-                half, gap = n, (n + 7) // 8 * 8 - n
-                logical = torch.empty(y.shape[:-1] + (2 * n,), dtype=torch.float32)
-                logical[..., 0::2] = src
-                logical[..., 1::2] = y
-                l = np.arange(2 * n)
-                out[..., l + (l >= half) * gap] = logical
+                out[..., 0:2 * n:2] = src
+                out[..., 1:2 * n:2] = y
         elif kind == 'conv':
             a = acts[o['in']][..., o['in_off']:o['in_off'] + o['c_in']].permute(0, 3, 1, 2)
             y = F.conv2d(a, q(torch.from_numpy(o['w'])), torch.from_numpy(o['b']), o['stride'], o['pad'])

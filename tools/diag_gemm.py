@@ -25,7 +25,7 @@ def ptr(a):
 
 
 def pad8(v):
-    return (v + 7) // 8 * 8
+    return (v + 15) // 16 * 16        # tensors are padded to 16 channels
 
 
 def run_case(h, w, B, K, N, in_off, shuffle, impl, seed=0):
@@ -36,7 +36,8 @@ def run_case(h, w, B, K, N, in_off, shuffle, impl, seed=0):
     cin_phys = pad8(in_off + K)
     _lib.check(L.pifpaf_net_tensor(net, h, w, cin_phys, ctypes.byref(tid))); t_in = tid.value
     hp = pad8(N)
-    _lib.check(L.pifpaf_net_tensor(net, h, w, 2 * hp if shuffle else hp, ctypes.byref(tid))); t_out = tid.value
+    wout = pad8(2 * N) if shuffle else hp
+    _lib.check(L.pifpaf_net_tensor(net, h, w, wout, ctypes.byref(tid))); t_out = tid.value
     t_src = -1
     if shuffle:
         _lib.check(L.pifpaf_net_tensor(net, h, w, hp, ctypes.byref(tid))); t_src = tid.value
@@ -50,16 +51,14 @@ def run_case(h, w, B, K, N, in_off, shuffle, impl, seed=0):
         _lib.check(L.pifpaf_net_set_tensor(net, t_src, B, ptr(src), src.size))
     _lib.check(L.pifpaf_net_conv1x1(net, t_in, in_off, K, N, ptr(wgt), ptr(bias), 1, t_out, 0, t_src, 0))
     _lib.check(L.pifpaf_net_forward(net, None, B, impl, None))
-    out = np.empty((B, h, w, 2 * hp if shuffle else hp), dtype=np.float32)
+    out = np.empty((B, h, w, wout), dtype=np.float32)
     _lib.check(L.pifpaf_net_tap_tensor(net, t_out, B, ptr(out), out.size))
     ref = np.maximum(a[..., in_off:in_off + K].astype(np.float64) @ wgt.astype(np.float64).T + bias, 0.0)
     if shuffle:
         logical = np.empty(ref.shape[:-1] + (2 * N,))
         logical[..., 0::2] = src[..., :N]
         logical[..., 1::2] = ref
-        l = np.arange(2 * N)
-        cols = l + (l >= N) * (hp - N)
-        got, want = out[..., cols], logical
+        got, want = out[..., :2 * N], logical
     else:
         got, want = out[..., :N], ref
     err = np.abs(got - want) / (np.abs(want) + 1.0)
@@ -76,7 +75,9 @@ def main():
         (8, 16, 1, 128, 64, 0, False),      # two k-blocks
         (8, 16, 1, 24, 176, 0, False),      # K < 64 (stem -> stage2), OOB k fill
         (12, 12, 1, 176, 176, 0, False),    # M = 144: partial second tile; K tail
-        (12, 12, 2, 174, 174, 176, False),  # x2 window at column offset, odd sizes
+        (12, 12, 2, 174, 174, 176, False),  # x2 window at an aligned column offset, odd sizes
+        (12, 12, 2, 174, 174, 174, False),  # x2 window at an UNALIGNED column offset (TMA coordinate 174)
+        (9, 11, 3, 87, 174, 87, True),      # odd (2-byte aligned) column offset
         (12, 12, 2, 176, 174, 0, True),     # fused shuffle
         (9, 11, 3, 352, 348, 0, True),      # two n-blocks
         (9, 11, 3, 696, 696, 0, False),     # 4 n-blocks, 11 k-blocks
