@@ -182,7 +182,8 @@ int pifpaf_net_input_conv(pifpaf_net_t* net, int32_t in_h, int32_t in_w, int32_t
  * shuffle_src_tensor < 0: plain output at columns [out_col_off, out_col_off+n_out) of out_tensor.
  * shuffle_src_tensor >= 0: fused cat + channel_shuffle(2) (basenetworks.py:233-242): output logical
  *   channel 2n <- shuffle_src[n], 2n+1 <- this conv[n], written contiguously (physical == logical order);
- *   in_col_off may be any column: the next block's x.chunk(2) is the TMA coordinate n_out. */
+ *   in_col_off must be a multiple of 8 (TMA coordinates must be 16-byte aligned): the next block's x.chunk(2)
+ *   starts its view at floor8(n_out) and zeroes the weight columns of the leading pass-through channels. */
 int pifpaf_net_conv1x1(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off, int32_t k_cols,
                        int32_t n_out, const float* weight, const float* bias, int32_t relu,
                        int32_t out_tensor, int32_t out_col_off,

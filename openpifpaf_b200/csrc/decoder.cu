@@ -33,6 +33,7 @@ constexpr int NW = NT / 32;
 constexpr int SORT_NT = 1024;
 constexpr int TILE = 32;           // CifHr tile edge in hi-res pixels
 constexpr int SC_CAP = 1024;       // per-warp score cache entries in k_grow
+constexpr int LIST_SMEM_ENTRIES = 8192;   // CAF list entries (c,x,y) staged in shared memory per image (96 KB)
 
 struct Dims {
     int B, F, C, K;
@@ -518,7 +519,9 @@ __global__ void __launch_bounds__(NT) k_caf_scored(const float* __restrict__ caf
 //   i1 = LAST index of the maximum score M;
 //   second = the running maximum of the prefix [0,i1) (last index on ties) unless
 //   a suffix element is strictly larger (first index on ties).
-__device__ Joint warp_blend(const float* __restrict__ L, int cap, int n, double x, double y,
+__device__ Joint warp_blend(const float* __restrict__ L, int cap, int n,
+                            const float* C0, const float* X1, const float* Y1,
+                            double x, double y,
                             double xy_scale, double filter_sigmas, bool only_max,
                             float* cache, int lane) {
     Joint zero; zero.v = 0.0; zero.x = 0.0; zero.y = 0.0; zero.s = 0.0;
@@ -527,10 +530,6 @@ __device__ Joint warp_blend(const float* __restrict__ L, int cap, int n, double 
     const float sigma2 = (float)(0.25 * xy_scale * xy_scale);
     const double xlo = x - (double)sigma_filter, xhi = x + (double)sigma_filter;
     const double ylo = y - (double)sigma_filter, yhi = y + (double)sigma_filter;
-    const float* C0 = L;
-    const float* X1 = L + cap;
-    const float* Y1 = L + 2 * (size_t)cap;
-
     auto score_at = [&](int i) -> float {
         const float ex = X1[i], ey = Y1[i];
         if ((double)ex < xlo) return -1.0f;
@@ -613,6 +612,9 @@ struct GrowCtx {
     int* new_edges;         // [2C]
     float* score_cache;     // [NW][SC_CAP]
     int* ctl;               // [8]: 0 heap_n, 1 n_new, 2 done
+    // the scanned components (c, x_src, y_src) of this image's CAF lists staged in shared memory
+    float* s_cxy;           // [3][LIST_SMEM_ENTRIES]
+    int* s_loff;            // [2C]: offset of list (caf_i*2 + dir) in s_cxy, or -1 if it did not fit
     // graph (global)
     const int* skeleton;    // [C][2]
     const int* adj_start;   // [K+1]
@@ -706,7 +708,15 @@ __device__ Joint warp_connection_value(GrowCtx& g, int edge, bool reverse_match_
     const int nf = g.list_counts[caf_i * 2 + (forward ? 0 : 1)];
     const int nb = g.list_counts[caf_i * 2 + (forward ? 1 : 0)];
     const Joint start_j = g.joints[start_i];
-    Joint new_j = warp_blend(Lf, g.hw, nf, start_j.x, start_j.y, start_j.s, filter_sigmas, false, cache, lane);
+    const int lif = caf_i * 2 + (forward ? 0 : 1), lib = caf_i * 2 + (forward ? 1 : 0);
+    const int of = g.s_loff[lif], ob = g.s_loff[lib];
+    const float* fC = of >= 0 ? g.s_cxy + of : Lf;
+    const float* fX = of >= 0 ? g.s_cxy + LIST_SMEM_ENTRIES + of : Lf + g.hw;
+    const float* fY = of >= 0 ? g.s_cxy + 2 * LIST_SMEM_ENTRIES + of : Lf + 2 * (size_t)g.hw;
+    const float* bC = ob >= 0 ? g.s_cxy + ob : Lb;
+    const float* bX = ob >= 0 ? g.s_cxy + LIST_SMEM_ENTRIES + ob : Lb + g.hw;
+    const float* bY = ob >= 0 ? g.s_cxy + 2 * LIST_SMEM_ENTRIES + ob : Lb + 2 * (size_t)g.hw;
+    Joint new_j = warp_blend(Lf, g.hw, nf, fC, fX, fY, start_j.x, start_j.y, start_j.s, filter_sigmas, false, cache, lane);
     if (new_j.v == 0.0) return new_j;
     new_j.v = sqrt(new_j.v * start_j.v);
     if (new_j.v < g.gp.keypoint_threshold || new_j.v < start_j.v * g.gp.keypoint_threshold_rel) {
@@ -714,7 +724,7 @@ __device__ Joint warp_connection_value(GrowCtx& g, int edge, bool reverse_match_
         return new_j;
     }
     if (g.gp.reverse_match && reverse_match_ && start_i < g.F) {
-        const Joint rev = warp_blend(Lb, g.hw, nb, new_j.x, new_j.y, new_j.s, filter_sigmas, false, cache, lane);
+        const Joint rev = warp_blend(Lb, g.hw, nb, bC, bX, bY, new_j.x, new_j.y, new_j.s, filter_sigmas, false, cache, lane);
         if (rev.v == 0.0) { new_j.v = 0.0; return new_j; }
         if (fabs(start_j.x - rev.x) + fabs(start_j.y - rev.y) > start_j.s) { new_j.v = 0.0; return new_j; }
     }
@@ -825,12 +835,41 @@ __device__ void grow_ctx_init(GrowCtx& g, unsigned char* smem, int K, int C) {
     g.heap_item = reinterpret_cast<int*>(smem + off); off += sizeof(int) * (2 * C + 2);
     g.new_edges = reinterpret_cast<int*>(smem + off); off += sizeof(int) * (2 * C + 2);
     g.ctl = reinterpret_cast<int*>(smem + off); off += sizeof(int) * 8;
+    g.s_loff = reinterpret_cast<int*>(smem + off); off += sizeof(int) * (2 * C + 2);
+    g.s_cxy = reinterpret_cast<float*>(smem + off); off += sizeof(float) * 3 * LIST_SMEM_ENTRIES;
     g.in_frontier = smem + off;
+}
+
+// Copy the scanned components of the image's CAF lists into shared memory (whole CTA; lists that do not fit stay
+// in global memory).  Must be called after g.lists / g.list_counts are set.
+__device__ void grow_stage_lists(GrowCtx& g) {
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int li = 0; li < 2 * g.C; li++) {
+            const int n = g.list_counts[li];
+            if (run + n <= LIST_SMEM_ENTRIES) { g.s_loff[li] = run; run += n; }
+            else g.s_loff[li] = -1;
+        }
+    }
+    __syncthreads();
+    for (int li = 0; li < 2 * g.C; li++) {
+        const int off = g.s_loff[li];
+        if (off < 0) continue;
+        const int n = g.list_counts[li];
+        const float* L = g.lists + ((size_t)li * 7) * g.hw;
+        for (int i = threadIdx.x; i < n; i += NT) {
+            g.s_cxy[off + i] = L[i];
+            g.s_cxy[LIST_SMEM_ENTRIES + off + i] = L[g.hw + i];
+            g.s_cxy[2 * LIST_SMEM_ENTRIES + off + i] = L[2 * (size_t)g.hw + i];
+        }
+    }
+    __syncthreads();
 }
 
 size_t grow_smem_bytes(int K, int C) {
     return sizeof(Joint) * K + sizeof(Joint) * 2 * C + sizeof(float) * NW * SC_CAP
-           + (sizeof(float) + 2 * sizeof(int)) * (2 * C + 2) + sizeof(int) * 8 + 2 * C + 16;
+           + (sizeof(float) + 2 * sizeof(int)) * (2 * C + 2) + sizeof(int) * 8 + sizeof(int) * (2 * C + 2)
+           + sizeof(float) * 3 * LIST_SMEM_ENTRIES + 2 * C + 16;
 }
 
 struct Graph {
@@ -857,6 +896,7 @@ __global__ void __launch_bounds__(NT) k_grow(Dims d, Graph gr, GrowParams gp,
     g.lists = lists + ((size_t)b * d.C * 2 * 7) * d.hw;
     g.list_counts = list_counts + (size_t)b * d.C * 2;
     g.K = d.K; g.C = d.C; g.F = d.F; g.hw = d.hw; g.gp = gp;
+    grow_stage_lists(g);
 
     Occ occ;
     occ.map = occ_map + (size_t)b * d.F * d.Ho * d.Wo;
@@ -946,6 +986,7 @@ __global__ void __launch_bounds__(NT) k_force_complete(Dims d, Graph gr, GrowPar
     g.lists = lists + ((size_t)b * d.C * 2 * 7) * d.hw;
     g.list_counts = list_counts + (size_t)b * d.C * 2;
     g.K = d.K; g.C = d.C; g.F = d.F; g.hw = d.hw; g.gp = gp;
+    grow_stage_lists(g);
     Joint* my_anns = anns + (size_t)b * d.max_ann * d.K;
     const int n = n_anns[b];
     for (int a = 0; a < n; a++) {
@@ -1094,7 +1135,8 @@ __global__ void __launch_bounds__(NT) k_pack(Dims d, const float4* __restrict__ 
 __global__ void k_blend_single(const float* __restrict__ L, int n, double x, double y, double s,
                                double filter_sigmas, int only_max, double* __restrict__ out) {
     __shared__ float cache[SC_CAP];
-    const Joint j = warp_blend(L, n, n, x, y, s, filter_sigmas, only_max != 0, cache, threadIdx.x & 31);
+    const Joint j = warp_blend(L, n, n, L, L + n, L + 2 * (size_t)n, x, y, s, filter_sigmas, only_max != 0, cache,
+                               threadIdx.x & 31);
     if (threadIdx.x == 0) { out[0] = j.x; out[1] = j.y; out[2] = j.s; out[3] = j.v; }
 }
 

@@ -167,7 +167,7 @@ struct HeadCol { int head; int plane; int op; int pad; };   // per GEMM output c
 
 struct GemmArgs {
     int M, N, K;                 // rows, real output channels, k extent (columns of the A view)
-    int a_col0;                  // first column of the A view inside its tensor (TMA coordinate; any value)
+    int a_col0;                  // first column of the A view inside its tensor (TMA coordinate; multiple of 8)
     int block_n, n_blocks, m_blocks, num_k_blocks, stages;
     int mode, relu;
     const float* bias;           // [n_blocks * block_n], zero padded
@@ -1084,7 +1084,9 @@ int choose_stages(int block_n, int n_blocks, int num_k_blocks, bool shuffle) {
 int emit_gemm(pifpaf_net* net, Op& op, int in_tensor, int in_col_off, int k_cols, int n_out,
               const float* weight, const float* bias) {
     const Tensor& tin = net->tensors[in_tensor];
-    PIFPAF_CHECK_ARG(in_col_off >= 0 && in_col_off + k_cols <= tin.c, "conv1x1 input column window outside the tensor");
+    // measured on B200: a TMA inner coordinate that is not 16-byte aligned raises an illegal-instruction fault
+    PIFPAF_CHECK_ARG(in_col_off >= 0 && in_col_off % 8 == 0 && in_col_off + k_cols <= tin.c,
+                     "conv1x1 input column window must start on a multiple of 8 channels and lie inside the tensor");
     int block_n, n_blocks;
     choose_block_n(n_out, &block_n, &n_blocks);
     const int n_pad = block_n * n_blocks;
@@ -1111,7 +1113,7 @@ int emit_gemm(pifpaf_net* net, Op& op, int in_tensor, int in_col_off, int k_cols
     op.flops_per_image = 2.0 * (double)op.rows_per_image * n_out * k_cols;
     op.bytes_per_image = (double)op.rows_per_image * k_cols * 2.0;      // A read once (bf16); outputs added by the caller
     op.weight_bytes = (double)n_out * k_cols * 2.0;
-    // the map covers the whole tensor; the view's first column is a TMA coordinate (no alignment needed).
+    // the map covers the whole tensor; the view's first column is a TMA coordinate (16-byte aligned).
     // Columns past the view multiply zero weight rows (B is zero padded), columns past the tensor are zero filled.
     rc = make_tmap(&op.tmap_a, tin.data, rows_max, (uint64_t)tin.c, (uint64_t)tin.c, BM);
     if (rc != PIFPAF_OK) return rc;

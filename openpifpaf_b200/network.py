@@ -16,8 +16,9 @@ folded into the physical channel placement computed here:
   activations are stored in logical channel order (rows padded to 16 channels);
   the last GEMM of a block writes logical channel 2n <- pass-through[n],
   2n+1 <- conv[n] (== cat + channel_shuffle(groups=2), basenetworks.py:233-242)
-  with aligned 256-bit stores, and the next block's x.chunk(2) is just the TMA
-  start coordinate `half` of its A operand (TMA needs no alignment there).
+  with aligned 256-bit stores, and the next block's x.chunk(2) is the TMA start
+  coordinate floor8(half) of its A operand (TMA coordinates must be 16-byte
+  aligned; the <= 7 leading pass-through columns meet zero weight columns).
 """
 import ctypes
 
@@ -223,8 +224,8 @@ class _DevArray:
 class _Layout:
     """Physical column placement of a logical channel vector: physical == logical order, rows padded to a
     multiple of 16 channels (32-byte aligned rows for 256-bit stores).  `split` marks tensors whose two
-    logical halves are consumed separately (x.chunk(2)): the second half starts at column `half`, which TMA
-    takes as a plain coordinate (no alignment requirement)."""
+    logical halves are consumed separately (x.chunk(2)): the second half starts at column `half`; its TMA
+    view starts at floor8(half) with zero weights on the leading columns."""
 
     def __init__(self, channels, split):
         self.channels = channels
@@ -314,9 +315,13 @@ def build_ops(plan, in_h, in_w):
                 conv1x1(t_d, 0, np.arange(bf), hp, e['b2_pw2'], True, t_out, shuffle=(t_b, 0))
             else:
                 assert lay.split and lay.half == bf
-                # x1, x2 = x.chunk(2): x2 is the column window [bf, 2*bf)   (basenetworks.py:234-236)
+                # x1, x2 = x.chunk(2): x2 is the column window [bf, 2*bf) (basenetworks.py:234-236).  TMA needs a
+                # 16-byte aligned start, so the view begins at floor8(bf); the up to 7 leading columns are
+                # pass-through channels and get zero weights.
+                a0 = bf // 8 * 8
+                lead = bf - a0
                 t_c = tensor(h, w, hp)
-                conv1x1(cur, bf, np.arange(bf), bf, e['b2_pw1'], True, t_c)
+                conv1x1(cur, a0, lead + np.arange(bf), lead + bf, e['b2_pw1'], True, t_c)
                 t_d = tensor(ho, wo, hp)
                 dwconv(t_c, np.arange(bf), hp, e['b2_dw'], kk, st, pd, t_d)
                 conv1x1(t_d, 0, np.arange(bf), hp, e['b2_pw2'], True, t_out, shuffle=(cur, 0))

@@ -76,8 +76,8 @@ def main():
         (8, 16, 1, 24, 176, 0, False),      # K < 64 (stem -> stage2), OOB k fill
         (12, 12, 1, 176, 176, 0, False),    # M = 144: partial second tile; K tail
         (12, 12, 2, 174, 174, 176, False),  # x2 window at an aligned column offset, odd sizes
-        (12, 12, 2, 174, 174, 174, False),  # x2 window at an UNALIGNED column offset (TMA coordinate 174)
-        (9, 11, 3, 87, 174, 87, True),      # odd (2-byte aligned) column offset
+        (12, 12, 2, 180, 174, 168, False),  # x2 view from floor8(174) (leading pass-through columns)
+        (9, 11, 3, 88, 174, 80, True),
         (12, 12, 2, 176, 174, 0, True),     # fused shuffle
         (9, 11, 3, 352, 348, 0, True),      # two n-blocks
         (9, 11, 3, 696, 696, 0, False),     # 4 n-blocks, 11 k-blocks
