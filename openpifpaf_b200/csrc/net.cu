@@ -1267,6 +1267,24 @@ int pifpaf_net_conv(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off, in
     PIFPAF_CHECK_ARG(to.h == ho && to.w == wo, "conv output tensor shape mismatch");
     PIFPAF_CHECK_ARG(in_col_off % 8 == 0 && in_col_off + c_in <= tin.c, "conv input column window");
     PIFPAF_CHECK_ARG(out_col_off % 16 == 0 && out_col_off + pad8(n_out) <= to.c, "conv output column window");
+    if (kernel == 1 && stride == 1 && pad == 0) {
+        // pointwise: the flat [pixels x channels] GEMM (no patch tiling waste), residual fused the same way
+        Op op; op.kind = OP_GEMM;
+        int rc = emit_gemm(net, op, in_tensor, in_col_off, c_in, n_out, weight, bias);
+        if (rc != PIFPAF_OK) return rc;
+        GemmArgs& g = op.g;
+        g.mode = MODE_PLAIN; g.relu = relu; g.out = to.data; g.ldo = to.c; g.out_col_off = out_col_off;
+        op.bytes_per_image += (double)op.rows_per_image * n_out * 2.0 * (residual_tensor >= 0 ? 2.0 : 1.0);
+        if (residual_tensor >= 0) {
+            PIFPAF_CHECK_ARG(residual_tensor < nt, "bad residual tensor");
+            const Tensor& tr = net->tensors[residual_tensor];
+            PIFPAF_CHECK_ARG(tr.h == ho && tr.w == wo && residual_col_off % 8 == 0 && residual_col_off + n_out <= tr.c,
+                             "residual tensor shape mismatch");
+            g.res = tr.data; g.ld_res = tr.c; g.res_col_off = residual_col_off;
+        }
+        net->ops.push_back(op);
+        return PIFPAF_OK;
+    }
     Op op; op.kind = OP_GEMM;
     int block_n, n_blocks;
     choose_block_n(n_out, &block_n, &n_blocks);
