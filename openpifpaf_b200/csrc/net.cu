@@ -175,6 +175,7 @@ struct GemmArgs {
     __nv_bfloat16* out; int ldo; int out_col_off;
     const __nv_bfloat16* src0; int ld0; int src0_col_off; int half; int gap;
     int src_tma;                 // pass-through tile arrives by TMA in shared memory (else read from global)
+    int b_resident;              // all K blocks of this CTA's weight tile stay in shared memory (loaded once)
     // heads
     const HeadCol* head_cols;    // [n_blocks * block_n]
     float* head_base[4]; int head_planes[4];
@@ -344,10 +345,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int a_bytes = BM * BK * 2;
     const int b_bytes = g.block_n * BK * 2;
-    const int stage_bytes = a_bytes + b_bytes;
+    // weights-resident mode: the ring carries only A; the CTA's weight tile (all K blocks of ONE n block) is
+    // loaded once -- weights are otherwise re-fetched from L2 for every M tile and outweigh the A traffic
+    const int stage_bytes = a_bytes + (g.b_resident ? 0 : b_bytes);
+    unsigned char* b_res = smem + (size_t)g.stages * stage_bytes;
+    const size_t b_res_bytes = g.b_resident ? (size_t)g.num_k_blocks * b_bytes : 0;
     // pass-through tiles of the fused shuffle: [2 accumulator stages][BM rows][block_n] bf16, filled by TMA
     const int src_bytes = g.src_tma ? BM * g.block_n * 2 : 0;
-    unsigned char* src_tiles = smem + (size_t)g.stages * stage_bytes;
+    unsigned char* src_tiles = b_res + b_res_bytes;
     float* bias_s = reinterpret_cast<float*>(src_tiles + 2 * (size_t)src_bytes);   // [n_blocks * block_n]
     unsigned char* tail = reinterpret_cast<unsigned char*>(bias_s + g.n_blocks * g.block_n);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);            // [stages]
@@ -355,7 +360,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
     uint64_t* tmem_full = empty_bar + g.stages;                         // [2]
     uint64_t* tmem_empty = tmem_full + 2;                               // [2]
     uint64_t* src_full = tmem_empty + 2;                                // [2]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(src_full + 2);
+    uint64_t* b_full = src_full + 2;                                    // [1]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tmem_cols = (2 * g.block_n <= 32) ? 32 : (2 * g.block_n <= 64) ? 64 : (2 * g.block_n <= 128) ? 128
@@ -373,6 +379,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
             for (int a = 0; a < 2; a++) {
                 mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], EPI_WARPS); mbar_init(&src_full[a], 1);
             }
+            mbar_init(b_full, 1);
             fence_barrier_init();
         }
         __syncwarp();
@@ -383,15 +390,29 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    const int num_tiles = g.m_blocks * g.n_blocks;
+    // tile schedule: streaming mode walks (m_blk, n_blk) tiles round-robin over the CTAs; weights-resident mode
+    // pins one n block per CTA (gridDim.x is a multiple of n_blocks) and walks M tiles only
+    const int num_tiles = g.b_resident ? 0 : g.m_blocks * g.n_blocks;
+    const int my_n = g.b_resident ? (int)(blockIdx.x % g.n_blocks) : 0;
+    const int m_first = g.b_resident ? (int)(blockIdx.x / g.n_blocks) : 0;
+    const int m_step = g.b_resident ? (int)(gridDim.x / g.n_blocks) : 0;
+#define PIFPAF_TILE_LOOP(m_blk, n_blk)                                                                             \
+    for (int it__ = g.b_resident ? m_first : (int)blockIdx.x, m_blk = 0, n_blk = 0;                                 \
+         (g.b_resident ? it__ < g.m_blocks : it__ < num_tiles) &&                                                   \
+         ((m_blk = g.b_resident ? it__ : it__ / g.n_blocks), (n_blk = g.b_resident ? my_n : it__ % g.n_blocks), true); \
+         it__ += g.b_resident ? m_step : (int)gridDim.x)
 
     if (warp == 0) {
         // ===== TMA producer (one elected lane) =====
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             int sacc = 0; uint32_t sacc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_blk = tile / g.n_blocks, n_blk = tile % g.n_blocks;
+            if (g.b_resident) {
+                mbar_expect_tx(b_full, (uint32_t)b_res_bytes);
+                for (int kb = 0; kb < g.num_k_blocks; kb++)
+                    tma_load_2d(b_res + (size_t)kb * b_bytes, &tmap_b, b_full, kb * BK, my_n * g.block_n);
+            }
+            PIFPAF_TILE_LOOP(m_blk, n_blk) {
                 int cb = 0, cy = 0, cx = 0, cimg = 0;
                 if (g.conv_k > 0) {
                     const int per_img = g.tiles_x * g.tiles_y;
@@ -412,7 +433,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
                     } else {
                         tma_load_2d(sa, &tmap_a, &full_bar[stage], g.a_col0 + kb * BK, m_blk * BM);
                     }
-                    tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * g.block_n);
+                    if (!g.b_resident) tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * g.block_n);
                     if (++stage == g.stages) { stage = 0; phase ^= 1; }
                 }
                 if (g.src_tma) {
@@ -432,7 +453,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
             const uint32_t idesc = make_instr_desc(BM, g.block_n);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            if (g.b_resident) mbar_wait(b_full, 0);
+            PIFPAF_TILE_LOOP(m_blk, n_blk) {
+                (void)m_blk; (void)n_blk;
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * g.block_n);
@@ -440,7 +463,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
                     mbar_wait(&full_bar[stage], phase);
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint32_t sb = sa + a_bytes;
+                    const uint32_t sb = g.b_resident ? smem_u32(b_res + (size_t)kb * b_bytes) : sa + a_bytes;
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; k++) {
                         const uint64_t adesc = make_smem_desc(sa + k * UMMA_K * 2);
@@ -463,8 +486,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
         const int c_begin = n_chunks * part / parts;
         const int c_end = n_chunks * (part + 1) / parts;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_blk = tile / g.n_blocks, n_blk = tile % g.n_blocks;
+        PIFPAF_TILE_LOOP(m_blk, n_blk) {
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
             if (g.src_tma) mbar_wait(&src_full[acc], acc_phase);
@@ -657,25 +679,31 @@ __global__ void __launch_bounds__(256) k_dwconv5(DwArgs a) {
     }
 }
 
-// Depthwise 5x5 with TMA-staged input tiles: a persistent CTA walks (channel block, image, tile) work items; one
-// elected thread streams the (TH*S+4-S+1) x (TW*S+4-S+1) x 64-channel input window of the NEXT items into a
-// double-buffered shared-memory ring (4-D tensor map, out-of-bounds zero fill == the conv padding) while the
-// 256 threads (8 channel groups x 32 pixel lanes) compute OX outputs x 8 channels each from shared memory.
-template <int S, int OX, int TH, int TW>
+// Depthwise 5x5 with TMA-staged input tiles.  A persistent CTA walks (channel block, image, tile) work items; one
+// elected thread streams the input window of the NEXT items ((TH-1)*S+5 x (TW-1)*S+5 pixels x 64 channels, 4-D
+// tensor map, out-of-bounds zero fill == the conv padding) into a double-buffered shared-memory ring.
+// Compute mapping (register blocking in BOTH spatial directions): one warp = one 4x4 block of output pixels,
+// one lane = one channel pair.  The lane keeps its 25x2 weights and a 4x4x2 f32 accumulator in registers and
+// reads every input pixel of the block's (3S+5)^2 window exactly once (4 bytes per lane, 128 bytes per warp
+// request: one conflict-free wavefront), i.e. 4 (S=1) / 7.6 (S=2) shared-memory reads per output instead of
+// 10 / 17.5 with row strips.
+template <int S, int TH, int TW>
 struct DwTile {
     static constexpr int IH = (TH - 1) * S + 5, IW = (TW - 1) * S + 5;
     static constexpr int BYTES = IH * IW * 64 * 2;
-    static constexpr int NCOL = (OX - 1) * S + 5;
-    static_assert(TH * (TW / OX) == 32, "32 pixel lanes");
+    static constexpr int WARPS = (TH / 4) * (TW / 4);
+    static constexpr int THREADS = WARPS * 32;
+    static constexpr int WIN = 3 * S + 5;       // input window edge of a 4x4 output block
 };
 
-template <int S, int OX, int TH, int TW>
-__global__ void __launch_bounds__(256, 2) k_dwconv5_tma(const __grid_constant__ CUtensorMap tmap_in, DwArgs a) {
-    using T = DwTile<S, OX, TH, TW>;
+template <int S, int TH, int TW>
+__global__ void __launch_bounds__(DwTile<S, TH, TW>::THREADS, 2)
+k_dwconv5_tma(const __grid_constant__ CUtensorMap tmap_in, DwArgs a) {
+    using T = DwTile<S, TH, TW>;
     extern __shared__ __align__(128) unsigned char dsm_raw[];
     unsigned char* dsm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dsm_raw) + 127) & ~uintptr_t(127));
     __shared__ uint64_t full[2];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles_x = (a.Wout + TW - 1) / TW, tiles_y = (a.Hout + TH - 1) / TH;
     const int cblks = (a.C8 + 7) / 8;
     const int per_c = a.B * tiles_y * tiles_x;
@@ -702,69 +730,77 @@ __global__ void __launch_bounds__(256, 2) k_dwconv5_tma(const __grid_constant__ 
         if ((int)blockIdx.x < total) issue(blockIdx.x, 0);
         if ((int)(blockIdx.x + gridDim.x) < total) issue(blockIdx.x + gridDim.x, 1);
     }
-    const int cg = tid & 7, pl = tid >> 3;            // channel group, pixel lane
-    const int yl = pl / (TW / OX), sx = pl % (TW / OX);
-    uint32_t phase[2] = {0, 0};
+    const int by = warp / (TW / 4), bx = warp % (TW / 4);       // 4x4 output block of this warp inside the tile
+    uint32_t phase0 = 0, phase1 = 0;
     int it = 0;
+    int w_cblk = -1;
+    float wgt[25][2];
+    float bias0 = 0.f, bias1 = 0.f;
     for (int w = blockIdx.x; w < total; w += gridDim.x, it++) {
         const int buf = it & 1;
         const int cblk = w / per_c; int r = w - cblk * per_c;
         const int b = r / (tiles_y * tiles_x); r -= b * tiles_y * tiles_x;
         const int ty = r / tiles_x, tx = r - ty * tiles_x;
-        const int c0 = cblk * 64 + cg * 8;
-        mbar_wait(&full[buf], phase[buf]);
-        phase[buf] ^= 1;
-        const int oy = ty * TH + yl, ox0 = tx * TW + sx * OX;
-        if (c0 < C && oy < a.Hout && ox0 < a.Wout) {
-            const unsigned char* tile = dsm + (size_t)buf * T::BYTES;
-            float acc[OX][8];
-            {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + c0));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + c0 + 4));
+        const int c0 = cblk * 64 + lane * 2;
+        if (cblk != w_cblk) {                       // (re)load this lane's weights: rarely, the block index is slowest
+            w_cblk = cblk;
+            const bool cok = c0 < C;
 #pragma unroll
-                for (int o = 0; o < OX; o++) {
-                    acc[o][0] = b0.x; acc[o][1] = b0.y; acc[o][2] = b0.z; acc[o][3] = b0.w;
-                    acc[o][4] = b1.x; acc[o][5] = b1.y; acc[o][6] = b1.z; acc[o][7] = b1.w;
-                }
+            for (int tp = 0; tp < 25; tp++) {
+                const float2 wv = cok ? __ldg(reinterpret_cast<const float2*>(a.weight + (size_t)tp * C + c0))
+                                      : make_float2(0.f, 0.f);
+                wgt[tp][0] = wv.x; wgt[tp][1] = wv.y;
             }
+            const float2 bv = cok ? __ldg(reinterpret_cast<const float2*>(a.bias + c0)) : make_float2(0.f, 0.f);
+            bias0 = bv.x; bias1 = bv.y;
+        }
+        if (buf == 0) { mbar_wait(&full[0], phase0); phase0 ^= 1; }
+        else { mbar_wait(&full[1], phase1); phase1 ^= 1; }
+        const int oy0 = ty * TH + by * 4, ox0 = tx * TW + bx * 4;
+        if (c0 < C && oy0 < a.Hout && ox0 < a.Wout) {
+            const unsigned char* tile = dsm + (size_t)buf * T::BYTES + lane * 4;
+            float acc[4][4][2];
 #pragma unroll
-            for (int ky = 0; ky < 5; ky++) {
-                float wv[5][8];
+            for (int i = 0; i < 4; i++)
 #pragma unroll
-                for (int kx = 0; kx < 5; kx++) {
-                    const float* wp = a.weight + (size_t)(ky * 5 + kx) * C + c0;
-                    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp));
-                    const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
-                    wv[kx][0] = w0.x; wv[kx][1] = w0.y; wv[kx][2] = w0.z; wv[kx][3] = w0.w;
-                    wv[kx][4] = w1.x; wv[kx][5] = w1.y; wv[kx][6] = w1.z; wv[kx][7] = w1.w;
+                for (int j = 0; j < 4; j++) { acc[i][j][0] = bias0; acc[i][j][1] = bias1; }
+#pragma unroll
+            for (int ry = 0; ry < T::WIN; ry++) {
+                float f[T::WIN][2];
+                const unsigned char* rowp = tile + ((size_t)(by * 4 * S + ry) * T::IW + bx * 4 * S) * 128;
+#pragma unroll
+                for (int cx = 0; cx < T::WIN; cx++) {
+                    const uint32_t v = *reinterpret_cast<const uint32_t*>(rowp + (size_t)cx * 128);
+                    f[cx][0] = __uint_as_float(v << 16);
+                    f[cx][1] = __uint_as_float(v & 0xffff0000u);
                 }
-                const unsigned char* rowp = tile + ((size_t)(yl * S + ky) * T::IW + sx * OX * S) * 128 + cg * 16;
 #pragma unroll
-                for (int col = 0; col < T::NCOL; col++) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(rowp + (size_t)col * 128);
-                    float f[8];
-                    unpack8(v, f);
+                for (int i = 0; i < 4; i++) {
+                    const int ky = ry - i * S;                    // compile-time after unrolling
+                    if (ky < 0 || ky >= 5) continue;
 #pragma unroll
-                    for (int o = 0; o < OX; o++) {
-                        const int kx = col - o * S;
-                        if (kx < 0 || kx >= 5) continue;
+                    for (int j = 0; j < 4; j++) {
 #pragma unroll
-                        for (int j = 0; j < 8; j++) acc[o][j] = fmaf(f[j], wv[kx][j], acc[o][j]);
+                        for (int kx = 0; kx < 5; kx++) {
+                            acc[i][j][0] = fmaf(f[j * S + kx][0], wgt[ky * 5 + kx][0], acc[i][j][0]);
+                            acc[i][j][1] = fmaf(f[j * S + kx][1], wgt[ky * 5 + kx][1], acc[i][j][1]);
+                        }
                     }
                 }
             }
 #pragma unroll
-            for (int o = 0; o < OX; o++) {
-                const int ox = ox0 + o;
-                if (ox >= a.Wout) continue;
-                if (a.relu) {
+            for (int i = 0; i < 4; i++) {
+                const int oy = oy0 + i;
+                if (oy >= a.Hout) continue;
 #pragma unroll
-                    for (int j = 0; j < 8; j++) acc[o][j] = fmaxf(acc[o][j], 0.f);
+                for (int j = 0; j < 4; j++) {
+                    const int ox = ox0 + j;
+                    if (ox >= a.Wout) continue;
+                    float v0 = acc[i][j][0], v1 = acc[i][j][1];
+                    if (a.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+                    *reinterpret_cast<uint32_t*>(a.out + ((size_t)(b * a.Hout + oy) * a.Wout + ox) * a.ld_out +
+                                                 a.out_col_off + c0) = pack_bf16(v0, v1);
                 }
-                uint4 ov;
-                ov.x = pack_bf16(acc[o][0], acc[o][1]); ov.y = pack_bf16(acc[o][2], acc[o][3]);
-                ov.z = pack_bf16(acc[o][4], acc[o][5]); ov.w = pack_bf16(acc[o][6], acc[o][7]);
-                *reinterpret_cast<uint4*>(a.out + ((size_t)(b * a.Hout + oy) * a.Wout + ox) * a.ld_out + a.out_col_off + c0) = ov;
             }
         }
         __syncthreads();                                // everyone is done with this buffer
@@ -774,6 +810,11 @@ __global__ void __launch_bounds__(256, 2) k_dwconv5_tma(const __grid_constant__ 
         }
     }
 }
+
+// tile shapes: stride 1 -> 8x16 outputs (8 warps, 30 KB window); stride 2 -> 8x8 outputs (4 warps, 46 KB window)
+constexpr int DW1_TH = 8, DW1_TW = 16, DW2_TH = 8, DW2_TW = 8;
+using DwS1 = DwTile<1, DW1_TH, DW1_TW>;
+using DwS2 = DwTile<2, DW2_TH, DW2_TW>;
 
 // generic depthwise kxk (any kernel/stride): one output pixel x 8 channels per thread
 __global__ void __launch_bounds__(256) k_dwconv(DwArgs a) {
@@ -830,47 +871,66 @@ struct InConvArgs {
     int B, Hin, Win, Hout, Wout, C8, kernel, stride, pad, relu;
 };
 
+template <int KS>
 __global__ void __launch_bounds__(256) k_input_conv(InConvArgs a) {
-    extern __shared__ float s_w[];      // weights + bias
+    // one thread = one output pixel, all output channels: the 3*k*k input samples are loaded once (registers for
+    // k = 3, thread-local memory for k = 7) and reused for every 8-channel group; weights are broadcast reads
+    // from shared memory
+    extern __shared__ __align__(16) float s_w[];      // [3*k*k][C] weights + [C] bias
+    constexpr int TAPS = 3 * KS * KS;
     const int C = a.C8 * 8;
-    const int n_w = 3 * a.kernel * a.kernel * C;
+    const int n_w = TAPS * C;
     for (int i = threadIdx.x; i < n_w; i += blockDim.x) s_w[i] = a.weight[i];
     for (int i = threadIdx.x; i < C; i += blockDim.x) s_w[n_w + i] = a.bias[i];
     __syncthreads();
-    const long long total = (long long)a.B * a.Hout * a.Wout * a.C8;
+    const long long total = (long long)a.B * a.Hout * a.Wout;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (long long)gridDim.x * blockDim.x) {
-        const int c8 = (int)(t % a.C8);
-        long long p = t / a.C8;
+        long long p = t;
         const int ox = (int)(p % a.Wout); p /= a.Wout;
         const int oy = (int)(p % a.Hout);
         const int b = (int)(p / a.Hout);
-        float acc[8];
+        float in[TAPS];
 #pragma unroll
-        for (int j = 0; j < 8; j++) acc[j] = s_w[n_w + c8 * 8 + j];
         for (int ci = 0; ci < 3; ci++) {
             const float* plane = a.in + ((size_t)b * 3 + ci) * a.Hin * a.Win;
-            for (int ky = 0; ky < a.kernel; ky++) {
-                const int iy = oy * a.stride - a.pad + ky;
-                if (iy < 0 || iy >= a.Hin) continue;
-                for (int kx = 0; kx < a.kernel; kx++) {
-                    const int ix = ox * a.stride - a.pad + kx;
-                    if (ix < 0 || ix >= a.Win) continue;
-                    const float v = __ldg(plane + (size_t)iy * a.Win + ix);
-                    const float* wp = s_w + (size_t)((ci * a.kernel + ky) * a.kernel + kx) * C + c8 * 8;
 #pragma unroll
-                    for (int j = 0; j < 8; j++) acc[j] = fmaf(v, wp[j], acc[j]);
+            for (int ky = 0; ky < KS; ky++) {
+                const int iy = oy * a.stride - a.pad + ky;
+#pragma unroll
+                for (int kx = 0; kx < KS; kx++) {
+                    const int ix = ox * a.stride - a.pad + kx;
+                    const bool ok = iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win;
+                    in[(ci * KS + ky) * KS + kx] = ok ? __ldg(plane + (size_t)iy * a.Win + ix) : 0.f;
                 }
             }
         }
-        if (a.relu) {
+        __nv_bfloat16* orow = a.out + ((size_t)(b * a.Hout + oy) * a.Wout + ox) * a.ld_out;
+        for (int c8 = 0; c8 < a.C8; c8++) {
+            float acc[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(s_w + n_w + c8 * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(s_w + n_w + c8 * 8 + 4);
+            acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
+            acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
 #pragma unroll
-            for (int j = 0; j < 8; j++) acc[j] = fmaxf(acc[j], 0.f);
+            for (int tp = 0; tp < TAPS; tp++) {
+                const float4 w0 = *reinterpret_cast<const float4*>(s_w + (size_t)tp * C + c8 * 8);
+                const float4 w1 = *reinterpret_cast<const float4*>(s_w + (size_t)tp * C + c8 * 8 + 4);
+                const float v = in[tp];
+                acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
+                acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+                acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
+                acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+            }
+            if (a.relu) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[j] = fmaxf(acc[j], 0.f);
+            }
+            uint4 o;
+            o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
+            o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
+            *reinterpret_cast<uint4*>(orow + c8 * 8) = o;
         }
-        uint4 o;
-        o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
-        o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
-        *reinterpret_cast<uint4*>(a.out + ((size_t)(b * a.Hout + oy) * a.Wout + ox) * a.ld_out + c8 * 8) = o;
     }
 }
 
@@ -1068,16 +1128,35 @@ void choose_block_n(int n_out, int* block_n, int* n_blocks) {
     *block_n = 16; *n_blocks = np / 16;
 }
 
-size_t gemm_smem_bytes(int block_n, int n_blocks, int stages, bool shuffle) {
-    return 1024 + (size_t)stages * (BM * BK * 2 + block_n * BK * 2) + (shuffle ? 2 * (size_t)BM * block_n * 2 : 0) +
-           (size_t)n_blocks * block_n * 4 + (2 * stages + 6) * 8 + 64;
+constexpr size_t GEMM_SMEM_BUDGET = 222 * 1024;
+
+size_t gemm_smem_bytes(int block_n, int n_blocks, int stages, bool shuffle, bool b_resident = false, int num_k_blocks = 0) {
+    const size_t b_stage = b_resident ? 0 : (size_t)block_n * BK * 2;
+    const size_t b_res = b_resident ? (size_t)num_k_blocks * block_n * BK * 2 : 0;
+    return 1024 + (size_t)stages * (BM * BK * 2 + b_stage) + b_res + (shuffle ? 2 * (size_t)BM * block_n * 2 : 0) +
+           (size_t)n_blocks * block_n * 4 + (2 * stages + 7) * 8 + 64;
 }
 
 int choose_stages(int block_n, int n_blocks, int num_k_blocks, bool shuffle) {
-    const size_t budget = 222 * 1024;
     int stages = std::min(8, std::max(2, num_k_blocks * 2));
-    while (stages > 2 && gemm_smem_bytes(block_n, n_blocks, stages, shuffle) > budget) stages--;
+    while (stages > 2 && gemm_smem_bytes(block_n, n_blocks, stages, shuffle) > GEMM_SMEM_BUDGET) stages--;
     return stages;
+}
+
+// weights-resident mode if the whole weight tile plus >= 3 A stages (and the pass-through double buffer) fit
+void plan_gemm_smem(GemmArgs& g, size_t* smem, bool src_tma) {
+    g.b_resident = 0;
+    if (g.conv_k == 0 && g.mode != MODE_HEADS &&
+        gemm_smem_bytes(g.block_n, g.n_blocks, 3, src_tma, true, g.num_k_blocks) <= GEMM_SMEM_BUDGET) {
+        int stages = 8;
+        while (gemm_smem_bytes(g.block_n, g.n_blocks, stages, src_tma, true, g.num_k_blocks) > GEMM_SMEM_BUDGET) stages--;
+        g.b_resident = 1;
+        g.stages = stages;
+        *smem = gemm_smem_bytes(g.block_n, g.n_blocks, stages, src_tma, true, g.num_k_blocks);
+        return;
+    }
+    g.stages = choose_stages(g.block_n, g.n_blocks, g.num_k_blocks, src_tma);
+    *smem = gemm_smem_bytes(g.block_n, g.n_blocks, g.stages, src_tma);
 }
 
 // common GEMM emit: weights [n_out][k_cols] f32 host -> bf16 [n_pad][k_pad8] device, bias padded
@@ -1142,10 +1221,10 @@ int pifpaf_net_create(pifpaf_net_t** out, int32_t device, int32_t max_batch) {
     pifpaf_net* net = new pifpaf_net();
     net->device = device; net->max_batch = max_batch; net->n_sm = prop.multiProcessorCount;
     PIFPAF_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    PIFPAF_CUDA_TRY(cudaFuncSetAttribute(k_dwconv5_tma<1, 4, 8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         2 * DwTile<1, 4, 8, 16>::BYTES + 128));
-    PIFPAF_CUDA_TRY(cudaFuncSetAttribute(k_dwconv5_tma<2, 2, 4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         2 * DwTile<2, 2, 4, 16>::BYTES + 128));
+    PIFPAF_CUDA_TRY(cudaFuncSetAttribute(k_dwconv5_tma<1, DW1_TH, DW1_TW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         2 * DwS1::BYTES + 128));
+    PIFPAF_CUDA_TRY(cudaFuncSetAttribute(k_dwconv5_tma<2, DW2_TH, DW2_TW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         2 * DwS2::BYTES + 128));
     *out = net;
     return PIFPAF_OK;
 }
@@ -1178,6 +1257,7 @@ int pifpaf_net_input_conv(pifpaf_net_t* net, int32_t in_h, int32_t in_w, int32_t
     const Tensor& to = net->tensors[out_tensor];
     const int ho = (in_h + 2 * pad - kernel) / stride + 1, wo = (in_w + 2 * pad - kernel) / stride + 1;
     PIFPAF_CHECK_ARG(to.h == ho && to.w == wo && to.c >= pad8(c_out), "output tensor shape mismatch");
+    PIFPAF_CHECK_ARG(kernel == 1 || kernel == 3 || kernel == 5 || kernel == 7, "input conv kernel must be 1, 3, 5 or 7");
     PIFPAF_CUDA_TRY(cudaSetDevice(net->device));
     const int C = pad8(c_out);
     std::vector<float> w((size_t)3 * kernel * kernel * C, 0.f), b(C, 0.f);
@@ -1238,15 +1318,14 @@ int pifpaf_net_conv1x1(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off,
         g.mode = MODE_SHUFFLE;
         g.src0 = ts.data; g.ld0 = ts.c; g.src0_col_off = shuffle_src_col_off;
         g.half = n_out; g.gap = 0;
-        g.src_tma = gemm_smem_bytes(g.block_n, g.n_blocks, 2, true) <= 222 * 1024 ? 1 : 0;
-        g.stages = choose_stages(g.block_n, g.n_blocks, g.num_k_blocks, g.src_tma != 0);
-        op.smem = gemm_smem_bytes(g.block_n, g.n_blocks, g.stages, g.src_tma != 0);
+        g.src_tma = gemm_smem_bytes(g.block_n, g.n_blocks, 2, true) <= GEMM_SMEM_BUDGET ? 1 : 0;
         // pass-through tile [BM rows][block_n cols], dense rows in shared memory (no swizzle)
         rc = make_tmap_plain(&op.tmap_src, ts.data + shuffle_src_col_off, (uint64_t)net->max_batch * ts.h * ts.w,
                              (uint64_t)std::min(ts.c - shuffle_src_col_off, pad16(n_out)), (uint64_t)ts.c,
                              (uint32_t)g.block_n, BM);
         if (rc != PIFPAF_OK) return rc;
     }
+    plan_gemm_smem(g, &op.smem, g.src_tma != 0);
     net->ops.push_back(op);
     return PIFPAF_OK;
 }
@@ -1282,6 +1361,7 @@ int pifpaf_net_conv(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off, in
                              "residual tensor shape mismatch");
             g.res = tr.data; g.ld_res = tr.c; g.res_col_off = residual_col_off;
         }
+        plan_gemm_smem(g, &op.smem, false);
         net->ops.push_back(op);
         return PIFPAF_OK;
     }
@@ -1366,8 +1446,8 @@ int pifpaf_net_dwconv(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off, 
     op.flops_per_image = 2.0 * ho * wo * channels * (double)kernel * kernel;
     op.bytes_per_image = ((double)tin.h * tin.w + (double)ho * wo) * channels * 2.0;
     if (kernel == 5 && (stride == 1 || stride == 2)) {
-        const uint32_t bw = stride == 1 ? DwTile<1, 4, 8, 16>::IW : DwTile<2, 2, 4, 16>::IW;
-        const uint32_t bh = stride == 1 ? DwTile<1, 4, 8, 16>::IH : DwTile<2, 2, 4, 16>::IH;
+        const uint32_t bw = stride == 1 ? DwS1::IW : DwS2::IW;
+        const uint32_t bh = stride == 1 ? DwS1::IH : DwS2::IH;
         rc = make_tmap_dw(&op.tmap_dw, tin.data + in_col_off, (uint64_t)C, (uint64_t)tin.w, (uint64_t)tin.h,
                           (uint64_t)net->max_batch, (uint64_t)tin.c, bw, bh);
         if (rc != PIFPAF_OK) return rc;
@@ -1438,10 +1518,13 @@ static int net_forward_impl(pifpaf_net_t* net, const float* images_dev, int32_t 
         if (op.kind == OP_INPUT_CONV) {
             InConvArgs a = op.ic;
             a.in = images_dev; a.B = batch;
-            const long long total = (long long)batch * a.Hout * a.Wout * a.C8;
+            const long long total = (long long)batch * a.Hout * a.Wout;
             const int grid = (int)std::min<long long>((total + 255) / 256, (long long)net->n_sm * 16);
             const size_t smem = sizeof(float) * ((size_t)3 * a.kernel * a.kernel * a.C8 * 8 + a.C8 * 8);
-            k_input_conv<<<grid, 256, smem, st>>>(a);
+            if (a.kernel == 3) k_input_conv<3><<<grid, 256, smem, st>>>(a);
+            else if (a.kernel == 7) k_input_conv<7><<<grid, 256, smem, st>>>(a);
+            else if (a.kernel == 5) k_input_conv<5><<<grid, 256, smem, st>>>(a);
+            else k_input_conv<1><<<grid, 256, smem, st>>>(a);
             PIFPAF_LAUNCH_CHECK();
         } else if (op.kind == OP_DW) {
             DwArgs a = op.dw;
@@ -1449,15 +1532,15 @@ static int net_forward_impl(pifpaf_net_t* net, const float* images_dev, int32_t 
             if (op.dw_tma && gemm_impl == 0) {
                 const int cblks = (a.C8 + 7) / 8;
                 if (a.stride == 1) {
-                    using T = DwTile<1, 4, 8, 16>;
-                    const long long total = (long long)batch * ((a.Hout + 7) / 8) * ((a.Wout + 15) / 16) * cblks;
+                    const long long total = (long long)batch * ((a.Hout + DW1_TH - 1) / DW1_TH) *
+                                            ((a.Wout + DW1_TW - 1) / DW1_TW) * cblks;
                     const int grid = (int)std::min<long long>(total, (long long)net->n_sm * 3);
-                    k_dwconv5_tma<1, 4, 8, 16><<<grid, 256, 2 * T::BYTES + 128, st>>>(op.tmap_dw, a);
+                    k_dwconv5_tma<1, DW1_TH, DW1_TW><<<grid, DwS1::THREADS, 2 * DwS1::BYTES + 128, st>>>(op.tmap_dw, a);
                 } else {
-                    using T = DwTile<2, 2, 4, 16>;
-                    const long long total = (long long)batch * ((a.Hout + 3) / 4) * ((a.Wout + 15) / 16) * cblks;
+                    const long long total = (long long)batch * ((a.Hout + DW2_TH - 1) / DW2_TH) *
+                                            ((a.Wout + DW2_TW - 1) / DW2_TW) * cblks;
                     const int grid = (int)std::min<long long>(total, (long long)net->n_sm * 2);
-                    k_dwconv5_tma<2, 2, 4, 16><<<grid, 256, 2 * T::BYTES + 128, st>>>(op.tmap_dw, a);
+                    k_dwconv5_tma<2, DW2_TH, DW2_TW><<<grid, DwS2::THREADS, 2 * DwS2::BYTES + 128, st>>>(op.tmap_dw, a);
                 }
             } else if (a.kernel == 5 && (a.stride == 1 || a.stride == 2)) {
                 const long long total = (long long)batch * ((a.Hout + DW_OY - 1) / DW_OY) * DW_OY *
@@ -1481,7 +1564,8 @@ static int net_forward_impl(pifpaf_net_t* net, const float* images_dev, int32_t 
                 k_gemm_simt<<<grid, 128, 0, st>>>(g);
             } else {
                 const int tiles = g.m_blocks * g.n_blocks;
-                const int grid = std::min(tiles, net->n_sm);
+                int grid = std::min(tiles, net->n_sm);
+                if (g.b_resident) grid = std::max(1, std::min(net->n_sm / g.n_blocks, g.m_blocks)) * g.n_blocks;
                 k_gemm_tc<<<grid, GEMM_THREADS, op.smem, st>>>(op.tmap_a, op.tmap_b,
                                                                 g.src_tma ? op.tmap_src : op.tmap_a, g);
             }
