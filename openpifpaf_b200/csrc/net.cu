@@ -1534,7 +1534,8 @@ static int net_forward_impl(pifpaf_net_t* net, const float* images_dev, int32_t 
                 if (a.stride == 1) {
                     const long long total = (long long)batch * ((a.Hout + DW1_TH - 1) / DW1_TH) *
                                             ((a.Wout + DW1_TW - 1) / DW1_TW) * cblks;
-                    const int grid = (int)std::min<long long>(total, (long long)net->n_sm * 3);
+                    // persistent grid == resident CTAs (2 per SM by registers/shared memory): no partial wave
+                    const int grid = (int)std::min<long long>(total, (long long)net->n_sm * 2);
                     k_dwconv5_tma<1, DW1_TH, DW1_TW><<<grid, DwS1::THREADS, 2 * DwS1::BYTES + 128, st>>>(op.tmap_dw, a);
                 } else {
                     const long long total = (long long)batch * ((a.Hout + DW2_TH - 1) / DW2_TH) *
