@@ -118,6 +118,19 @@ def max_over_ranks(value, world, device):
     return value
 
 
+def measured_traffic(kernel, launches_per_step):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture of this same command (profiles/), or None.
+    Only accepted if the capture holds a whole number of steps of the kernel's launches."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r1_dram_traffic_bench_step.json')
+    try:
+        k = json.load(open(path))['kernels'][kernel]
+    except (OSError, KeyError, ValueError):
+        return None, 'no ncu capture committed'
+    if k['launches'] % launches_per_step != 0:
+        return None, 'capture does not cover whole steps'
+    return round(k['dram_bytes_per_launch']), 'profiles/r1_dram_traffic_bench_step.json (ncu, bs64 step)'
+
+
 # ----------------------------------------------------------------------------- this repo's arm
 def run_b200(args):
     from openpifpaf_b200 import _lib, constants, network, predictor as pred_mod, synth
@@ -181,10 +194,14 @@ def run_b200(args):
         gemm_ms = float(ms_op[sel].sum())
         achieved_gbs = float(nbytes[sel].sum()) / (gemm_ms * 1e-3) / 1e9
         achieved_tf = float(flops[sel].sum()) / (gemm_ms * 1e-3) / 1e12
+        traffic, traffic_src = measured_traffic('k_gemm_tc', int(sel.sum()))
         roofline = {
             'kernel': 'k_gemm_tc (tcgen05 1x1-conv GEMMs, %d launches/step)' % int(sel.sum()),
             'bound': 'hbm', 'achieved': round(achieved_gbs, 1), 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-            'frac': round(achieved_gbs / pk['hbm_gbs'], 4), 'traffic': None, 'peak_source': pk['source'],
+            'frac': round(achieved_gbs / pk['hbm_gbs'], 4), 'traffic': traffic, 'traffic_unit': 'bytes/launch (dram read+write)',
+            'traffic_source': traffic_src,
+            'algorithmic_bytes_per_launch': round(float(nbytes[sel].sum()) / int(sel.sum())),
+            'peak_source': pk['source'],
             'tensor_tflops': round(achieved_tf, 1), 'tensor_frac_of_measured_bf16': round(achieved_tf / pk['bf16_tflops'], 4),
             'share_of_forward': round(gemm_ms / float(ms_op.sum()), 3),
             'forward_ms': round(float(ms_op.sum()), 3),

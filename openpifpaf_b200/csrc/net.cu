@@ -679,30 +679,56 @@ __global__ void __launch_bounds__(256) k_dwconv5(DwArgs a) {
     }
 }
 
-// Depthwise 5x5 with TMA-staged input tiles.  A persistent CTA walks (channel block, image, tile) work items; one
-// elected thread streams the input window of the NEXT items ((TH-1)*S+5 x (TW-1)*S+5 pixels x 64 channels, 4-D
-// tensor map, out-of-bounds zero fill == the conv padding) into a double-buffered shared-memory ring.
-// Compute mapping (register blocking in BOTH spatial directions): one warp = one 4x4 block of output pixels,
-// one lane = one channel pair.  The lane keeps its 25x2 weights and a 4x4x2 f32 accumulator in registers and
-// reads every input pixel of the block's (3S+5)^2 window exactly once (4 bytes per lane, 128 bytes per warp
-// request: one conflict-free wavefront), i.e. 4 (S=1) / 7.6 (S=2) shared-memory reads per output instead of
-// 10 / 17.5 with row strips.
-template <int S, int TH, int TW>
+// Depthwise 5x5 with TMA-staged input tiles.  A persistent CTA walks (channel block, image, tile) work items; the
+// input window of an item ((TH-1)*S+5 x (TW-1)*S+5 pixels x 64 channels, 4-D tensor map, out-of-bounds zero fill
+// == the conv padding) is streamed by TMA into an NSTAGE-deep shared-memory ring.  There is no CTA-wide barrier in
+// the steady state: every warp counts itself out of a ring slot with one shared-memory atomic, and the warp that
+// finishes a slot LAST re-arms it with the TMA of the item NSTAGE rounds ahead, so fast warps (edge tiles with
+// out-of-range blocks) run ahead of slow ones by up to NSTAGE-1 items.
+// Compute mapping (register blocking in BOTH spatial directions): one warp = one 4 x BW block of output pixels,
+// one lane = one channel pair.  The lane keeps its 25x2 weights and a 4 x BW x 2 f32 accumulator in registers and
+// reads every input pixel of the block's window exactly once (4 bytes per lane, 128 bytes per warp request: one
+// conflict-free wavefront).
+template <int S, int TH, int TW, int BW, int NSTAGE>
 struct DwTile {
     static constexpr int IH = (TH - 1) * S + 5, IW = (TW - 1) * S + 5;
     static constexpr int BYTES = IH * IW * 64 * 2;
-    static constexpr int WARPS = (TH / 4) * (TW / 4);
+    static constexpr int WARPS = (TH / 4) * (TW / BW);
     static constexpr int THREADS = WARPS * 32;
-    static constexpr int WIN = 3 * S + 5;       // input window edge of a 4x4 output block
+    static constexpr int WIN_Y = 3 * S + 5;            // input window of a 4 x BW output block
+    static constexpr int WIN_X = (BW - 1) * S + 5;
+    static constexpr int SMEM = NSTAGE * BYTES + 128;
 };
 
-template <int S, int TH, int TW>
-__global__ void __launch_bounds__(DwTile<S, TH, TW>::THREADS, 2)
+// position of a work item and its increment per persistent-loop step, kept as mixed-radix digits
+// (channel block, image, tile row, tile column) so that the loop needs no integer division
+struct DwPos { int c, b, y, x; };
+
+__device__ __forceinline__ DwPos dw_decompose(int w, int per_c, int tiles_y, int tiles_x) {
+    DwPos p;
+    p.c = w / per_c; int r = w - p.c * per_c;
+    p.b = r / (tiles_y * tiles_x); r -= p.b * tiles_y * tiles_x;
+    p.y = r / tiles_x; p.x = r - p.y * tiles_x;
+    return p;
+}
+
+__device__ __forceinline__ void dw_advance(DwPos& p, const DwPos& d, int B, int tiles_y, int tiles_x) {
+    p.x += d.x; int carry = p.x >= tiles_x; p.x -= carry ? tiles_x : 0;
+    p.y += d.y + carry; carry = p.y >= tiles_y; p.y -= carry ? tiles_y : 0;
+    p.b += d.b + carry; carry = p.b >= B; p.b -= carry ? B : 0;
+    p.c += d.c + carry;
+}
+
+template <int S, int TH, int TW, int BW, int NSTAGE>
+__global__ void __launch_bounds__(DwTile<S, TH, TW, BW, NSTAGE>::THREADS, 2)
 k_dwconv5_tma(const __grid_constant__ CUtensorMap tmap_in, DwArgs a) {
-    using T = DwTile<S, TH, TW>;
+    using T = DwTile<S, TH, TW, BW, NSTAGE>;
     extern __shared__ __align__(128) unsigned char dsm_raw[];
-    unsigned char* dsm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dsm_raw) + 127) & ~uintptr_t(127));
-    __shared__ uint64_t full[2];
+    // align inside the shared window with pointer arithmetic on the array itself (keeps the address space known to
+    // the compiler: LDS instead of generic loads)
+    unsigned char* dsm = dsm_raw + ((128u - (smem_u32(dsm_raw) & 127u)) & 127u);
+    __shared__ uint64_t full[NSTAGE];
+    __shared__ int done[NSTAGE];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles_x = (a.Wout + TW - 1) / TW, tiles_y = (a.Hout + TH - 1) / TH;
     const int cblks = (a.C8 + 7) / 8;
@@ -710,40 +736,38 @@ k_dwconv5_tma(const __grid_constant__ CUtensorMap tmap_in, DwArgs a) {
     const int total = per_c * cblks;
     const int C = a.C8 * 8;
 
-    if (tid == 0) {
-        mbar_init(&full[0], 1); mbar_init(&full[1], 1);
-        fence_barrier_init();
-        tma_prefetch_desc(&tmap_in);
-    }
-    __syncthreads();
-
-    auto issue = [&](int w, int buf) {
-        const int cblk = w / per_c; int r = w - cblk * per_c;
-        const int b = r / (tiles_y * tiles_x); r -= b * tiles_y * tiles_x;
-        const int ty = r / tiles_x, tx = r - ty * tiles_x;
+    auto issue = [&](const DwPos& p, int buf) {
         mbar_expect_tx(&full[buf], (uint32_t)T::BYTES);
-        tma_load_4d(dsm + (size_t)buf * T::BYTES, &tmap_in, &full[buf], cblk * 64, tx * TW * S - a.pad,
-                    ty * TH * S - a.pad, b);
+        tma_load_4d(dsm + (size_t)buf * T::BYTES, &tmap_in, &full[buf], p.c * 64, p.x * TW * S - a.pad,
+                    p.y * TH * S - a.pad, p.b);
     };
 
     if (tid == 0) {
-        if ((int)blockIdx.x < total) issue(blockIdx.x, 0);
-        if ((int)(blockIdx.x + gridDim.x) < total) issue(blockIdx.x + gridDim.x, 1);
+#pragma unroll
+        for (int s = 0; s < NSTAGE; s++) { mbar_init(&full[s], 1); done[s] = 0; }
+        fence_barrier_init();
+        tma_prefetch_desc(&tmap_in);
+#pragma unroll
+        for (int s = 0; s < NSTAGE; s++) {
+            const int w0 = blockIdx.x + s * gridDim.x;
+            if (w0 < total) issue(dw_decompose(w0, per_c, tiles_y, tiles_x), s);
+        }
     }
-    const int by = warp / (TW / 4), bx = warp % (TW / 4);       // 4x4 output block of this warp inside the tile
-    uint32_t phase0 = 0, phase1 = 0;
-    int it = 0;
+    __syncthreads();
+
+    const int by = warp / (TW / BW), bx = warp % (TW / BW);     // 4 x BW output block of this warp inside the tile
+    const DwPos step = dw_decompose(gridDim.x, per_c, tiles_y, tiles_x);
+    const DwPos step_ring = dw_decompose(NSTAGE * gridDim.x, per_c, tiles_y, tiles_x);
+    DwPos pos = dw_decompose(blockIdx.x, per_c, tiles_y, tiles_x);
+    const size_t out_row = (size_t)a.Wout * a.ld_out;           // elements per output image row
+    int buf = 0; uint32_t phase = 0;
     int w_cblk = -1;
     float wgt[25][2];
     float bias0 = 0.f, bias1 = 0.f;
-    for (int w = blockIdx.x; w < total; w += gridDim.x, it++) {
-        const int buf = it & 1;
-        const int cblk = w / per_c; int r = w - cblk * per_c;
-        const int b = r / (tiles_y * tiles_x); r -= b * tiles_y * tiles_x;
-        const int ty = r / tiles_x, tx = r - ty * tiles_x;
-        const int c0 = cblk * 64 + lane * 2;
-        if (cblk != w_cblk) {                       // (re)load this lane's weights: rarely, the block index is slowest
-            w_cblk = cblk;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int c0 = pos.c * 64 + lane * 2;
+        if (pos.c != w_cblk) {                      // (re)load this lane's weights: rarely, the block index is slowest
+            w_cblk = pos.c;
             const bool cok = c0 < C;
 #pragma unroll
             for (int tp = 0; tp < 25; tp++) {
@@ -754,23 +778,24 @@ k_dwconv5_tma(const __grid_constant__ CUtensorMap tmap_in, DwArgs a) {
             const float2 bv = cok ? __ldg(reinterpret_cast<const float2*>(a.bias + c0)) : make_float2(0.f, 0.f);
             bias0 = bv.x; bias1 = bv.y;
         }
-        if (buf == 0) { mbar_wait(&full[0], phase0); phase0 ^= 1; }
-        else { mbar_wait(&full[1], phase1); phase1 ^= 1; }
-        const int oy0 = ty * TH + by * 4, ox0 = tx * TW + bx * 4;
-        if (c0 < C && oy0 < a.Hout && ox0 < a.Wout) {
-            const unsigned char* tile = dsm + (size_t)buf * T::BYTES + lane * 4;
-            float acc[4][4][2];
+        const int oy0 = pos.y * TH + by * 4, ox0 = pos.x * TW + bx * BW;
+        // every warp waits (also those whose block lies past the image edge): passing this wait proves that all
+        // warps counted out of the slot's previous item, so the per-slot count never mixes two items
+        mbar_wait(&full[buf], phase);
+        if (oy0 < a.Hout && ox0 < a.Wout && c0 < C) {
+            const unsigned char* tile = dsm + (size_t)buf * T::BYTES + lane * 4 +
+                                        ((by * 4 * S) * T::IW + bx * BW * S) * 128;
+            float acc[4][BW][2];
 #pragma unroll
             for (int i = 0; i < 4; i++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) { acc[i][j][0] = bias0; acc[i][j][1] = bias1; }
+                for (int j = 0; j < BW; j++) { acc[i][j][0] = bias0; acc[i][j][1] = bias1; }
 #pragma unroll
-            for (int ry = 0; ry < T::WIN; ry++) {
-                float f[T::WIN][2];
-                const unsigned char* rowp = tile + ((size_t)(by * 4 * S + ry) * T::IW + bx * 4 * S) * 128;
+            for (int ry = 0; ry < T::WIN_Y; ry++) {
+                float f[T::WIN_X][2];
 #pragma unroll
-                for (int cx = 0; cx < T::WIN; cx++) {
-                    const uint32_t v = *reinterpret_cast<const uint32_t*>(rowp + (size_t)cx * 128);
+                for (int cx = 0; cx < T::WIN_X; cx++) {
+                    const uint32_t v = *reinterpret_cast<const uint32_t*>(tile + (ry * T::IW + cx) * 128);
                     f[cx][0] = __uint_as_float(v << 16);
                     f[cx][1] = __uint_as_float(v & 0xffff0000u);
                 }
@@ -779,42 +804,69 @@ k_dwconv5_tma(const __grid_constant__ CUtensorMap tmap_in, DwArgs a) {
                     const int ky = ry - i * S;                    // compile-time after unrolling
                     if (ky < 0 || ky >= 5) continue;
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
+                    for (int kx = 0; kx < 5; kx++) {
 #pragma unroll
-                        for (int kx = 0; kx < 5; kx++) {
+                        for (int j = 0; j < BW; j++) {
                             acc[i][j][0] = fmaf(f[j * S + kx][0], wgt[ky * 5 + kx][0], acc[i][j][0]);
                             acc[i][j][1] = fmaf(f[j * S + kx][1], wgt[ky * 5 + kx][1], acc[i][j][1]);
                         }
                     }
                 }
             }
+            if (a.relu) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int oy = oy0 + i;
-                if (oy >= a.Hout) continue;
+                for (int i = 0; i < 4; i++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int ox = ox0 + j;
-                    if (ox >= a.Wout) continue;
-                    float v0 = acc[i][j][0], v1 = acc[i][j][1];
-                    if (a.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-                    *reinterpret_cast<uint32_t*>(a.out + ((size_t)(b * a.Hout + oy) * a.Wout + ox) * a.ld_out +
-                                                 a.out_col_off + c0) = pack_bf16(v0, v1);
+                    for (int j = 0; j < BW; j++) {
+                        acc[i][j][0] = fmaxf(acc[i][j][0], 0.f); acc[i][j][1] = fmaxf(acc[i][j][1], 0.f);
+                    }
+            }
+            __nv_bfloat16* orow = a.out + ((size_t)(pos.b * a.Hout + oy0) * a.Wout + ox0) * a.ld_out + a.out_col_off + c0;
+            if (oy0 + 4 <= a.Hout && ox0 + BW <= a.Wout) {          // interior block: no per-pixel predicates
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    __nv_bfloat16* op = orow + i * out_row;
+#pragma unroll
+                    for (int j = 0; j < BW; j++)
+                        *reinterpret_cast<uint32_t*>(op + (size_t)j * a.ld_out) = pack_bf16(acc[i][j][0], acc[i][j][1]);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (oy0 + i >= a.Hout) continue;
+                    __nv_bfloat16* op = orow + i * out_row;
+#pragma unroll
+                    for (int j = 0; j < BW; j++) {
+                        if (ox0 + j >= a.Wout) continue;
+                        *reinterpret_cast<uint32_t*>(op + (size_t)j * a.ld_out) = pack_bf16(acc[i][j][0], acc[i][j][1]);
+                    }
                 }
             }
         }
-        __syncthreads();                                // everyone is done with this buffer
-        if (tid == 0) {
-            const int wn = w + 2 * gridDim.x;
-            if (wn < total) issue(wn, buf);
+        // count this warp out of the slot; the last one out re-arms it.  Every shared-memory read of the slot has
+        // been consumed by an fma above (results are in registers), the fence orders them before the count.
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            if (atomicAdd(&done[buf], 1) == T::WARPS - 1) {
+                done[buf] = 0;
+                if (w + NSTAGE * (int)gridDim.x < total) {
+                    DwPos pn = pos;
+                    dw_advance(pn, step_ring, a.B, tiles_y, tiles_x);
+                    issue(pn, buf);
+                }
+            }
         }
+        dw_advance(pos, step, a.B, tiles_y, tiles_x);
+        if (++buf == NSTAGE) { buf = 0; phase ^= 1; }
     }
 }
 
-// tile shapes: stride 1 -> 8x16 outputs (8 warps, 30 KB window); stride 2 -> 8x8 outputs (4 warps, 46 KB window)
+// tile shapes: stride 1 -> 8x16 outputs, 4x4 blocks (8 warps, 30 KB window, 3-deep ring);
+//              stride 2 -> 8x8 outputs, 4x4 blocks (4 warps, 46 KB window, 2-deep ring)
 constexpr int DW1_TH = 8, DW1_TW = 16, DW2_TH = 8, DW2_TW = 8;
-using DwS1 = DwTile<1, DW1_TH, DW1_TW>;
-using DwS2 = DwTile<2, DW2_TH, DW2_TW>;
+using DwS1 = DwTile<1, DW1_TH, DW1_TW, 4, 3>;
+using DwS2 = DwTile<2, DW2_TH, DW2_TW, 4, 2>;
 
 // generic depthwise kxk (any kernel/stride): one output pixel x 8 channels per thread
 __global__ void __launch_bounds__(256) k_dwconv(DwArgs a) {
@@ -1033,7 +1085,7 @@ int make_tmap_dw(CUtensorMap* map, const void* base, uint64_t c, uint64_t w, uin
     const cuuint32_t box[4] = {64, box_w, box_h, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         pifpaf::set_error("cuTensorMapEncodeTiled (dw) failed (%d): c=%llu w=%llu h=%llu b=%llu ld=%llu box=%ux%u", (int)r,
@@ -1221,10 +1273,10 @@ int pifpaf_net_create(pifpaf_net_t** out, int32_t device, int32_t max_batch) {
     pifpaf_net* net = new pifpaf_net();
     net->device = device; net->max_batch = max_batch; net->n_sm = prop.multiProcessorCount;
     PIFPAF_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    PIFPAF_CUDA_TRY(cudaFuncSetAttribute(k_dwconv5_tma<1, DW1_TH, DW1_TW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         2 * DwS1::BYTES + 128));
-    PIFPAF_CUDA_TRY(cudaFuncSetAttribute(k_dwconv5_tma<2, DW2_TH, DW2_TW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         2 * DwS2::BYTES + 128));
+    PIFPAF_CUDA_TRY(cudaFuncSetAttribute(k_dwconv5_tma<1, DW1_TH, DW1_TW, 4, 3>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, DwS1::SMEM));
+    PIFPAF_CUDA_TRY(cudaFuncSetAttribute(k_dwconv5_tma<2, DW2_TH, DW2_TW, 4, 2>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, DwS2::SMEM));
     *out = net;
     return PIFPAF_OK;
 }
@@ -1531,17 +1583,17 @@ static int net_forward_impl(pifpaf_net_t* net, const float* images_dev, int32_t 
             a.B = batch;
             if (op.dw_tma && gemm_impl == 0) {
                 const int cblks = (a.C8 + 7) / 8;
+                // persistent grid == resident CTAs (2 per SM by registers/shared memory): no partial wave
                 if (a.stride == 1) {
                     const long long total = (long long)batch * ((a.Hout + DW1_TH - 1) / DW1_TH) *
                                             ((a.Wout + DW1_TW - 1) / DW1_TW) * cblks;
-                    // persistent grid == resident CTAs (2 per SM by registers/shared memory): no partial wave
                     const int grid = (int)std::min<long long>(total, (long long)net->n_sm * 2);
-                    k_dwconv5_tma<1, DW1_TH, DW1_TW><<<grid, DwS1::THREADS, 2 * DwS1::BYTES + 128, st>>>(op.tmap_dw, a);
+                    k_dwconv5_tma<1, DW1_TH, DW1_TW, 4, 3><<<grid, DwS1::THREADS, DwS1::SMEM, st>>>(op.tmap_dw, a);
                 } else {
                     const long long total = (long long)batch * ((a.Hout + DW2_TH - 1) / DW2_TH) *
                                             ((a.Wout + DW2_TW - 1) / DW2_TW) * cblks;
                     const int grid = (int)std::min<long long>(total, (long long)net->n_sm * 2);
-                    k_dwconv5_tma<2, DW2_TH, DW2_TW><<<grid, DwS2::THREADS, 2 * DwS2::BYTES + 128, st>>>(op.tmap_dw, a);
+                    k_dwconv5_tma<2, DW2_TH, DW2_TW, 4, 2><<<grid, DwS2::THREADS, DwS2::SMEM, st>>>(op.tmap_dw, a);
                 }
             } else if (a.kernel == 5 && (a.stride == 1 || a.stride == 2)) {
                 const long long total = (long long)batch * ((a.Hout + DW_OY - 1) / DW_OY) * DW_OY *

@@ -29,6 +29,11 @@ timeout -k 5 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 50
    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1; echo "rc=$?"
 timeout -k 5 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_decoder.csv \
    python tools/diag_decoder_perf.py 2 > gpurun_out/decoder_under_ncu.log 2>&1; echo "rc=$?"
+echo "== ncu dram traffic of one bench step (57 network launches after 3 warm-up steps)"
+timeout -k 5 300 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
+   -k regex:'k_gemm_tc|k_dwconv5|k_input_conv' -s 171 -c 57 --csv --log-file gpurun_out/dram_traffic_step.csv \
+   python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu_traffic.log 2>&1; echo "rc=$?"
+python tools/summarize_traffic.py gpurun_out/dram_traffic_step.csv gpurun_out/dram_traffic_step.json
 echo "== ncu full"
 timeout -k 5 500 ncu --set full --clock-control none --import-source on -k regex:'k_gemm_tc|k_dwconv5' -s 70 -c 12 \
    -o gpurun_out/prof_net -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_net.log 2>&1; echo "rc=$?"
