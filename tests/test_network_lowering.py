@@ -86,7 +86,12 @@ def test_lowering_reproduces_oracle_net(shape):
         if o['kind'] in ('conv1x1', 'dwconv'):
             assert o['out_off'] % 16 == 0 and o['in_off'] % 8 == 0
     assert all(c % 16 == 0 for (_, _, c) in tensors)
-    assert any(o['kind'] == 'conv1x1' and o['in_off'] == 168 for o in ops)       # x.chunk(2) of 348 channels
+    # x.chunk(2) of 348 channels: the view starts at or below column 174 on a multiple of 8, the leading columns
+    # carry zero weights
+    a0 = network._view_start(174)
+    assert a0 % 8 == 0 and 174 - 64 < a0 <= 174
+    views = [o for o in ops if o['kind'] == 'conv1x1' and o['in_off'] == a0]
+    assert views and all(not o['w'][:, :174 - a0].any() for o in views)
 
 
 def test_random_plan_has_reference_architecture():

@@ -98,6 +98,17 @@ def full_size(base='shufflenetv2k16', size=641, B=8):
                 sel = kind == k
                 print(f'   {kn}: {sel.sum()} ops {ms_op[sel].sum():.2f} ms, {flops[sel].sum() / ms_op[sel].sum() / 1e9:.1f} TFLOP/s, '
                       f'{nbytes[sel].sum() / ms_op[sel].sum() / 1e6:.0f} GB/s', flush=True)
+            views = {}
+            for i, o in enumerate(net.op_desc):
+                if o['kind'] == 'conv1x1' and o.get('in_off', 0) > 0:
+                    hh = net.tensor_shapes[o['out']][0]
+                    v = views.setdefault(hh, [o['in_off'], o['k_cols'], 0, 0.0])
+                    v[2] += 1; v[3] += float(ms_op[i])
+            for hh, (off, kc, cnt, tot) in sorted(views.items(), reverse=True):
+                print(f'   chunk-view GEMMs at {hh}x{hh}: start column {off}, k_cols {kc}: {cnt} ops {tot:.3f} ms '
+                      f'({tot / cnt * 1e3:.1f} us each)', flush=True)
+            if os.environ.get('DIAG_NET_FAST'):
+                return
             order = np.argsort(-ms_op)[:8]
             for i in order:
                 print(f'      op {i} kind {kind[i]} {ms_op[i]:.3f} ms {flops[i] / ms_op[i] / 1e9:.1f} TFLOP/s '
