@@ -1075,7 +1075,11 @@ int make_tmap_conv(CUtensorMap* map, const void* base, uint64_t c, uint64_t w, u
     return PIFPAF_OK;
 }
 
-// 4-D bf16 NHWC view {C, W, H, B}, dense (un-swizzled) box of 64 channels x box_w x box_h pixels
+// 4-D bf16 NHWC view {C, W, H, B}, dense (un-swizzled) box of 64 channels x box_w x box_h pixels.
+// No L2 promotion: the 128-byte channel block of a pixel is all the kernel wants from that pixel for a long time
+// (the channel block is the slowest work index) and pixel strides of 352 / 704 bytes leave most blocks straddling
+// 128-byte lines.  ncu (round 1): 256-byte promotion read 2x the algorithmic bytes from DRAM; 128-byte promotion
+// requested 1.5x the sectors of no promotion for the same DRAM bytes.
 int make_tmap_dw(CUtensorMap* map, const void* base, uint64_t c, uint64_t w, uint64_t h, uint64_t b, uint64_t ld,
                  uint32_t box_w, uint32_t box_h) {
     PFN_encodeTiled fn = get_encode_fn();
@@ -1085,7 +1089,7 @@ int make_tmap_dw(CUtensorMap* map, const void* base, uint64_t c, uint64_t w, uin
     const cuuint32_t box[4] = {64, box_w, box_h, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         pifpaf::set_error("cuTensorMapEncodeTiled (dw) failed (%d): c=%llu w=%llu h=%llu b=%llu ld=%llu box=%ux%u", (int)r,

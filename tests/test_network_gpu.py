@@ -139,3 +139,41 @@ def test_resnet_implicit_gemm_matches_emulation_and_fp32(name, size, batch):
         err = (hg.cpu() - hw_).abs()
         assert float(err.max()) < tol * float(hw_.std()) + 1e-3
         assert float(err.mean()) < 1e-2 * float(hw_.std())
+
+
+def test_k30_wholebody_network_and_decode():
+    """BASELINE configs[3]: shufflenetv2k30 + wholebody heads (F=133, C=160; 1945 head channels in one GEMM,
+    2048-wide stage-4 GEMMs) per op vs the bf16 emulation, fields vs fp32 PyTorch, then the Predictor end to end
+    (the decoder handle sized for 133 keypoints / 160 connections) against the oracle decoder on the same fields."""
+    shell = net_oracle.make_shell('shufflenetv2k30', n_keypoints=133, n_connections=160, seed=3)
+    plan = network.plan_from_shell(shell)
+    h, w, B = 129, 161, 2
+    x = torch.randn(B, 3, h, w, generator=torch.Generator().manual_seed(8))
+    tensors, ops, _ = network.build_ops(plan, h, w)
+    emu_heads, emu_acts = ops_emulator.run_ops(tensors, ops, x, bf16=True)
+    net = network.CompiledNet(plan, h, w, B)
+    heads = net.forward(x.cuda())
+    torch.cuda.synchronize()
+    for o in ops:
+        if o['kind'] == 'heads':
+            continue
+        got = net.tap(o['out'], B)
+        ref = emu_acts[o['out']].numpy()
+        scale = max(float(np.abs(ref).max()), 1e-6)
+        assert float(np.abs(got - ref).max()) / scale < 3e-2, (o['kind'], o['out'])
+    with torch.no_grad():
+        want = shell(x)
+    for hg, hw_ in zip(heads, want):
+        assert hg.shape == hw_.shape
+        err = (hg.cpu() - hw_).abs()
+        assert float(err.max()) < 8e-2 * float(hw_.std()) + 1e-3      # 100 bf16 layers
+        assert float(err.mean()) < 1e-2 * float(hw_.std())
+    skeleton = constants.wholebody_skeleton()
+    pred = predictor.Predictor(net, constants.WHOLEBODY_N_KEYPOINTS, skeleton)
+    res = pred.batch(x.pin_memory())
+    cif, caf = [t.cpu().numpy() for t in net.forward(x.cuda())]
+    sk = np.asarray(skeleton, dtype=np.int64) - 1
+    p = oc.default_params(seed_sort_stable=1)
+    for b in range(B):
+        oa, _ = oc.decode(cif[b], 16, caf[b], 16, sk, constants.WHOLEBODY_N_KEYPOINTS, params=p)
+        helpers.assert_annotations_close(res[b][0].numpy(), oa, f'k30 wholebody image {b}')

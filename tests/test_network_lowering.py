@@ -94,6 +94,23 @@ def test_lowering_reproduces_oracle_net(shape):
     assert views and all(not o['w'][:, :174 - a0].any() for o in views)
 
 
+def test_k30_wholebody_lowering_reproduces_oracle_net():
+    """BASELINE configs[3]: shufflenetv2k30 with the wholebody heads (133 keypoints, 160 connections)."""
+    shell = net_oracle.make_shell('shufflenetv2k30', n_keypoints=133, n_connections=160, seed=3)
+    x = torch.randn(1, 3, 65, 81)
+    with torch.no_grad():
+        want = shell(x)
+    plan = network.plan_from_shell(shell)
+    assert [len(st) for st in plan['stages']] == [8, 16, 6]
+    tensors, ops, _ = network.build_ops(plan, 65, 81)
+    got, _ = ops_emulator.run_ops(tensors, ops, x)
+    assert [tuple(g.shape) for g in got] == [(1, 133, 5, 5, 6), (1, 160, 8, 5, 6)]
+    for g, wnt in zip(got, want):
+        assert float((g - wnt).abs().max()) < 2e-5
+    head = ops[-1]
+    assert head['kind'] == 'heads' and head['w'].shape == (133 * 5 + 160 * 8, 2048)
+
+
 def test_random_plan_has_reference_architecture():
     plan = network.random_plan('shufflenetv2k16')
     assert [len(s) for s in plan['stages']] == [4, 8, 4]
