@@ -17,8 +17,9 @@ folded into the physical channel placement computed here:
   the last GEMM of a block writes logical channel 2n <- pass-through[n],
   2n+1 <- conv[n] (== cat + channel_shuffle(groups=2), basenetworks.py:233-242)
   with aligned 256-bit stores, and the next block's x.chunk(2) is the TMA start
-  coordinate floor8(half) of its A operand (TMA coordinates must be 16-byte
-  aligned; the <= 7 leading pass-through columns meet zero weight columns).
+  coordinate _view_start(half) of its A operand (16-byte aligned at least, 32-byte
+  or more where the K-block count allows; the leading pass-through columns meet
+  zero weight columns).
 """
 import ctypes
 import os
@@ -195,21 +196,27 @@ def random_plan(base_name='shufflenetv2k16', heads=((17, 1, 1, 1), (19, 1, 2, 2)
     return plan
 
 
-def calibrate_random_heads(plan, device=0, seed=0):
-    """Give a random-init plan trained-network-like head statistics: measure the RMS of the backbone features
-    on a small random batch (on the GPU, through the product kernels) and rescale the head weights so that the
-    head pre-activations have unit scale.  Together with random_plan's confidence bias this yields sparse
-    confidence maps (a few cells per image above the decoder thresholds) instead of saturated noise."""
-    net = CompiledNet(plan, 161, 161, 2, device=device)
-    x = torch.randn((2, 3, 161, 161), generator=torch.Generator().manual_seed(seed)).to(f'cuda:{device}')
+def calibrate_random_heads(plan, device=0, seed=0, size=161, batch=2):
+    """Give a random-init plan trained-network-like head statistics: measure mean and spread of the backbone
+    features on a small random batch (on the GPU, through the product kernels), then centre and rescale the head
+    so that every head channel's pre-activation is ~N(0, 1) over positions: w' = w / std, b' = b - w' . mean.
+    (Post-ReLU features have a large common mean; without centring every head channel gets its own random DC
+    offset and whole confidence maps saturate.)  Together with random_plan's confidence bias this yields
+    confidence maps with isolated cells above the decoder thresholds instead of saturated noise.
+    Returns (feature std, feature mean norm)."""
+    net = CompiledNet(plan, size, size, batch, device=device)
+    x = torch.randn((batch, 3, size, size), generator=torch.Generator().manual_seed(seed)).to(f'cuda:{device}')
     net.forward(x)
     torch.cuda.synchronize()
     t, lay = net.info['feature']
-    feat = net.tap(t, 2)[..., lay.cols()]
-    rms = float(np.sqrt(np.mean(np.square(feat, dtype=np.float64))))
+    feat = net.tap(t, batch)[..., lay.cols()].astype(np.float64)
+    mu = feat.reshape(-1, feat.shape[-1]).mean(axis=0)
+    std = float(np.sqrt(np.mean(np.square(feat - mu))))
     for hd in plan['heads']:
-        hd['w'] = (hd['w'] / np.float32(max(rms, 1e-6))).astype(np.float32)
-    return rms
+        w = hd['w'].astype(np.float64) / max(std, 1e-6)
+        hd['b'] = (hd['b'].astype(np.float64) - w @ mu).astype(np.float32)
+        hd['w'] = w.astype(np.float32)
+    return std, float(np.linalg.norm(mu))
 
 
 # ----------------------------------------------------------------------------- compiled net
@@ -226,7 +233,7 @@ class _Layout:
     """Physical column placement of a logical channel vector: physical == logical order, rows padded to a
     multiple of 16 channels (32-byte aligned rows for 256-bit stores).  `split` marks tensors whose two
     logical halves are consumed separately (x.chunk(2)): the second half starts at column `half`; its TMA
-    view starts at floor8(half) with zero weights on the leading columns."""
+    view starts at _view_start(half) with zero weights on the leading columns."""
 
     def __init__(self, channels, split):
         self.channels = channels
@@ -332,8 +339,8 @@ def build_ops(plan, in_h, in_w):
             else:
                 assert lay.split and lay.half == bf
                 # x1, x2 = x.chunk(2): x2 is the column window [bf, 2*bf) (basenetworks.py:234-236).  TMA needs a
-                # 16-byte aligned start, so the view begins at floor8(bf); the up to 7 leading columns are
-                # pass-through channels and get zero weights.
+                # 16-byte aligned start (32 bytes or more is faster), so the view begins at _view_start(bf) <= bf;
+                # the leading columns are pass-through channels and get zero weights.
                 a0 = _view_start(bf)
                 lead = bf - a0
                 t_c = tensor(h, w, hp)
