@@ -182,12 +182,26 @@ int pifpaf_net_input_conv(pifpaf_net_t* net, int32_t in_h, int32_t in_w, int32_t
  * shuffle_src_tensor < 0: plain output at columns [out_col_off, out_col_off+n_out) of out_tensor.
  * shuffle_src_tensor >= 0: fused cat + channel_shuffle(2) (basenetworks.py:233-242): output logical
  *   channel 2n <- shuffle_src[n], 2n+1 <- this conv[n], written contiguously (physical == logical order);
- *   in_col_off must be a multiple of 8 (TMA coordinates must be 16-byte aligned): the next block's x.chunk(2)
- *   starts its view at floor8(n_out) and zeroes the weight columns of the leading pass-through channels. */
+ *   in_col_off must be a multiple of 8 (TMA coordinates must be 16-byte aligned): in the 'shuffle' layout the next
+ *   block's x.chunk(2) starts its view at or below n_out on such a column and zeroes the weight columns of the
+ *   leading pass-through channels. */
 int pifpaf_net_conv1x1(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off, int32_t k_cols,
                        int32_t n_out, const float* weight, const float* bias, int32_t relu,
                        int32_t out_tensor, int32_t out_col_off,
                        int32_t shuffle_src_tensor, int32_t shuffle_src_col_off);
+
+/* 1x1 conv whose output columns go to SEVERAL tensors (the 'bins' activation layout of the ShuffleNetV2K stages):
+ * torch.cat + channel_shuffle + the next block's x.chunk(2) (basenetworks.py:233-242) only ever move channels, so
+ * the host routes every channel, at production time, into the buffer of the block that will consume it
+ * (openpifpaf_b200/network.py::_plan_stage_bins) and no pass-through channel is copied.
+ * weight [n_out][k_cols] / bias [n_out] are already in GEMM column order (padding columns: zero weight and bias);
+ * piece i = GEMM columns [piece_col0[i], +piece_count[i]) -> columns [piece_tensor_col[i], +piece_count[i]) of
+ * tensor piece_tensor[i]; pieces tile [0, n_out) in order; counts and tensor columns are multiples of 16
+ * (32 bytes: every lane writes whole sectors with 256-bit stores). */
+int pifpaf_net_conv1x1_scatter(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off, int32_t k_cols,
+                               int32_t n_out, const float* weight, const float* bias, int32_t relu,
+                               int32_t n_pieces, const int32_t* piece_col0, const int32_t* piece_count,
+                               const int32_t* piece_tensor, const int32_t* piece_tensor_col);
 
 /* Dense kxk conv (k <= 7, stride 1 or 2) as an implicit GEMM on tensor cores (torchvision ResNet blocks behind
  * basenetworks.py:71-150): reads channels [in_col_off, in_col_off+c_in) of in_tensor through a 4-D TMA map

@@ -57,6 +57,7 @@ SYMBOLS = {
     'pifpaf_net_tensor': (ctypes.c_int, [VP, c_i32, c_i32, c_i32, P(c_i32)]),
     'pifpaf_net_input_conv': (ctypes.c_int, [VP, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, VP, VP, c_i32, c_i32]),
     'pifpaf_net_conv1x1': (ctypes.c_int, [VP, c_i32, c_i32, c_i32, c_i32, VP, VP, c_i32, c_i32, c_i32, c_i32, c_i32]),
+    'pifpaf_net_conv1x1_scatter': (ctypes.c_int, [VP, c_i32, c_i32, c_i32, c_i32, VP, VP, c_i32, c_i32, VP, VP, VP, VP]),
     'pifpaf_net_conv': (ctypes.c_int, [VP, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, VP, VP, c_i32, c_i32, c_i32,
                                        c_i32, c_i32]),
     'pifpaf_net_dwconv': (ctypes.c_int, [VP, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, VP, VP, c_i32, c_i32, c_i32]),

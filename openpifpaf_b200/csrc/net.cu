@@ -161,7 +161,11 @@ __host__ __device__ inline uint32_t make_instr_desc(int m, int n) {
 }
 
 // ------------------------------------------------------------------ GEMM arguments
-enum { MODE_PLAIN = 0, MODE_SHUFFLE = 1, MODE_HEADS = 2 };
+enum { MODE_PLAIN = 0, MODE_SHUFFLE = 1, MODE_HEADS = 2, MODE_SCATTER = 3 };
+
+// MODE_SCATTER: destination of one chunk of 16 GEMM columns (32 bytes per row, one 256-bit store per lane): base
+// already points at the chunk's first column inside its tensor (a multiple of 16 channels)
+struct DestGroup { __nv_bfloat16* base; int ld; int pad; };
 
 struct HeadCol { int head; int plane; int op; int pad; };   // per GEMM output column (heads mode)
 
@@ -176,6 +180,9 @@ struct GemmArgs {
     const __nv_bfloat16* src0; int ld0; int src0_col_off; int half; int gap;
     int src_tma;                 // pass-through tile arrives by TMA in shared memory (else read from global)
     int b_resident;              // all K blocks of this CTA's weight tile stay in shared memory (loaded once)
+    // scatter: chunks of 16 columns go to different tensors (the 'bins' layout: every channel is written once,
+    // into the buffer of the block that consumes it)
+    const DestGroup* dest;       // [n_blocks * block_n / 16]
     // heads
     const HeadCol* head_cols;    // [n_blocks * block_n]
     float* head_base[4]; int head_planes[4];
@@ -275,6 +282,20 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, int m, int n0,
             else if (hc.op == 3) v += (float)y;
             else if (hc.op == 4) v = softplus_f(v);
             g.head_base[hc.head][((size_t)b * g.head_planes[hc.head] + hc.plane) * g.hw + pix] = v;
+        }
+        return;
+    }
+    if (g.mode == MODE_SCATTER) {
+        uint32_t w[CHUNK / 2];
+#pragma unroll
+        for (int j = 0; j < CHUNK; j += 2) {
+            float a0 = acc[j] + bv[j], a1 = acc[j + 1] + bv[j + 1];
+            if (g.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+            w[j >> 1] = pack_bf16(a0, a1);
+        }
+        if (n0 < g.N) {
+            const DestGroup d = g.dest[n0 >> 4];
+            st_global_256(d.base + (size_t)m * d.ld, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
         }
         return;
     }
@@ -1168,7 +1189,8 @@ inline int pad8(int v) { return (v + 7) & ~7; }
 inline int pad16(int v) { return (v + 15) & ~15; }
 
 // choose the UMMA N tile (<= 256, multiple of 16): the LARGEST tile whose padded work is within
-// 4 % of the minimum over all tilings
+// 10 % of the minimum over all tilings (tiny tiles waste the epilogue and the weight-resident mode; N = 368 must
+// become 2 x 192, not 23 x 16)
 void choose_block_n(int n_out, int* block_n, int* n_blocks) {
     const int np = pad16(n_out);
     long min_cost = -1;
@@ -1181,7 +1203,7 @@ void choose_block_n(int n_out, int* block_n, int* n_blocks) {
     for (int nb = 1; nb <= np / 16; nb++) {
         const int bn = pad16((np + nb - 1) / nb);
         if (bn > 256) continue;
-        if ((long)bn * nb * 100 <= min_cost * 104) { *block_n = bn; *n_blocks = nb; return; }
+        if ((long)bn * nb * 100 <= min_cost * 110) { *block_n = bn; *n_blocks = nb; return; }
     }
     *block_n = 16; *n_blocks = np / 16;
 }
@@ -1384,6 +1406,47 @@ int pifpaf_net_conv1x1(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off,
         if (rc != PIFPAF_OK) return rc;
     }
     plan_gemm_smem(g, &op.smem, g.src_tma != 0);
+    net->ops.push_back(op);
+    return PIFPAF_OK;
+}
+
+int pifpaf_net_conv1x1_scatter(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off, int32_t k_cols,
+                               int32_t n_out, const float* weight, const float* bias, int32_t relu,
+                               int32_t n_pieces, const int32_t* piece_col0, const int32_t* piece_count,
+                               const int32_t* piece_tensor, const int32_t* piece_tensor_col) {
+    PIFPAF_CHECK_ARG(net != nullptr && weight != nullptr && piece_col0 && piece_count && piece_tensor && piece_tensor_col,
+                     "null argument");
+    const int nt = (int)net->tensors.size();
+    PIFPAF_CHECK_ARG(in_tensor >= 0 && in_tensor < nt, "bad tensor id");
+    PIFPAF_CHECK_ARG(k_cols >= 1 && n_out >= 16 && n_out % 16 == 0 && n_pieces >= 1, "bad conv size");
+    PIFPAF_CUDA_TRY(cudaSetDevice(net->device));
+    const Tensor& tin = net->tensors[in_tensor];
+    Op op; op.kind = OP_GEMM;
+    int rc = emit_gemm(net, op, in_tensor, in_col_off, k_cols, n_out, weight, bias);
+    if (rc != PIFPAF_OK) return rc;
+    GemmArgs& g = op.g;
+    g.mode = MODE_SCATTER; g.relu = relu;
+    std::vector<DestGroup> groups((size_t)g.n_blocks * g.block_n / 16, DestGroup{nullptr, 0, 0});
+    int expect = 0;
+    for (int i = 0; i < n_pieces; i++) {
+        PIFPAF_CHECK_ARG(piece_col0[i] == expect && piece_count[i] >= 16 && piece_count[i] % 16 == 0,
+                         "pieces must tile [0, n_out) in order, in multiples of 16 columns");
+        PIFPAF_CHECK_ARG(piece_tensor[i] >= 0 && piece_tensor[i] < nt, "bad piece tensor id");
+        const Tensor& to = net->tensors[piece_tensor[i]];
+        PIFPAF_CHECK_ARG(to.h == tin.h && to.w == tin.w, "conv1x1 keeps the spatial shape");
+        PIFPAF_CHECK_ARG(piece_tensor_col[i] >= 0 && piece_tensor_col[i] % 16 == 0 &&
+                         piece_tensor_col[i] + piece_count[i] <= to.c, "piece window outside its tensor");
+        for (int c = 0; c < piece_count[i]; c += 16)
+            groups[(size_t)(expect + c) / 16] = DestGroup{to.data + piece_tensor_col[i] + c, to.c, 0};
+        expect += piece_count[i];
+    }
+    PIFPAF_CHECK_ARG(expect == n_out, "pieces must cover all n_out columns");
+    DestGroup* d_groups = nullptr;
+    rc = net_upload(net, &d_groups, groups);
+    if (rc != PIFPAF_OK) return rc;
+    g.dest = d_groups;
+    op.bytes_per_image += (double)op.rows_per_image * n_out * 2.0;
+    plan_gemm_smem(g, &op.smem, false);
     net->ops.push_back(op);
     return PIFPAF_OK;
 }

@@ -230,19 +230,22 @@ class _DevArray:
 
 
 class _Layout:
-    """Physical column placement of a logical channel vector: physical == logical order, rows padded to a
-    multiple of 16 channels (32-byte aligned rows for 256-bit stores).  `split` marks tensors whose two
-    logical halves are consumed separately (x.chunk(2)): the second half starts at column `half`; its TMA
-    view starts at _view_start(half) with zero weights on the leading columns."""
+    """Physical column placement of a logical channel vector; rows padded to a multiple of 16 channels (32-byte
+    aligned rows for 256-bit stores).  Default: physical == logical order.  `split` marks tensors of the
+    'shuffle' layout whose two logical halves are consumed separately (x.chunk(2)): the second half starts at
+    column `half`; its TMA view starts at _view_start(half) with zero weights on the leading columns.
+    `phys` (int array [channels]) places logical channel c at physical column phys[c] of a `width`-wide row (the
+    'bins' layout's stage outputs, whose rows hold the channels in order of production)."""
 
-    def __init__(self, channels, split):
+    def __init__(self, channels, split, phys=None, width=None):
         self.channels = channels
         self.split = split
         self.half = channels // 2 if split else None
-        self.width = pad16(channels)
+        self.width = pad16(channels) if width is None else width
+        self.phys = None if phys is None else np.asarray(phys, dtype=np.int64)
 
     def cols(self):
-        return np.arange(self.channels)
+        return np.arange(self.channels) if self.phys is None else self.phys
 
 
 def _view_start(half):
@@ -268,7 +271,74 @@ def _ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def build_ops(plan, in_h, in_w):
+def _plan_stage_bins(bf, n_blocks):
+    """Channel routing of one ShuffleNetV2K stage for the 'bins' layout, in which no pass-through channel is ever
+    copied.  The reference (basenetworks.py:233-242) computes, for block t >= 1 with input vector L_t (2*bf
+    channels), L_{t+1}[2n] = L_t[n] (pass-through) and L_{t+1}[2n+1] = branch2(L_t[bf:])[n]; block 0 gives
+    L_1[2n] = branch1[n], L_1[2n+1] = branch2[n].  So a channel born at position p of L_v sits at position
+    p * 2^(t-v) of L_t until that position reaches bf: then it is an input of block t's branch2 (weight column
+    position - bf) and dies; channels that never reach bf live on into L_T, the stage output.
+    Every channel is therefore WRITTEN ONCE, by its producer GEMM, straight into the buffer of the block that
+    consumes it ("bin" t = the bf inputs of block t, or the stage output), and never moved: the producer GEMM's
+    columns are ordered by destination, each destination piece padded to a multiple of 16 channels (32 bytes:
+    whole sectors, one 256-bit store per lane and 16 columns).
+
+    Producers: 0 = branch1 of block 0, 1 = branch2 of block 0, t + 1 = branch2 of block t (1 <= t < n_blocks).
+    Returns (producers, bins, final):
+      producers[k] = {'order': int[n_total] (GEMM column -> producer output channel, -1 padding),
+                      'pieces': [(col0, count, dest, dest_col)], dest = block index t or 'final'}
+      bins[t]      = {'width': W (multiple of 16), 'wcol': int[W] (slot -> weight column of block t's first 1x1, -1 padding)}
+      final        = {'width': W, 'logical': int[W] (slot -> channel index of the stage output, -1 padding)}"""
+    T = n_blocks
+
+    def route(v, p):
+        for t in range(max(v, 1), T):
+            pos = p << (t - v)
+            if pos >= bf:
+                return t, pos - bf
+        return 'final', p << (T - v)
+
+    births = [(1, [2 * n for n in range(bf)]), (1, [2 * n + 1 for n in range(bf)])]
+    births += [(t + 1, [2 * n + 1 for n in range(bf)]) for t in range(1, T)]
+    dest_fill = {t: 0 for t in range(1, T)}
+    dest_fill['final'] = 0
+    slots = {d: [] for d in dest_fill}              # dest -> list of (dest_col, values) pieces
+    producers = []
+    for v, positions in births:
+        routed = [route(v, p) for p in positions]
+        order, pieces = [], []
+        for d in list(range(1, T)) + ['final']:
+            members = [n for n in range(bf) if routed[n][0] == d]
+            if not members:
+                continue
+            padded = (len(members) + 15) // 16 * 16
+            pieces.append((len(order), padded, d, dest_fill[d]))
+            slots[d].append((dest_fill[d], [routed[n][1] for n in members] + [-1] * (padded - len(members))))
+            order += members + [-1] * (padded - len(members))
+            dest_fill[d] += padded
+        producers.append({'order': np.asarray(order, dtype=np.int64), 'pieces': pieces})
+
+    def flat(d):
+        out = np.full((dest_fill[d],), -1, dtype=np.int64)
+        for col, vals in slots[d]:
+            out[col:col + len(vals)] = vals
+        return out
+
+    bins = {t: {'width': dest_fill[t], 'wcol': flat(t)} for t in range(1, T)}
+    final = {'width': dest_fill['final'], 'logical': flat('final')}
+    for t in range(1, T):
+        assert sorted(int(c) for c in bins[t]['wcol'] if c >= 0) == list(range(bf))
+    assert sorted(int(c) for c in final['logical'] if c >= 0) == list(range(2 * bf))
+    return producers, bins, final
+
+
+def default_layout():
+    """'bins' (no pass-through copies, see _plan_stage_bins) or 'shuffle' (every block writes the interleaved
+    2*bf-channel tensor through the fused cat+shuffle epilogue); PIFPAF_LAYOUT overrides."""
+    return os.environ.get('PIFPAF_LAYOUT', 'bins')
+
+
+def build_ops(plan, in_h, in_w, layout=None):
     """Lower a plan to the op list of libpifpaf_b200 (pure Python; no GPU needed).
 
     Returns (tensors, ops): tensors[i] = (h, w, c_phys); ops are dicts with a 'kind' in
@@ -277,6 +347,9 @@ def build_ops(plan, in_h, in_w):
         return _build_ops_resnet(plan, in_h, in_w)
     if plan.get('kind') != 'shufflenetv2k':
         raise RuntimeError('unsupported plan kind')
+    layout = default_layout() if layout is None else layout
+    if layout not in ('bins', 'shuffle'):
+        raise RuntimeError("layout must be 'bins' or 'shuffle'")
     tensors, ops = [], []
 
     def tensor(h, w, c):
@@ -294,6 +367,21 @@ def build_ops(plan, in_h, in_w):
         ops.append({'kind': 'conv1x1', 'in': tin, 'in_off': in_off, 'k_cols': k_cols, 'n_out': n,
                     'w': wp, 'b': _f32(b), 'relu': int(relu), 'out': tout, 'out_off': 0,
                     'shuffle_src': s_t, 'shuffle_off': s_off})
+
+    def conv1x1_scatter(tin, in_cols, k_cols, wb, relu, order, pieces):
+        """1x1 conv whose GEMM columns are the producer's output channels in `order` (-1: padding column, zero
+        weights) and whose column pieces (col0, count, tensor, tensor_col) go to different tensors."""
+        w, b = wb
+        w = w.reshape(w.shape[0], -1)
+        assert len(in_cols) == w.shape[1]
+        real = order >= 0
+        wp = np.zeros((len(order), k_cols), dtype=np.float32)
+        wp[np.ix_(np.nonzero(real)[0], in_cols)] = w[order[real]]
+        bp = np.zeros((len(order),), dtype=np.float32)
+        bp[real] = b[order[real]]
+        ops.append({'kind': 'conv1x1', 'in': tin, 'in_off': 0, 'k_cols': k_cols, 'n_out': len(order),
+                    'w': wp, 'b': bp, 'relu': int(relu), 'out': pieces[0][2], 'out_off': pieces[0][3],
+                    'shuffle_src': -1, 'shuffle_off': 0, 'pieces': [tuple(int(v) for v in pc) for pc in pieces]})
 
     def dwconv(tin, cols, width, wb, kernel, stride, pad, tout):
         w, b = wb
@@ -315,7 +403,49 @@ def build_ops(plan, in_h, in_w):
                 'pad': inp['pad'], 'c_out': c0, 'w': _f32(inp['w']), 'b': _f32(inp['b']), 'relu': 1, 'out': cur})
     lay = _Layout(c0, split=False)
     block_outputs = []
-    for blocks in plan['stages']:
+    for blocks in plan['stages'] if layout == 'bins' else []:
+        # ---- 'bins' layout: every channel is written once, into the buffer of the block that consumes it
+        bf = blocks[0]['b2_pw2'][0].shape[0]
+        hp = pad16(bf)
+        e0 = blocks[0]
+        kk, st, pd = e0['kernel'], e0['stride'], e0['pad']
+        ho, wo = (h + 2 * pd - kk) // st + 1, (w + 2 * pd - kk) // st + 1
+        producers, bins, final = _plan_stage_bins(bf, len(blocks))
+        t_bin = {t: tensor(ho, wo, pad16(bins[t]['width'])) for t in bins}
+        t_bin['final'] = tensor(ho, wo, pad16(final['width']))
+
+        def pieces_of(k):
+            return [(c0_, cnt, t_bin[d], dc) for (c0_, cnt, d, dc) in producers[k]['pieces']]
+
+        cols = lay.cols()
+        # block 0, branch1: dw (stride) -> 1x1; branch2: 1x1 -> dw (stride) -> 1x1   (basenetworks.py:200-226)
+        t_a = tensor(ho, wo, lay.width)
+        dwconv(cur, cols, lay.width, e0['b1_dw'], kk, st, pd, t_a)
+        conv1x1_scatter(t_a, cols, lay.width, e0['b1_pw'], True, producers[0]['order'], pieces_of(0))
+        t_c = tensor(h, w, hp)
+        conv1x1(cur, 0, cols, lay.width, e0['b2_pw1'], True, t_c)
+        t_d = tensor(ho, wo, hp)
+        dwconv(t_c, np.arange(bf), hp, e0['b2_dw'], kk, st, pd, t_d)
+        conv1x1_scatter(t_d, np.arange(bf), hp, e0['b2_pw2'], True, producers[1]['order'], pieces_of(1))
+        h, w = ho, wo
+        for t, e in enumerate(blocks[1:], start=1):
+            assert not e['first'] and e['stride'] == 1 and e['b2_pw2'][0].shape[0] == bf
+            # x2 = the bin of block t: slot j holds the channel that meets weight column wcol[j] of the first 1x1
+            wcol = bins[t]['wcol']
+            in_cols = np.empty((bf,), dtype=np.int64)
+            in_cols[wcol[wcol >= 0]] = np.nonzero(wcol >= 0)[0]
+            width = tensors[t_bin[t]][2]
+            t_c = tensor(h, w, hp)
+            conv1x1(t_bin[t], 0, in_cols, width, e['b2_pw1'], True, t_c)
+            t_d = tensor(h, w, hp)
+            dwconv(t_c, np.arange(bf), hp, e['b2_dw'], e['kernel'], 1, e['pad'], t_d)
+            conv1x1_scatter(t_d, np.arange(bf), hp, e['b2_pw2'], True, producers[t + 1]['order'], pieces_of(t + 1))
+        logical = final['logical']
+        phys = np.empty((2 * bf,), dtype=np.int64)
+        phys[logical[logical >= 0]] = np.nonzero(logical >= 0)[0]
+        cur, lay = t_bin['final'], _Layout(2 * bf, split=False, phys=phys, width=tensors[t_bin['final']][2])
+        block_outputs.append((cur, lay))
+    for blocks in plan['stages'] if layout == 'shuffle' else []:
         for e in blocks:
             bf = e['b2_pw2'][0].shape[0]
             hp = pad16(bf)
@@ -424,12 +554,12 @@ def _build_ops_resnet(plan, in_h, in_w):
 class CompiledNet:
     """A plan compiled to libpifpaf_b200 ops for a fixed input size and maximum batch."""
 
-    def __init__(self, plan, in_h, in_w, max_batch, device=0):
+    def __init__(self, plan, in_h, in_w, max_batch, device=0, layout=None):
         self.lib = _lib.lib()
         self.device = int(device)
         self.max_batch = int(max_batch)
         self.in_h, self.in_w = int(in_h), int(in_w)
-        self.tensor_shapes, ops, self.info = build_ops(plan, self.in_h, self.in_w)
+        self.tensor_shapes, ops, self.info = build_ops(plan, self.in_h, self.in_w, layout=layout)
         self.op_desc = [{k: v for k, v in o.items() if not isinstance(v, np.ndarray)} for o in ops]
         self.handle = ctypes.c_void_p()
         _lib.check(self.lib.pifpaf_net_create(ctypes.byref(self.handle), self.device, self.max_batch))
@@ -462,6 +592,11 @@ class CompiledNet:
             if o['kind'] == 'input_conv':
                 _lib.check(L.pifpaf_net_input_conv(H, o['in_h'], o['in_w'], o['kernel'], o['stride'], o['pad'],
                                                    o['c_out'], _ptr(o['w']), _ptr(o['b']), o['relu'], o['out']))
+            elif o['kind'] == 'conv1x1' and 'pieces' in o:
+                pcs = np.ascontiguousarray(np.asarray(o['pieces'], dtype=np.int32).T)     # rows: col0, count, tensor, col
+                _lib.check(L.pifpaf_net_conv1x1_scatter(H, o['in'], o['in_off'], o['k_cols'], o['n_out'],
+                                                        _ptr(o['w']), _ptr(o['b']), o['relu'], pcs.shape[1],
+                                                        _ptr(pcs[0]), _ptr(pcs[1]), _ptr(pcs[2]), _ptr(pcs[3])))
             elif o['kind'] == 'conv1x1':
                 _lib.check(L.pifpaf_net_conv1x1(H, o['in'], o['in_off'], o['k_cols'], o['n_out'], _ptr(o['w']),
                                                 _ptr(o['b']), o['relu'], o['out'], o['out_off'],

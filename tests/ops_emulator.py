@@ -34,7 +34,10 @@ def run_ops(tensors, ops, images, bf16=False):
             y = q(y)
             n = o['n_out']
             out = acts[o['out']]
-            if o['shuffle_src'] < 0:
+            if 'pieces' in o:
+                for (c0, cnt, t_id, t_col) in o['pieces']:
+                    acts[t_id][..., t_col:t_col + cnt] = y[..., c0:c0 + cnt]
+            elif o['shuffle_src'] < 0:
                 out[..., o['out_off']:o['out_off'] + n] = y
             else:
                 src = acts[o['shuffle_src']][..., o['shuffle_off']:o['shuffle_off'] + n]

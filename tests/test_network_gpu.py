@@ -23,24 +23,27 @@ def small():
     return shell, plan
 
 
-def test_every_op_matches_bf16_emulation(small):
-    """each fused op against a CPU emulation that rounds to bf16 at the same points (tcgen05 and SIMT debug)."""
+@pytest.mark.parametrize('layout', ['bins', 'shuffle'])
+def test_every_op_matches_bf16_emulation(small, layout):
+    """each fused op against a CPU emulation that rounds to bf16 at the same points (tcgen05 and SIMT debug),
+    for both activation layouts (scatter GEMMs into per-block bins / fused cat+shuffle epilogue)."""
     shell, plan = small
     h, w, B = 97, 129, 2
     x = torch.randn(B, 3, h, w, generator=torch.Generator().manual_seed(0))
-    tensors, ops, _ = network.build_ops(plan, h, w)
+    tensors, ops, _ = network.build_ops(plan, h, w, layout=layout)
     emu_heads, emu_acts = ops_emulator.run_ops(tensors, ops, x, bf16=True)
-    net = network.CompiledNet(plan, h, w, B)
+    net = network.CompiledNet(plan, h, w, B, layout=layout)
     for impl in (1, 0):
         heads = net.forward(x.cuda(), gemm_impl=impl)
         torch.cuda.synchronize()
         for o in ops:
             if o['kind'] == 'heads':
                 continue
-            got = net.tap(o['out'], B)
-            ref = emu_acts[o['out']].numpy()
-            scale = max(float(np.abs(ref).max()), 1e-6)
-            assert float(np.abs(got - ref).max()) / scale < 3e-2, (impl, o['kind'], o['out'])
+            for t_id in sorted({pc[2] for pc in o['pieces']}) if 'pieces' in o else [o['out']]:
+                got = net.tap(t_id, B)
+                ref = emu_acts[t_id].numpy()
+                scale = max(float(np.abs(ref).max()), 1e-6)
+                assert float(np.abs(got - ref).max()) / scale < 3e-2, (impl, o['kind'], t_id)
         for hg, he in zip(heads, emu_heads):
             assert float((hg.cpu() - he).abs().max()) < 5e-2
 

@@ -68,30 +68,75 @@ def test_oracle_net_equals_reference_modules():
         torch.testing.assert_close(g, w, rtol=0, atol=1e-5)
 
 
+@pytest.mark.parametrize('layout', ['bins', 'shuffle'])
 @pytest.mark.parametrize('shape', [(97, 129), (65, 65)])
-def test_lowering_reproduces_oracle_net(shape):
+def test_lowering_reproduces_oracle_net(shape, layout):
     h, w = shape
     shell = net_oracle.make_shell('shufflenetv2k16', seed=1)
     x = torch.randn(2, 3, h, w)
     with torch.no_grad():
         want = shell(x)
     plan = network.plan_from_shell(shell)
-    tensors, ops, _ = network.build_ops(plan, h, w)
+    tensors, ops, _ = network.build_ops(plan, h, w, layout=layout)
     got, _ = ops_emulator.run_ops(tensors, ops, x)
     for g, wnt in zip(got, want):
         assert g.shape == wnt.shape
         assert float((g - wnt).abs().max()) < 2e-5
     # rows start on 32-byte boundaries (256-bit stores); TMA views start on 16-byte boundaries
+    assert all(c % 16 == 0 for (_, _, c) in tensors)
     for o in ops:
         if o['kind'] in ('conv1x1', 'dwconv'):
-            assert o['out_off'] % 16 == 0 and o['in_off'] % 8 == 0
-    assert all(c % 16 == 0 for (_, _, c) in tensors)
-    # x.chunk(2) of 348 channels: the view starts at or below column 174 on a multiple of 8, the leading columns
-    # carry zero weights
-    a0 = network._view_start(174)
-    assert a0 % 8 == 0 and 174 - 64 < a0 <= 174
-    views = [o for o in ops if o['kind'] == 'conv1x1' and o['in_off'] == a0]
-    assert views and all(not o['w'][:, :174 - a0].any() for o in views)
+            assert o['in_off'] % 8 == 0
+    if layout == 'shuffle':
+        for o in ops:
+            if o['kind'] in ('conv1x1', 'dwconv'):
+                assert o['out_off'] % 16 == 0
+        # x.chunk(2) of 348 channels: the view starts at or below column 174 on a multiple of 8, the leading
+        # columns carry zero weights
+        a0 = network._view_start(174)
+        assert a0 % 8 == 0 and 174 - 64 < a0 <= 174
+        views = [o for o in ops if o['kind'] == 'conv1x1' and o['in_off'] == a0]
+        assert views and all(not o['w'][:, :174 - a0].any() for o in views)
+    else:
+        # no fused shuffle, no column views: every 1x1 reads a whole tensor and the scatter pieces tile its columns
+        assert all(o['shuffle_src'] < 0 and o['in_off'] == 0 for o in ops if o['kind'] == 'conv1x1')
+        scat = [o for o in ops if 'pieces' in o]
+        assert len(scat) == 2 * 3 + (3 + 7 + 3)          # two producers per first block + one per later block
+        for o in scat:
+            cols = 0
+            for (c0, cnt, t_id, t_col) in o['pieces']:
+                assert c0 == cols and cnt % 16 == 0 and t_col % 16 == 0 and t_col + cnt <= tensors[t_id][2]
+                cols += cnt
+            assert cols == o['n_out'] == o['w'].shape[0]
+
+
+def test_stage_bins_route_every_channel_once():
+    """_plan_stage_bins against a direct simulation of cat + channel_shuffle + chunk on channel labels."""
+    for bf, T in ((174, 4), (348, 8), (6, 3), (10, 5), (256, 8)):
+        producers, bins, final = network._plan_stage_bins(bf, T)
+        # labels: (producer, channel); block 0 interleaves producers 0 and 1; block t interleaves x1 with producer t+1
+        vec = [lab for n in range(bf) for lab in ((0, n), (1, n))]
+        consumed = {}
+        for t in range(1, T):
+            x1, x2 = vec[:bf], vec[bf:]
+            consumed[t] = x2
+            vec = [lab for n in range(bf) for lab in (x1[n], (t + 1, n))]
+        where = {}                                         # label -> (dest, slot)
+        for k, pr in enumerate(producers):
+            for (c0, cnt, d, dc) in pr['pieces']:
+                for i in range(cnt):
+                    n = int(pr['order'][c0 + i])
+                    if n >= 0:
+                        assert (k, n) not in where
+                        where[(k, n)] = (d, dc + i)
+        assert len(where) == (T + 1) * bf
+        for t in range(1, T):
+            for wc, lab in enumerate(consumed[t]):
+                d, slot = where[lab]
+                assert d == t and bins[t]['wcol'][slot] == wc
+        for c, lab in enumerate(vec):
+            d, slot = where[lab]
+            assert d == 'final' and final['logical'][slot] == c
 
 
 def test_k30_wholebody_lowering_reproduces_oracle_net():
