@@ -710,10 +710,6 @@ __global__ void __launch_bounds__(256) k_dwconv5(DwArgs a) {
 // one lane = one channel pair.  The lane keeps its 25x2 weights and a 4 x BW x 2 f32 accumulator in registers and
 // reads every input pixel of the block's window exactly once (4 bytes per lane, 128 bytes per warp request: one
 // conflict-free wavefront).
-#ifndef DW_PACKED_COLS
-#define DW_PACKED_COLS 2      // of the 4 output columns of a warp's block: how many accumulate with FFMA2
-#endif
-
 template <int S, int TH, int TW, int BW, int NSTAGE>
 struct DwTile {
     static constexpr int IH = (TH - 1) * S + 5, IW = (TW - 1) * S + 5;
@@ -724,22 +720,6 @@ struct DwTile {
     static constexpr int WIN_X = (BW - 1) * S + 5;
     static constexpr int SMEM = NSTAGE * BYTES + 128;
 };
-
-// Blackwell packed fp32 FMA (FFMA2): two independent IEEE fp32 fused multiply-adds on 64-bit register pairs in one
-// issue slot, bit-identical to two fmaf() calls.  Measured on B200 (round 1): FFMA2 runs on the fmaheavy pipe only,
-// at half the FMA rate of scalar FFMA, so a kernel made of FFMA2 alone trades its issue bound for a pipe bound; the
-// depthwise kernel uses it for HALF of its accumulators so that issue slots and FMA pipes fill up together.
-__device__ __forceinline__ uint64_t f32x2_pack(float lo, float hi) {
-    uint64_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void f32x2_unpack(uint64_t v, float& lo, float& hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ void f32x2_fma(uint64_t& acc, uint64_t a, uint64_t b) {
-    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
-}
 
 // position of a work item and its increment per persistent-loop step, kept as mixed-radix digits
 // (channel block, image, tile row, tile column) so that the loop needs no integer division
@@ -826,18 +806,11 @@ k_dwconv5_tma(const __grid_constant__ CUtensorMap tmap_in, DwArgs a) {
         if (oy0 < a.Hout && ox0 < a.Wout && c0 < C) {
             const unsigned char* tile = dsm + (size_t)buf * T::BYTES + lane * 4 +
                                         ((by * 4 * S) * T::IW + bx * BW * S) * 128;
-            // accumulators of output columns j < JP live as packed pairs (FFMA2), the others as scalars (FFMA)
-            constexpr int JP = DW_PACKED_COLS < BW ? DW_PACKED_COLS : BW;
             float acc[4][BW][2];
-            uint64_t accp[4][JP > 0 ? JP : 1];
-            const uint64_t bias2 = f32x2_pack(bias0, bias1);
 #pragma unroll
             for (int i = 0; i < 4; i++)
 #pragma unroll
-                for (int j = 0; j < BW; j++) {
-                    if (j < JP) accp[i][j] = bias2;
-                    else { acc[i][j][0] = bias0; acc[i][j][1] = bias1; }
-                }
+                for (int j = 0; j < BW; j++) { acc[i][j][0] = bias0; acc[i][j][1] = bias1; }
 #pragma unroll
             for (int ry = 0; ry < T::WIN_Y; ry++) {
                 float f[T::WIN_X][2];
@@ -853,23 +826,14 @@ k_dwconv5_tma(const __grid_constant__ CUtensorMap tmap_in, DwArgs a) {
                     if (ky < 0 || ky >= 5) continue;
 #pragma unroll
                     for (int kx = 0; kx < 5; kx++) {
-                        const uint64_t w2 = f32x2_pack(wgt[ky * 5 + kx][0], wgt[ky * 5 + kx][1]);
 #pragma unroll
                         for (int j = 0; j < BW; j++) {
-                            if (j < JP) {
-                                f32x2_fma(accp[i][j], f32x2_pack(f[j * S + kx][0], f[j * S + kx][1]), w2);
-                            } else {
-                                acc[i][j][0] = fmaf(f[j * S + kx][0], wgt[ky * 5 + kx][0], acc[i][j][0]);
-                                acc[i][j][1] = fmaf(f[j * S + kx][1], wgt[ky * 5 + kx][1], acc[i][j][1]);
-                            }
+                            acc[i][j][0] = fmaf(f[j * S + kx][0], wgt[ky * 5 + kx][0], acc[i][j][0]);
+                            acc[i][j][1] = fmaf(f[j * S + kx][1], wgt[ky * 5 + kx][1], acc[i][j][1]);
                         }
                     }
                 }
             }
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-#pragma unroll
-                for (int j = 0; j < JP; j++) f32x2_unpack(accp[i][j], acc[i][j][0], acc[i][j][1]);
             if (a.relu) {
 #pragma unroll
                 for (int i = 0; i < 4; i++)
