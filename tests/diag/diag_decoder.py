@@ -7,7 +7,7 @@ import time
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from openpifpaf_b200 import synth, decoder as dec   # noqa: E402
 from oracle import cifcaf as oc                      # noqa: E402
 

@@ -13,7 +13,7 @@ if ! grep -q "DIAG_GEMM ALL OK" gpurun_out/diag_gemm.log; then
 fi
 echo "== pytest -m gpu (all but resnet)"; timeout -k 5 400 python -m pytest tests -m gpu -q -x --durations=6 -k "not resnet" > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?"
 tail -25 gpurun_out/pytest_gpu.log
-echo "== diag_net"; timeout -k 5 300 python tools/diag_net.py > gpurun_out/diag_net.log 2>&1; echo "rc=$?"
+echo "== diag_net"; timeout -k 5 300 python tests/diag/diag_net.py > gpurun_out/diag_net.log 2>&1; echo "rc=$?"
 tail -30 gpurun_out/diag_net.log
 echo "== decoder perf"; timeout -k 5 200 python tools/diag_decoder_perf.py > gpurun_out/decoder_perf.log 2>&1; echo "rc=$?"
 tail -8 gpurun_out/decoder_perf.log
