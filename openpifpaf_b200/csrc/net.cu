@@ -153,6 +153,7 @@ enum { MODE_PLAIN = 0, MODE_SHUFFLE = 1, MODE_HEADS = 2, MODE_SCATTER = 3 };
 // MODE_SCATTER: destination of one chunk of 16 GEMM columns (32 bytes per row, one 256-bit store per lane): base
 // already points at the chunk's first column inside its tensor (a multiple of 16 channels)
 struct DestGroup { __nv_bfloat16* base; int ld; int pad; };
+static_assert(sizeof(DestGroup) == 16, "DestGroup is copied to shared memory as 16-byte entries");
 
 struct HeadCol { int head; int plane; int op; int pad; };   // per GEMM output column (heads mode)
 
@@ -243,8 +244,11 @@ __device__ __forceinline__ void store_words(uint32_t* p, const uint32_t (&w)[CHU
 // bias: pointer to this chunk's CHUNK biases (shared memory in the tensor-core kernel, global in the debug
 // kernel).  src_row: this lane's row of the pass-through tile at the chunk's first column (shared memory, filled
 // by TMA) or nullptr to read it from global memory.
+// dest: the MODE_SCATTER destination table (shared memory in the tensor-core kernel: a global load per chunk put
+// 11 warps per issue on the long scoreboard, ncu round 1; global in the debug kernel)
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, int m, int n0, const float* acc,
-                                               const float* bias, const __nv_bfloat16* src_row) {
+                                               const float* bias, const __nv_bfloat16* src_row,
+                                               const DestGroup* dest) {
     float bv[CHUNK];
     {
         const float4* bp = reinterpret_cast<const float4*>(bias);
@@ -281,7 +285,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, int m, int n0,
             w[j >> 1] = pack_bf16(a0, a1);
         }
         if (n0 < g.N) {
-            const DestGroup d = g.dest[n0 >> 4];
+            const DestGroup d = dest[n0 >> 4];
             st_global_256(d.base + (size_t)m * d.ld, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
         }
         return;
@@ -362,7 +366,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
     const int src_bytes = g.src_tma ? BM * g.block_n * 2 : 0;
     unsigned char* src_tiles = b_res + b_res_bytes;
     float* bias_s = reinterpret_cast<float*>(src_tiles + 2 * (size_t)src_bytes);   // [n_blocks * block_n]
-    unsigned char* tail = reinterpret_cast<unsigned char*>(bias_s + g.n_blocks * g.block_n);
+    DestGroup* dest_s = reinterpret_cast<DestGroup*>(bias_s + g.n_blocks * g.block_n);   // [n_blocks * block_n / 16]
+    unsigned char* tail = reinterpret_cast<unsigned char*>(dest_s + g.n_blocks * g.block_n / CHUNK);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);            // [stages]
     uint64_t* empty_bar = full_bar + g.stages;                          // [stages]
     uint64_t* tmem_full = empty_bar + g.stages;                         // [2]
@@ -381,6 +386,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
         if (g.src_tma) tma_prefetch_desc(&tmap_src);
     }
     for (int i = threadIdx.x; i < g.n_blocks * g.block_n; i += GEMM_THREADS) bias_s[i] = g.bias[i];
+    if (g.mode == MODE_SCATTER)
+        for (int i = threadIdx.x; i < g.n_blocks * g.block_n / CHUNK; i += GEMM_THREADS) dest_s[i] = g.dest[i];
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < g.stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -511,7 +518,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
                 for (int j = 0; j < CHUNK; j++) accf[j] = __uint_as_float(v[j]);
                 const int n0 = n_blk * g.block_n + c;
                 if (n0 < ((g.N + 7) & ~7))
-                    epilogue_chunk(g, m, n0, accf, bias_s + n0, g.src_tma ? src_tile_row + c : nullptr);
+                    epilogue_chunk(g, m, n0, accf, bias_s + n0, g.src_tma ? src_tile_row + c : nullptr, dest_s);
             };
             if (c_begin < c_end) tmem_ld16_async(t_row + (uint32_t)(c_begin * CHUNK), va);
             for (int ci = c_begin; ci < c_end; ci += 2) {
@@ -584,7 +591,7 @@ __global__ void __launch_bounds__(128) k_gemm_simt(GemmArgs g) {
                 }
             }
         }
-        if (n0 < ((g.N + 7) & ~7)) epilogue_chunk(g, m, n0, acc, g.bias + n0, nullptr);
+        if (n0 < ((g.N + 7) & ~7)) epilogue_chunk(g, m, n0, acc, g.bias + n0, nullptr, g.dest);
     }
 }
 
@@ -1201,7 +1208,7 @@ size_t gemm_smem_bytes(int block_n, int n_blocks, int stages, bool shuffle, bool
     const size_t b_stage = b_resident ? 0 : (size_t)block_n * BK * 2;
     const size_t b_res = b_resident ? (size_t)num_k_blocks * block_n * BK * 2 : 0;
     return 1024 + (size_t)stages * (BM * BK * 2 + b_stage) + b_res + (shuffle ? 2 * (size_t)BM * block_n * 2 : 0) +
-           (size_t)n_blocks * block_n * 4 + (2 * stages + 7) * 8 + 64;
+           (size_t)n_blocks * block_n * 5 + (2 * stages + 7) * 8 + 64;      // bias (4 B) + scatter table (1 B) per column
 }
 
 int choose_stages(int block_n, int n_blocks, int num_k_blocks, bool shuffle) {
