@@ -110,6 +110,39 @@ def test_lowering_reproduces_oracle_net(shape, layout):
             assert cols == o['n_out'] == o['w'].shape[0]
 
 
+def _simulate_stage(bf, T):
+    """cat + channel_shuffle + chunk of basenetworks.py:233-242 on channel labels (producer, channel)."""
+    vec = [lab for n in range(bf) for lab in ((0, n), (1, n))]
+    consumed = {}
+    for t in range(1, T):
+        x1, x2 = vec[:bf], vec[bf:]
+        consumed[t] = x2
+        vec = [lab for n in range(bf) for lab in (x1[n], (t + 1, n))]
+    return consumed, vec
+
+
+@pytest.mark.parametrize('seed', range(4))
+def test_stage_bins_random_sizes(seed):
+    """any branch width / block count: every bin holds exactly the inputs of its block, pieces are 16-aligned"""
+    rng = np.random.default_rng(seed)
+    bf, T = int(rng.integers(1, 90)) * 2, int(rng.integers(1, 10))
+    producers, bins, final = network._plan_stage_bins(bf, T)
+    consumed, vec = _simulate_stage(bf, T)
+    where = {}
+    for k, pr in enumerate(producers):
+        assert len(pr['order']) % 16 == 0
+        for (c0, cnt, d, dc) in pr['pieces']:
+            assert cnt % 16 == 0 and dc % 16 == 0
+            for i in range(cnt):
+                if pr['order'][c0 + i] >= 0:
+                    where[(k, int(pr['order'][c0 + i]))] = (d, dc + i)
+    for t in range(1, T):
+        assert [bins[t]['wcol'][where[lab][1]] for lab in consumed[t]] == list(range(bf))
+        assert all(where[lab][0] == t for lab in consumed[t])
+    assert [final['logical'][where[lab][1]] for lab in vec] == list(range(2 * bf))
+    assert all(where[lab][0] == 'final' for lab in vec)
+
+
 def test_stage_bins_route_every_channel_once():
     """_plan_stage_bins against a direct simulation of cat + channel_shuffle + chunk on channel labels."""
     for bf, T in ((174, 4), (348, 8), (6, 3), (10, 5), (256, 8)):
