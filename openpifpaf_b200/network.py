@@ -11,15 +11,17 @@ same attribute names), folds every eval-mode BatchNorm into its convolution and
 returns a plain "plan" of float32 numpy arrays.  `CompiledNet` turns a plan into
 a fused op list of libpifpaf_b200 (tcgen05 GEMMs for the 1x1 convolutions) and
 replays it.  torch.cat / chunk / channel_shuffle never run as kernels: they are
-folded into the physical channel placement computed here:
+folded into the physical channel placement computed here.
 
-  activations are stored in logical channel order (rows padded to 16 channels);
-  the last GEMM of a block writes logical channel 2n <- pass-through[n],
-  2n+1 <- conv[n] (== cat + channel_shuffle(groups=2), basenetworks.py:233-242)
-  with aligned 256-bit stores, and the next block's x.chunk(2) is the TMA start
-  coordinate _view_start(half) of its A operand (16-byte aligned at least, 32-byte
-  or more where the K-block count allows; the leading pass-through columns meet
-  zero weight columns).
+  'bins' layout (default): every channel of a stage is written once, by the GEMM
+  that produces it, into the buffer of the block that consumes it; pass-through
+  channels are never copied (see _plan_stage_bins).
+
+  'shuffle' layout: activations in logical channel order; the last GEMM of a block
+  writes logical channel 2n <- pass-through[n], 2n+1 <- conv[n] (== cat +
+  channel_shuffle(groups=2), basenetworks.py:233-242) with aligned 256-bit stores,
+  and the next block's x.chunk(2) is the TMA start coordinate _view_start(half) of
+  its A operand (the leading pass-through columns meet zero weight columns).
 """
 import ctypes
 import os
