@@ -233,6 +233,13 @@ int pifpaf_net_head_output(pifpaf_net_t* net, int32_t head, float** dev_ptr,
  * by tests to cross-check the tensor-core path. */
 int pifpaf_net_forward(pifpaf_net_t* net, const float* images_dev, int32_t batch, int32_t gemm_impl,
                        void* stream);
+/* Shell.forward on RAW images: images_nhwc_dev [batch][in_h][in_w][3] uint8 (device).  The stem applies the
+ * reference's eval preprocessing on load -- torchvision ToTensor + Normalize (transforms/__init__.py:26-33):
+ * ((u / 255) - mean[c]) / std[c], IEEE division and subtraction, zero padding in the normalised domain -- so the
+ * fields equal pifpaf_net_forward on the normalised float image bit for bit, with a quarter of the input bytes. */
+int pifpaf_net_forward_u8(pifpaf_net_t* net, const uint8_t* images_nhwc_dev, int32_t batch, const float* mean,
+                          const float* stdev, int32_t gemm_impl, void* stream);
+
 /* Same as pifpaf_net_forward but brackets every op with CUDA events on `stream` and, after a final
  * synchronise, writes per-op milliseconds to op_ms[num_ops] (profiling leg of bench.py; never the
  * headline timing).  op_kind[i]: 0 input conv, 1 tcgen05 GEMM, 2 depthwise conv; op_flops/op_bytes are

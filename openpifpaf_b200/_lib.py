@@ -64,6 +64,7 @@ SYMBOLS = {
     'pifpaf_net_heads': (ctypes.c_int, [VP, c_i32, c_i32, c_i32, VP, VP, VP, VP, VP]),
     'pifpaf_net_head_output': (ctypes.c_int, [VP, c_i32, P(VP), P(c_i32), P(c_i32), P(c_i32), P(c_i32)]),
     'pifpaf_net_forward': (ctypes.c_int, [VP, VP, c_i32, c_i32, VP]),
+    'pifpaf_net_forward_u8': (ctypes.c_int, [VP, VP, c_i32, VP, VP, c_i32, VP]),
     'pifpaf_net_forward_timed': (ctypes.c_int, [VP, VP, c_i32, c_i32, VP, VP, VP, VP, VP]),
     'pifpaf_net_tap_tensor': (ctypes.c_int, [VP, c_i32, c_i32, VP, c_i64]),
     'pifpaf_net_set_tensor': (ctypes.c_int, [VP, c_i32, c_i32, VP, c_i64]),

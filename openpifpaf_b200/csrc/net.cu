@@ -935,12 +935,15 @@ __global__ void __launch_bounds__(256) k_dwconv(DwArgs a) {
 // ------------------------------------------------------------------ input conv: f32 NCHW [B,3,H,W] -> bf16 NHWC
 struct InConvArgs {
     const float* in; __nv_bfloat16* out; int ld_out;
+    // raw-image variant: uint8 [B][H][W][3] (what PIL / the decoder of a video stream delivers); the kernel applies
+    // torchvision's ToTensor + Normalize (transforms/__init__.py:26-33) on load: ((u / 255) - mean[c]) / std[c]
+    const uint8_t* in_u8; float mean[3], stdev[3];
     const float* weight;   // [3*k*k][C8*8] (tap-major)
     const float* bias;     // [C8*8]
     int B, Hin, Win, Hout, Wout, C8, kernel, stride, pad, relu;
 };
 
-template <int KS>
+template <int KS, bool U8>
 __global__ void __launch_bounds__(256) k_input_conv(InConvArgs a) {
     // one thread = one output pixel, all output channels: the 3*k*k input samples are loaded once (registers for
     // k = 3, thread-local memory for k = 7) and reused for every 8-channel group; weights are broadcast reads
@@ -970,7 +973,16 @@ __global__ void __launch_bounds__(256) k_input_conv(InConvArgs a) {
                 for (int kx = 0; kx < KS; kx++) {
                     const int ix = ox * a.stride - a.pad + kx;
                     const bool ok = iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win;
-                    in[(ci * KS + ky) * KS + kx] = ok ? __ldg(plane + (size_t)iy * a.Win + ix) : 0.f;
+                    float v = 0.f;
+                    if (ok) {
+                        if (U8) {
+                            const float u = (float)__ldg(a.in_u8 + (((size_t)b * a.Hin + iy) * a.Win + ix) * 3 + ci);
+                            v = __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.f), a.mean[ci]), a.stdev[ci]);
+                        } else {
+                            v = __ldg(plane + (size_t)iy * a.Win + ix);
+                        }
+                    }
+                    in[(ci * KS + ky) * KS + kx] = v;
                 }
             }
         }
@@ -1620,10 +1632,12 @@ int pifpaf_net_head_output(pifpaf_net_t* net, int32_t head, float** dev_ptr,
     return PIFPAF_OK;
 }
 
+struct RawImages { const uint8_t* images; float mean[3], stdev[3]; };
+
 static int net_forward_impl(pifpaf_net_t* net, const float* images_dev, int32_t batch, int32_t gemm_impl,
-                            cudaStream_t st, cudaEvent_t* events) {
+                            cudaStream_t st, cudaEvent_t* events, const RawImages* u8 = nullptr) {
     PIFPAF_CHECK_ARG(net != nullptr, "null argument");
-    PIFPAF_CHECK_ARG(images_dev != nullptr || net->in_h == 0, "images pointer is null");
+    PIFPAF_CHECK_ARG(images_dev != nullptr || u8 != nullptr || net->in_h == 0, "images pointer is null");
     PIFPAF_CHECK_ARG(batch >= 1 && batch <= net->max_batch, "batch exceeds max_batch");
     PIFPAF_CUDA_TRY(cudaSetDevice(net->device));
     int op_index = 0;
@@ -1636,10 +1650,17 @@ static int net_forward_impl(pifpaf_net_t* net, const float* images_dev, int32_t 
             const long long total = (long long)batch * a.Hout * a.Wout;
             const int grid = (int)std::min<long long>((total + 255) / 256, (long long)net->n_sm * 16);
             const size_t smem = sizeof(float) * ((size_t)3 * a.kernel * a.kernel * a.C8 * 8 + a.C8 * 8);
-            if (a.kernel == 3) k_input_conv<3><<<grid, 256, smem, st>>>(a);
-            else if (a.kernel == 7) k_input_conv<7><<<grid, 256, smem, st>>>(a);
-            else if (a.kernel == 5) k_input_conv<5><<<grid, 256, smem, st>>>(a);
-            else k_input_conv<1><<<grid, 256, smem, st>>>(a);
+            if (u8 != nullptr) {
+                a.in_u8 = u8->images;
+                for (int c = 0; c < 3; c++) { a.mean[c] = u8->mean[c]; a.stdev[c] = u8->stdev[c]; }
+                if (a.kernel == 3) k_input_conv<3, true><<<grid, 256, smem, st>>>(a);
+                else if (a.kernel == 7) k_input_conv<7, true><<<grid, 256, smem, st>>>(a);
+                else if (a.kernel == 5) k_input_conv<5, true><<<grid, 256, smem, st>>>(a);
+                else k_input_conv<1, true><<<grid, 256, smem, st>>>(a);
+            } else if (a.kernel == 3) k_input_conv<3, false><<<grid, 256, smem, st>>>(a);
+            else if (a.kernel == 7) k_input_conv<7, false><<<grid, 256, smem, st>>>(a);
+            else if (a.kernel == 5) k_input_conv<5, false><<<grid, 256, smem, st>>>(a);
+            else k_input_conv<1, false><<<grid, 256, smem, st>>>(a);
             PIFPAF_LAUNCH_CHECK();
         } else if (op.kind == OP_DW) {
             DwArgs a = op.dw;
@@ -1695,6 +1716,18 @@ static int net_forward_impl(pifpaf_net_t* net, const float* images_dev, int32_t 
 int pifpaf_net_forward(pifpaf_net_t* net, const float* images_dev, int32_t batch, int32_t gemm_impl,
                        void* stream_v) {
     return net_forward_impl(net, images_dev, batch, gemm_impl, reinterpret_cast<cudaStream_t>(stream_v), nullptr);
+}
+
+int pifpaf_net_forward_u8(pifpaf_net_t* net, const uint8_t* images_nhwc_dev, int32_t batch, const float* mean,
+                          const float* stdev, int32_t gemm_impl, void* stream_v) {
+    PIFPAF_CHECK_ARG(images_nhwc_dev != nullptr && mean != nullptr && stdev != nullptr, "null argument");
+    RawImages raw;
+    raw.images = images_nhwc_dev;
+    for (int c = 0; c < 3; c++) {
+        PIFPAF_CHECK_ARG(stdev[c] > 0.f, "std must be positive");
+        raw.mean[c] = mean[c]; raw.stdev[c] = stdev[c];
+    }
+    return net_forward_impl(net, nullptr, batch, gemm_impl, reinterpret_cast<cudaStream_t>(stream_v), nullptr, &raw);
 }
 
 int pifpaf_net_forward_timed(pifpaf_net_t* net, const float* images_dev, int32_t batch, int32_t gemm_impl,

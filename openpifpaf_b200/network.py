@@ -635,11 +635,38 @@ class CompiledNet:
         _lib.check(self.lib.pifpaf_net_forward(self.handle, image_batch.data_ptr(), b, int(gemm_impl),
                                                ctypes.c_void_p(st.cuda_stream)))
         self._keepalive = image_batch
+        return self._head_views(b)
+
+    def _head_views(self, b):
         outs = []
         for hd in self.heads:
             arr = _DevArray(hd['ptr'], (b, hd['n_fields'], hd['n_comp'], hd['h'], hd['w']))
             outs.append(torch.as_tensor(arr, device=f'cuda:{self.device}'))
         return tuple(outs)
+
+    # the reference's eval preprocessing constants (transforms/__init__.py:26-33)
+    IMAGE_MEAN = (0.485, 0.456, 0.406)
+    IMAGE_STD = (0.229, 0.224, 0.225)
+
+    def forward_uint8(self, image_batch, *, mean=IMAGE_MEAN, std=IMAGE_STD, gemm_impl=0, stream=None):
+        """Shell.forward on raw images: image_batch [B,H,W,3] uint8 CUDA (HWC, as PIL / numpy hold them).  ToTensor
+        and Normalize(mean, std) of the reference's EVAL_TRANSFORM are applied inside the stem kernel; the result
+        equals forward() on the normalised float batch bit for bit."""
+        if not image_batch.is_cuda or image_batch.dtype != torch.uint8:
+            raise RuntimeError('image_batch must be a uint8 CUDA tensor')
+        if image_batch.dim() != 4 or image_batch.shape[3] != 3 or tuple(image_batch.shape[1:3]) != (self.in_h, self.in_w):
+            raise RuntimeError(f'expected [B,{self.in_h},{self.in_w},3]')
+        b = int(image_batch.shape[0])
+        if b > self.max_batch:
+            raise RuntimeError('batch exceeds max_batch')
+        image_batch = image_batch.contiguous()
+        st = stream if stream is not None else torch.cuda.current_stream(image_batch.device)
+        m = (ctypes.c_float * 3)(*[float(v) for v in mean])
+        s = (ctypes.c_float * 3)(*[float(v) for v in std])
+        _lib.check(self.lib.pifpaf_net_forward_u8(self.handle, image_batch.data_ptr(), b, m, s, int(gemm_impl),
+                                                  ctypes.c_void_p(st.cuda_stream)))
+        self._keepalive = image_batch
+        return self._head_views(b)
 
     def forward_timed(self, image_batch, *, gemm_impl=0):
         """Profiling pass: per-op (ms, kind, flops, bytes); kind 0 input conv, 1 tcgen05 GEMM, 2 depthwise."""

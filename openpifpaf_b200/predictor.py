@@ -33,31 +33,41 @@ class Predictor:
         self._dev_images = None
         self.last_nn_time = 0.0
         self.last_decoder_time = 0.0
+        self.image_mean = _network.CompiledNet.IMAGE_MEAN
+        self.image_std = _network.CompiledNet.IMAGE_STD
 
     def fields_batch(self, image_batch):
         """decoder/decoder.py:76-112 without the .cpu(): returns device-resident head tensors."""
-        return self.net.forward(image_batch)
+        return self._forward(image_batch)
+
+    def _forward(self, image_batch_dev):
+        """float32 [B,3,H,W] (already normalised, what the reference's dataloader yields) or raw uint8 [B,H,W,3]
+        (ToTensor + Normalize of transforms/__init__.py:26-33 fused into the stem kernel)."""
+        if image_batch_dev.dtype == torch.uint8:
+            return self.net.forward_uint8(image_batch_dev, mean=self.image_mean, std=self.image_std)
+        return self.net.forward(image_batch_dev)
 
     def batch_device(self, image_batch_dev):
         """Device-resident images -> enqueue forward + decode on the current stream (no host sync)."""
-        heads = self.net.forward(image_batch_dev)
+        heads = self._forward(image_batch_dev)
         cif, caf = heads[self.cif_head], heads[self.caf_head]
         self.decoder.decode_batch_async(cif, self.net.heads[self.cif_head]['stride'],
                                         caf, self.net.heads[self.caf_head]['stride'])
 
     def batch(self, image_batch_host):
-        """decoder/decoder.py:114-137: image batch (host, ideally pinned, float32 [B,3,H,W]) -> per-image
-        (annotations [N,K,4], ids [N]) CPU tensors.  H2D, forward, decode and D2H all inside."""
+        """decoder/decoder.py:114-137: image batch (host, ideally pinned; float32 [B,3,H,W] normalised, or raw
+        uint8 [B,H,W,3]) -> per-image (annotations [N,K,4], ids [N]) CPU tensors.  H2D, forward, decode and D2H
+        all inside."""
         t0 = time.perf_counter()
         with torch.cuda.stream(self.stream):
-            if self._dev_images is None or self._dev_images.shape != image_batch_host.shape:
-                self._dev_images = torch.empty(image_batch_host.shape, dtype=torch.float32, device=self.device)
+            if (self._dev_images is None or self._dev_images.shape != image_batch_host.shape
+                    or self._dev_images.dtype != image_batch_host.dtype):
+                self._dev_images = torch.empty(image_batch_host.shape, dtype=image_batch_host.dtype, device=self.device)
             self._dev_images.copy_(image_batch_host, non_blocking=True)
             self.batch_device(self._dev_images)
             result = self.decoder.fetch(stream=self.stream)
         self.last_nn_time = self.last_decoder_time = time.perf_counter() - t0
         return result
-
 
     def batches(self, host_batches):
         """Pipelined variant of `batch` over an iterable of host image batches (what Predictor.dataloader /
@@ -68,8 +78,8 @@ class Predictor:
         outstanding = 0
         for i, host in enumerate(host_batches):
             s = i % 2
-            if dev[s] is None or dev[s].shape != host.shape:
-                dev[s] = torch.empty(host.shape, dtype=torch.float32, device=self.device)
+            if dev[s] is None or dev[s].shape != host.shape or dev[s].dtype != host.dtype:
+                dev[s] = torch.empty(host.shape, dtype=host.dtype, device=self.device)
                 copied[s], consumed[s] = torch.cuda.Event(), None
             with torch.cuda.stream(self.copy_stream):
                 if consumed[s] is not None:

@@ -180,3 +180,28 @@ def test_k30_wholebody_network_and_decode():
     for b in range(B):
         oa, _ = oc.decode(cif[b], 16, caf[b], 16, sk, constants.WHOLEBODY_N_KEYPOINTS, params=p)
         helpers.assert_annotations_close(res[b][0].numpy(), oa, f'k30 wholebody image {b}')
+
+
+def test_raw_uint8_images_equal_normalised_float_images():
+    """SURVEY 8f rank 2 (GPU preprocessing): the stem applies ToTensor + Normalize (transforms/__init__.py:26-33)
+    on load; fields and annotations are identical, bit for bit, to the float path fed with the same normalisation
+    done by torch on the host."""
+    plan = network.random_plan('shufflenetv2k16', seed=0)
+    B, H, W = 3, 193, 161
+    net = network.CompiledNet(plan, H, W, B)
+    g = torch.Generator().manual_seed(11)
+    raw = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8)
+    mean = torch.tensor(network.CompiledNet.IMAGE_MEAN, dtype=torch.float32)
+    std = torch.tensor(network.CompiledNet.IMAGE_STD, dtype=torch.float32)
+    normalised = ((raw.permute(0, 3, 1, 2).to(torch.float32) / 255.0) - mean.view(1, 3, 1, 1)) / std.view(1, 3, 1, 1)
+    want = [t.clone() for t in net.forward(normalised.contiguous().cuda())]
+    got = net.forward_uint8(raw.cuda())
+    for tg, tw in zip(got, want):
+        assert torch.equal(tg, tw)
+    pred = predictor.Predictor(net, constants.COCO_N_KEYPOINTS, constants.COCO_PERSON_SKELETON)
+    res_f = pred.batch(normalised.contiguous().pin_memory())
+    res_u = pred.batch(raw.pin_memory())
+    for (af, idf), (au, idu) in zip(res_f, res_u):
+        assert torch.equal(af, au) and torch.equal(idf, idu)
+    with pytest.raises(RuntimeError):
+        net.forward_uint8(raw[:, :10].cuda())

@@ -2,6 +2,6 @@
 # last check of the tree as committed: whole GPU suite + smoke
 set +e
 mkdir -p gpurun_out
-timeout -k 5 500 python -m pytest tests -m gpu -q -x --durations=5 > gpurun_out/pytest_gpu_final.log 2>&1; echo "rc=$?"
-tail -12 gpurun_out/pytest_gpu_final.log
+timeout -k 5 500 python -m pytest tests -m gpu -q --durations=5 > gpurun_out/pytest_gpu_final.log 2>&1; echo "rc=$?"
+tail -14 gpurun_out/pytest_gpu_final.log
 timeout -k 5 150 python __graft_entry__.py smoke > gpurun_out/smoke_final.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/smoke_final.log
