@@ -954,6 +954,12 @@ __global__ void __launch_bounds__(256) k_input_conv(InConvArgs a) {
     const int n_w = TAPS * C;
     for (int i = threadIdx.x; i < n_w; i += blockDim.x) s_w[i] = a.weight[i];
     for (int i = threadIdx.x; i < C; i += blockDim.x) s_w[n_w + i] = a.bias[i];
+    // raw images: the 256 possible values of a channel, normalised once per CTA with IEEE division / subtraction
+    // (bit-identical to torchvision's ToTensor + Normalize on the host) -> one byte load + one table read per sample
+    float* s_lut = s_w + n_w + C;                     // [3][256]
+    if (U8)
+        for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x)
+            s_lut[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)(i & 255), 255.f), a.mean[i >> 8]), a.stdev[i >> 8]);
     __syncthreads();
     const long long total = (long long)a.B * a.Hout * a.Wout;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -976,8 +982,7 @@ __global__ void __launch_bounds__(256) k_input_conv(InConvArgs a) {
                     float v = 0.f;
                     if (ok) {
                         if (U8) {
-                            const float u = (float)__ldg(a.in_u8 + (((size_t)b * a.Hin + iy) * a.Win + ix) * 3 + ci);
-                            v = __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.f), a.mean[ci]), a.stdev[ci]);
+                            v = s_lut[ci * 256 + __ldg(a.in_u8 + (((size_t)b * a.Hin + iy) * a.Win + ix) * 3 + ci)];
                         } else {
                             v = __ldg(plane + (size_t)iy * a.Win + ix);
                         }
@@ -1649,7 +1654,7 @@ static int net_forward_impl(pifpaf_net_t* net, const float* images_dev, int32_t 
             a.in = images_dev; a.B = batch;
             const long long total = (long long)batch * a.Hout * a.Wout;
             const int grid = (int)std::min<long long>((total + 255) / 256, (long long)net->n_sm * 16);
-            const size_t smem = sizeof(float) * ((size_t)3 * a.kernel * a.kernel * a.C8 * 8 + a.C8 * 8);
+            const size_t smem = sizeof(float) * ((size_t)3 * a.kernel * a.kernel * a.C8 * 8 + a.C8 * 8 + 3 * 256);
             if (u8 != nullptr) {
                 a.in_u8 = u8->images;
                 for (int c = 0; c < 3; c++) { a.mean[c] = u8->mean[c]; a.stdev[c] = u8->stdev[c]; }
