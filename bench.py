@@ -310,10 +310,31 @@ def cpu_step(shell, decode, images):
     return n
 
 
-def cpu_baseline(args, sample_images=4):
+def pick_cpu_threads(shell):
+    """The CPU arm gets the thread count that serves it best: PyTorch-CPU convolutions at batch 4 need not scale
+    to every core of a many-core host (round 1: 0.15 images/s with all 128 threads of the GPU box, 0.66 with the 8
+    threads of the build container), so a short probe (one 321x321 image per candidate) picks among all cores,
+    1/2, 1/4 and 1/8 of them."""
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    candidates = sorted({max(1, cores // d) for d in (1, 2, 4, 8)}, reverse=True)
+    probe = torch.randn((1, 3, 321, 321), generator=torch.Generator().manual_seed(7))
+    best, best_dt = cores, None
+    for n in candidates:
+        torch.set_num_threads(n)
+        with torch.no_grad():
+            shell(probe)
+            t0 = time.perf_counter()
+            shell(probe)
+            dt = time.perf_counter() - t0
+        if best_dt is None or dt < best_dt:
+            best, best_dt = n, dt
+    torch.set_num_threads(best)
+    return best, candidates
+
+
+def cpu_baseline(args, sample_images=4):
     shell, decode, dec_kind = cpu_path_setup()
+    cores, _ = pick_cpu_threads(shell)
     images = torch.randn((sample_images, 3, SIZE, SIZE), generator=torch.Generator().manual_seed(1234))
     cpu_step(shell, decode, images[:1])                      # warm-up
     t0 = time.perf_counter()
@@ -322,16 +343,16 @@ def cpu_baseline(args, sample_images=4):
     return {'value': round(sample_images / dt, 3), 'unit': 'images/s', 'cores': cores,
             'kind': 'port' if dec_kind == 'port' else 'reference',
             'sample': f'{sample_images} images 641x641: PyTorch-CPU fp32 forward of the same architecture '
-                      f'(port of the reference modules, {cores} threads) + {dec_kind} C++ CifCaf decoder, single pass'}
+                      f'(port of the reference modules, {cores} threads = the fastest of all / half / quarter / eighth of '
+                      f'the {os.cpu_count()} host cores) + {dec_kind} C++ CifCaf decoder, single pass'}
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     shell, decode, dec_kind = cpu_path_setup()
+    cores, _ = pick_cpu_threads(shell)
     sample = args.cpu_sample
     images = torch.randn((sample, 3, SIZE, SIZE), generator=torch.Generator().manual_seed(1234))
     for _ in range(min(args.warmup, 1)):
@@ -343,7 +364,8 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = sample * steps / dt
     desc = (f'{sample} images per step, {steps} steps: PyTorch-CPU fp32 forward (port of the reference modules, '
-            f'{cores} threads) + {dec_kind} C++ CifCaf decoder (serial per image, decoder/decoder.py:33-34)')
+            f'{cores} threads = the fastest of all / half / quarter / eighth of the {os.cpu_count()} host cores) + '
+            f'{dec_kind} C++ CifCaf decoder (serial per image, decoder/decoder.py:33-34)')
     out = {
         'metric': METRIC, 'value': round(value, 3), 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': steps,
         'warmup': min(args.warmup, 1), 'ms_per_step': round(dt / steps * 1e3, 2), 'higher_is_better': True,
