@@ -11,7 +11,8 @@ path (paths relative to /root/reference/src/openpifpaf/):
   model_defaults (BN eps >= 1e-3)     network/nets.py:63-78
 
 Attribute names and state_dict keys equal the reference's, so a reference
-`Shell` state_dict loads here unchanged; tests/test_oracle_vs_ref.py checks the
+`Shell` state_dict loads here unchanged; tests/test_network_lowering.py
+(test_oracle_net_equals_reference_modules, test_oracle_resnet_equals_reference_module) checks the
 two produce identical fields when /root/reference is importable (parity pinned
 against the Python reference imported in the build container).  It is the fp32
 numerics reference for the CUDA kernels and the "port" CPU baseline of bench.py.
