@@ -9,7 +9,7 @@
  *
  * Parity status: PINNED.  This restatement is checked bit-for-bit against the
  * unmodified reference C++ compiled from /root/reference into oracle/_ref/
- * (oracle/build_ref.py) by tests/test_oracle_vs_ref.py, and against the golden
+ * (oracle/build_ref.py) by tests/test_oracle.py, and against the golden
  * vectors under tests/golden/ that oracle/make_golden.py dumped from that
  * reference build.  (The reference's own tests hold no numeric KAT for the
  * decoder)
