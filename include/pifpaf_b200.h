@@ -148,6 +148,11 @@ int pifpaf_decoder_tap_seeds(pifpaf_decoder_t* dec, int32_t b, int64_t* out_f, f
 int pifpaf_decoder_tap_caf(pifpaf_decoder_t* dec, int32_t b, float* out_fwd, int64_t* n_fwd,
                            float* out_bwd, int64_t* n_bwd);
 
+/* Work counters of the last decode, summed over its batch (synchronises; bench.py's decoder roofline):
+ * stats[0] hi-res CifHr pixels written (the map is tile-sparse), [1] seeds (CifSeeds.get), [2] CAF list entries
+ * (forward + backward, CafScored.get; of the force-complete refill if that ran), [3] annotations before NMS. */
+int pifpaf_decoder_last_stats(pifpaf_decoder_t* dec, int64_t* stats, int32_t n_stats);
+
 /* Free op grow_connection_blend (csrc/src/cifcaf.cpp:32-113, module.cpp:60):
  * caf [n][7] f32 HOST; writes x,y,s,v to out_xysv[4]. */
 int pifpaf_grow_connection_blend(const float* caf, int64_t n, double x, double y, double s,
@@ -227,6 +232,15 @@ int pifpaf_net_heads(pifpaf_net_t* net, int32_t in_tensor, int32_t k_cols, int32
                      const float* weight, const float* bias);
 int pifpaf_net_head_output(pifpaf_net_t* net, int32_t head, float** dev_ptr,
                            int32_t* n_fields, int32_t* n_comp, int32_t* h, int32_t* w);
+
+/* Head-output buffering.  n_buffers == 2: successive forwards alternate between two sets of head-output buffers, so
+ * that the decode of forward i (reading set i & 1 on another stream) may overlap forward i+1;
+ * pifpaf_net_head_output then reports the set the LAST forward wrote.  The reference has no counterpart: its fields are
+ * fresh tensors per call (network/heads.py:330-378) copied to the host before decoding (decoder/decoder.py:98). */
+int pifpaf_net_set_head_buffers(pifpaf_net_t* net, int32_t n_buffers);
+/* Cap the persistent grids of the forward kernels at n_sm SMs (0 = all): leaves SMs free for a decode that runs
+ * concurrently on another stream (one CTA per image, decoder.cu k_grow). */
+int pifpaf_net_set_sm_limit(pifpaf_net_t* net, int32_t n_sm);
 
 /* Shell.forward (network/nets.py:35-48) on images_dev [batch][3][in_h][in_w] f32 (device), async on stream.
  * gemm_impl: 0 = tcgen05 tensor-core kernels (the product); 1 = plain SIMT debug kernel used only

@@ -52,6 +52,7 @@ SYMBOLS = {
     'pifpaf_decoder_tap_cifhr': (ctypes.c_int, [VP, c_i32, VP, c_i64]),
     'pifpaf_decoder_tap_seeds': (ctypes.c_int, [VP, c_i32, VP, VP, c_i64, P(c_i64)]),
     'pifpaf_decoder_tap_caf': (ctypes.c_int, [VP, c_i32, VP, VP, VP, VP]),
+    'pifpaf_decoder_last_stats': (ctypes.c_int, [VP, VP, c_i32]),
     'pifpaf_net_create': (ctypes.c_int, [P(VP), c_i32, c_i32]),
     'pifpaf_net_destroy': (None, [VP]),
     'pifpaf_net_tensor': (ctypes.c_int, [VP, c_i32, c_i32, c_i32, P(c_i32)]),
@@ -63,6 +64,8 @@ SYMBOLS = {
     'pifpaf_net_dwconv': (ctypes.c_int, [VP, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, VP, VP, c_i32, c_i32, c_i32]),
     'pifpaf_net_heads': (ctypes.c_int, [VP, c_i32, c_i32, c_i32, VP, VP, VP, VP, VP]),
     'pifpaf_net_head_output': (ctypes.c_int, [VP, c_i32, P(VP), P(c_i32), P(c_i32), P(c_i32), P(c_i32)]),
+    'pifpaf_net_set_head_buffers': (ctypes.c_int, [VP, c_i32]),
+    'pifpaf_net_set_sm_limit': (ctypes.c_int, [VP, c_i32]),
     'pifpaf_net_forward': (ctypes.c_int, [VP, VP, c_i32, c_i32, VP]),
     'pifpaf_net_forward_u8': (ctypes.c_int, [VP, VP, c_i32, VP, VP, c_i32, VP]),
     'pifpaf_net_forward_timed': (ctypes.c_int, [VP, VP, c_i32, c_i32, VP, VP, VP, VP, VP]),

@@ -1377,6 +1377,9 @@ int pifpaf_decoder_create(pifpaf_decoder_t** out, int32_t device, int32_t n_keyp
     TRY_D(cudaFuncSetAttribute(k_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ns));
     const size_t ss = sizeof(int) * (((size_t)F + 1 + 3) / 4 * 4 + 256 + 256 + 8) + 2 * 32 * 256 + 16;
     TRY_D(cudaFuncSetAttribute(k_seed_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss));
+    // the memsets / table uploads above ran on the legacy default stream; decodes are enqueued on caller streams
+    // (possibly non-blocking ones) that do not order themselves behind it
+    TRY_D(cudaDeviceSynchronize());
 #undef ALLOC
 #undef TRY_D
     *out = dec;
@@ -1651,6 +1654,27 @@ int pifpaf_decoder_tap_caf(pifpaf_decoder_t* dec, int32_t b, float* out_fwd, int
             (dir == 0 ? n_fwd : n_bwd)[c] = n;
         }
     }
+    return PIFPAF_OK;
+}
+
+int pifpaf_decoder_last_stats(pifpaf_decoder_t* dec, int64_t* stats, int32_t n_stats) {
+    PIFPAF_CHECK_ARG(dec != nullptr && dec->has_last, "no decode to report on");
+    PIFPAF_CHECK_ARG(stats != nullptr && n_stats >= 4, "stats must hold at least 4 values");
+    const Dims& d = dec->last;
+    PIFPAF_CUDA_TRY(cudaSetDevice(dec->device));
+    PIFPAF_CUDA_TRY(cudaDeviceSynchronize());
+    int tiles = 0;
+    PIFPAF_CUDA_TRY(cudaMemcpy(&tiles, dec->d_work_count, sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<int> seeds(d.B), anns(d.B), lists((size_t)d.B * d.C * 2 + 1);
+    PIFPAF_CUDA_TRY(cudaMemcpy(seeds.data(), dec->d_n_seeds, sizeof(int) * d.B, cudaMemcpyDeviceToHost));
+    PIFPAF_CUDA_TRY(cudaMemcpy(anns.data(), dec->d_n_anns, sizeof(int) * d.B, cudaMemcpyDeviceToHost));
+    if (d.C > 0)
+        PIFPAF_CUDA_TRY(cudaMemcpy(lists.data(), dec->d_list_counts, sizeof(int) * (size_t)d.B * d.C * 2, cudaMemcpyDeviceToHost));
+    long long ns = 0, na = 0, nl = 0;
+    for (int b = 0; b < d.B; b++) { ns += seeds[b]; na += anns[b]; }
+    for (size_t i = 0; i < (size_t)d.B * d.C * 2; i++) nl += lists[i];
+    stats[0] = (int64_t)tiles * TILE * TILE;   // hi-res CifHr pixels written (sparse map)
+    stats[1] = ns; stats[2] = nl; stats[3] = na;
     return PIFPAF_OK;
 }
 

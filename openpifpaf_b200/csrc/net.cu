@@ -1154,6 +1154,7 @@ struct Op {
     double flops_per_image = 0;
     double bytes_per_image = 0;      // algorithmic activation bytes (inputs once + outputs once)
     double weight_bytes = 0;
+    int n_real = 0;                  // output channels that are not padding (emit_gemm)
 };
 
 }  // namespace
@@ -1165,7 +1166,13 @@ struct pifpaf_net {
     std::vector<void*> owned;            // device allocations (weights, biases, tables)
     // heads
     int n_heads = 0;
-    float* head_out[4] = {nullptr, nullptr, nullptr, nullptr};
+    // head outputs, optionally double buffered: forward i writes head_out[i & 1] so that a decode of forward i-1
+    // (another stream) may still read the other set (pifpaf_net_set_head_buffers)
+    float* head_out[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+    int head_buffers = 1, head_cur = 0;
+    size_t head_elems[4] = {0, 0, 0, 0};
+    bool setup_synced = false;           // build-time memsets / uploads (legacy stream) ordered before the first forward
+    int sm_limit = 0;                    // > 0: persistent grids use at most this many SMs
     int head_fields[4] = {0, 0, 0, 0}, head_comp[4] = {0, 0, 0, 0}, head_h = 0, head_w = 0;
     int in_h = 0, in_w = 0;
 };
@@ -1180,6 +1187,7 @@ int net_alloc(pifpaf_net* net, T** p, size_t n, bool zero) {
         return e == cudaErrorMemoryAllocation ? PIFPAF_E_NOMEM : PIFPAF_E_CUDA;
     }
     net->owned.push_back(*p);
+    net->setup_synced = false;
     if (zero) {
         e = cudaMemset(*p, 0, sizeof(T) * (n ? n : 1));
         if (e != cudaSuccess) { pifpaf::set_error("cudaMemset failed: %s", cudaGetErrorString(e)); return PIFPAF_E_CUDA; }
@@ -1280,9 +1288,24 @@ int emit_gemm(pifpaf_net* net, Op& op, int in_tensor, int in_col_off, int k_cols
     g.a = tin.data + in_col_off; g.lda = tin.c; g.wgt = d_w; g.ldw = k_pad;
     op.a_tensor = in_tensor; op.rows_per_image = tin.h * tin.w;
     op.smem = gemm_smem_bytes(block_n, n_blocks, g.stages, false);
-    op.flops_per_image = 2.0 * (double)op.rows_per_image * n_out * k_cols;
-    op.bytes_per_image = (double)op.rows_per_image * k_cols * 2.0;      // A read once (bf16); outputs added by the caller
-    op.weight_bytes = (double)n_out * k_cols * 2.0;
+    // ALGORITHMIC work: padding columns / rows (zero weights: view lead-ins of the 'shuffle' layout, 16-channel
+    // padding of the 'bins' pieces) are not counted -- nnz MACs, the input channels some weight reads, the output
+    // channels some weight or bias produces
+    long long nnz = 0; int k_real = 0, n_real = 0;
+    {
+        std::vector<char> k_used(k_cols, 0);
+        for (int n = 0; n < n_out; n++) {
+            bool row = bias != nullptr && bias[n] != 0.f;
+            for (int k = 0; k < k_cols; k++)
+                if (weight[(size_t)n * k_cols + k] != 0.f) { nnz++; k_used[k] = 1; row = true; }
+            n_real += row ? 1 : 0;
+        }
+        for (int k = 0; k < k_cols; k++) k_real += k_used[k];
+    }
+    op.n_real = n_real;
+    op.flops_per_image = 2.0 * (double)op.rows_per_image * (double)nnz;
+    op.bytes_per_image = (double)op.rows_per_image * k_real * 2.0;      // A read once (bf16); outputs added by the caller
+    op.weight_bytes = (double)nnz * 2.0;
     // the map covers the whole tensor; the view's first column is a TMA coordinate (16-byte aligned).
     // Columns past the view multiply zero weight rows (B is zero padded), columns past the tensor are zero filled.
     rc = make_tmap(&op.tmap_a, tin.data, rows_max, (uint64_t)tin.c, (uint64_t)tin.c, BM);
@@ -1393,7 +1416,7 @@ int pifpaf_net_conv1x1(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off,
     GemmArgs& g = op.g;
     g.relu = relu; g.out = to.data; g.ldo = to.c; g.out_col_off = out_col_off;
     // outputs: n_out bf16 per row; the fused shuffle also reads and re-writes the pass-through half
-    op.bytes_per_image += (double)op.rows_per_image * n_out * 2.0 * (shuffle_src_tensor >= 0 ? 3.0 : 1.0);
+    op.bytes_per_image += (double)op.rows_per_image * op.n_real * 2.0 * (shuffle_src_tensor >= 0 ? 3.0 : 1.0);
     PIFPAF_CHECK_ARG(out_col_off % 16 == 0, "output column offset must be a multiple of 16");
     if (shuffle_src_tensor < 0) {
         g.mode = MODE_PLAIN;
@@ -1456,7 +1479,7 @@ int pifpaf_net_conv1x1_scatter(pifpaf_net_t* net, int32_t in_tensor, int32_t in_
     rc = net_upload(net, &d_groups, groups);
     if (rc != PIFPAF_OK) return rc;
     g.dest = d_groups;
-    op.bytes_per_image += (double)op.rows_per_image * n_out * 2.0;
+    op.bytes_per_image += (double)op.rows_per_image * op.n_real * 2.0;
     plan_gemm_smem(g, &op.smem, false);
     net->ops.push_back(op);
     return PIFPAF_OK;
@@ -1485,7 +1508,7 @@ int pifpaf_net_conv(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off, in
         if (rc != PIFPAF_OK) return rc;
         GemmArgs& g = op.g;
         g.mode = MODE_PLAIN; g.relu = relu; g.out = to.data; g.ldo = to.c; g.out_col_off = out_col_off;
-        op.bytes_per_image += (double)op.rows_per_image * n_out * 2.0 * (residual_tensor >= 0 ? 2.0 : 1.0);
+        op.bytes_per_image += (double)op.rows_per_image * op.n_real * 2.0 * (residual_tensor >= 0 ? 2.0 : 1.0);
         if (residual_tensor >= 0) {
             PIFPAF_CHECK_ARG(residual_tensor < nt, "bad residual tensor");
             const Tensor& tr = net->tensors[residual_tensor];
@@ -1604,7 +1627,7 @@ int pifpaf_net_heads(pifpaf_net_t* net, int32_t in_tensor, int32_t k_cols, int32
     if (rc != PIFPAF_OK) return rc;
     GemmArgs& g = op.g;
     g.mode = MODE_HEADS; g.relu = 0;
-    op.bytes_per_image += (double)op.rows_per_image * n_total * 4.0;
+    op.bytes_per_image += (double)op.rows_per_image * op.n_real * 4.0;
     std::vector<HeadCol> cols((size_t)g.block_n * g.n_blocks, HeadCol{0, 0, 0, 0});
     int col = 0, op_off = 0;
     for (int i = 0; i < n_heads; i++) {
@@ -1612,9 +1635,10 @@ int pifpaf_net_heads(pifpaf_net_t* net, int32_t in_tensor, int32_t k_cols, int32
             for (int c = 0; c < n_comp[i]; c++) cols[col++] = HeadCol{i, f * n_comp[i] + c, comp_ops[op_off + c], 0};
         op_off += n_comp[i];
         net->head_fields[i] = n_fields[i]; net->head_comp[i] = n_comp[i];
-        rc = net_alloc(net, &net->head_out[i], (size_t)net->max_batch * n_fields[i] * n_comp[i] * tin.h * tin.w, true);
+        net->head_elems[i] = (size_t)net->max_batch * n_fields[i] * n_comp[i] * tin.h * tin.w;
+        rc = net_alloc(net, &net->head_out[0][i], net->head_elems[i], true);
         if (rc != PIFPAF_OK) return rc;
-        g.head_base[i] = net->head_out[i];
+        g.head_base[i] = net->head_out[0][i];
         g.head_planes[i] = n_fields[i] * n_comp[i];
     }
     HeadCol* d_cols = nullptr;
@@ -1629,7 +1653,7 @@ int pifpaf_net_heads(pifpaf_net_t* net, int32_t in_tensor, int32_t k_cols, int32
 int pifpaf_net_head_output(pifpaf_net_t* net, int32_t head, float** dev_ptr,
                            int32_t* n_fields, int32_t* n_comp, int32_t* h, int32_t* w) {
     PIFPAF_CHECK_ARG(net != nullptr && head >= 0 && head < net->n_heads, "bad head index");
-    if (dev_ptr) *dev_ptr = net->head_out[head];
+    if (dev_ptr) *dev_ptr = net->head_out[net->head_cur][head];     // the set the last forward wrote
     if (n_fields) *n_fields = net->head_fields[head];
     if (n_comp) *n_comp = net->head_comp[head];
     if (h) *h = net->head_h;
@@ -1645,6 +1669,14 @@ static int net_forward_impl(pifpaf_net_t* net, const float* images_dev, int32_t 
     PIFPAF_CHECK_ARG(images_dev != nullptr || u8 != nullptr || net->in_h == 0, "images pointer is null");
     PIFPAF_CHECK_ARG(batch >= 1 && batch <= net->max_batch, "batch exceeds max_batch");
     PIFPAF_CUDA_TRY(cudaSetDevice(net->device));
+    if (!net->setup_synced) {
+        // tensors were zero-filled and weights uploaded on the legacy default stream at emit time; `st` may be a
+        // non-blocking stream that does not order itself behind it
+        PIFPAF_CUDA_TRY(cudaDeviceSynchronize());
+        net->setup_synced = true;
+    }
+    if (net->head_buffers == 2) net->head_cur ^= 1;
+    const int n_sm = net->sm_limit > 0 ? std::min(net->sm_limit, net->n_sm) : net->n_sm;
     int op_index = 0;
     for (Op& op : net->ops) {
         if (events) PIFPAF_CUDA_TRY(cudaEventRecord(events[op_index], st));
@@ -1653,7 +1685,7 @@ static int net_forward_impl(pifpaf_net_t* net, const float* images_dev, int32_t 
             InConvArgs a = op.ic;
             a.in = images_dev; a.B = batch;
             const long long total = (long long)batch * a.Hout * a.Wout;
-            const int grid = (int)std::min<long long>((total + 255) / 256, (long long)net->n_sm * 16);
+            const int grid = (int)std::min<long long>((total + 255) / 256, (long long)n_sm * 16);
             const size_t smem = sizeof(float) * ((size_t)3 * a.kernel * a.kernel * a.C8 * 8 + a.C8 * 8 + 3 * 256);
             if (u8 != nullptr) {
                 a.in_u8 = u8->images;
@@ -1676,38 +1708,40 @@ static int net_forward_impl(pifpaf_net_t* net, const float* images_dev, int32_t 
                 if (a.stride == 1) {
                     const long long total = (long long)batch * ((a.Hout + DW1_TH - 1) / DW1_TH) *
                                             ((a.Wout + DW1_TW - 1) / DW1_TW) * cblks;
-                    const int grid = (int)std::min<long long>(total, (long long)net->n_sm * 2);
+                    const int grid = (int)std::min<long long>(total, (long long)n_sm * 2);
                     k_dwconv5_tma<1, DW1_TH, DW1_TW, 4, 3><<<grid, DwS1::THREADS, DwS1::SMEM, st>>>(op.tmap_dw, a);
                 } else {
                     const long long total = (long long)batch * ((a.Hout + DW2_TH - 1) / DW2_TH) *
                                             ((a.Wout + DW2_TW - 1) / DW2_TW) * cblks;
-                    const int grid = (int)std::min<long long>(total, (long long)net->n_sm);
+                    const int grid = (int)std::min<long long>(total, (long long)n_sm);
                     k_dwconv5_tma<2, DW2_TH, DW2_TW, 4, 2><<<grid, DwS2::THREADS, DwS2::SMEM, st>>>(op.tmap_dw, a);
                 }
             } else if (a.kernel == 5 && (a.stride == 1 || a.stride == 2)) {
                 const long long total = (long long)batch * ((a.Hout + DW_OY - 1) / DW_OY) * DW_OY *
                                         ((a.Wout + DW_OX - 1) / DW_OX) * a.C8;
-                const int grid = (int)std::min<long long>((total + 255) / 256, (long long)net->n_sm * 64);
+                const int grid = (int)std::min<long long>((total + 255) / 256, (long long)n_sm * 64);
                 if (a.stride == 1) k_dwconv5<1><<<grid, 256, 0, st>>>(a);
                 else k_dwconv5<2><<<grid, 256, 0, st>>>(a);
             } else {
                 const long long total = (long long)batch * a.Hout * a.Wout * a.C8;
-                const int grid = (int)std::min<long long>((total + 255) / 256, (long long)net->n_sm * 32);
+                const int grid = (int)std::min<long long>((total + 255) / 256, (long long)n_sm * 32);
                 k_dwconv<<<grid, 256, 0, st>>>(a);
             }
             PIFPAF_LAUNCH_CHECK();
         } else {
             GemmArgs g = op.g;
+            if (g.mode == MODE_HEADS)
+                for (int i = 0; i < net->n_heads; i++) g.head_base[i] = net->head_out[net->head_cur][i];
             g.M = batch * op.rows_per_image;
             g.m_blocks = g.conv_k > 0 ? batch * op.tiles_per_image : (g.M + BM - 1) / BM;
             if (gemm_impl == 1) {
                 const long long jobs = (long long)g.m_blocks * 4 * (g.n_blocks * g.block_n / CHUNK);
-                const int grid = (int)std::min<long long>((jobs + 3) / 4, (long long)net->n_sm * 16);
+                const int grid = (int)std::min<long long>((jobs + 3) / 4, (long long)n_sm * 16);
                 k_gemm_simt<<<grid, 128, 0, st>>>(g);
             } else {
                 const int tiles = g.m_blocks * g.n_blocks;
-                int grid = std::min(tiles, net->n_sm);
-                if (g.b_resident) grid = std::max(1, std::min(net->n_sm / g.n_blocks, g.m_blocks)) * g.n_blocks;
+                int grid = std::min(tiles, n_sm);
+                if (g.b_resident) grid = std::max(1, std::min(n_sm / g.n_blocks, g.m_blocks)) * g.n_blocks;
                 k_gemm_tc<<<grid, GEMM_THREADS, op.smem, st>>>(op.tmap_a, op.tmap_b,
                                                                 g.src_tma ? op.tmap_src : op.tmap_a, g);
             }
@@ -1791,6 +1825,29 @@ int pifpaf_net_set_tensor(pifpaf_net_t* net, int32_t id, int32_t batch, const fl
     }
     cudaFree(d_tmp);
     if (e != cudaSuccess) { pifpaf::set_error("set_tensor failed: %s", cudaGetErrorString(e)); return PIFPAF_E_CUDA; }
+    return PIFPAF_OK;
+}
+
+int pifpaf_net_set_head_buffers(pifpaf_net_t* net, int32_t n_buffers) {
+    PIFPAF_CHECK_ARG(net != nullptr && (n_buffers == 1 || n_buffers == 2), "n_buffers must be 1 or 2");
+    PIFPAF_CUDA_TRY(cudaSetDevice(net->device));
+    if (n_buffers == 2) {
+        for (int i = 0; i < net->n_heads; i++) {
+            if (net->head_out[1][i] != nullptr) continue;
+            int rc = net_alloc(net, &net->head_out[1][i], net->head_elems[i], true);
+            if (rc != PIFPAF_OK) return rc;
+        }
+        net->setup_synced = false;
+    } else {
+        net->head_cur = 0;
+    }
+    net->head_buffers = n_buffers;
+    return PIFPAF_OK;
+}
+
+int pifpaf_net_set_sm_limit(pifpaf_net_t* net, int32_t n_sm) {
+    PIFPAF_CHECK_ARG(net != nullptr && n_sm >= 0, "bad argument");
+    net->sm_limit = n_sm;
     return PIFPAF_OK;
 }
 

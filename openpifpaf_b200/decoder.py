@@ -81,7 +81,8 @@ class CifCaf(metaclass=_Statics):
         'keypoint_threshold': 0.15, 'keypoint_threshold_rel': 0.5,
         'reverse_match': True, 'force_complete': False, 'force_complete_caf_th': 0.001,
     }
-    #: per-image capacity for annotations before NMS (the reference grows a std::vector)
+    #: per-image capacity for annotations before NMS.  The reference grows a std::vector; here an image that needs
+    #: more raises RuntimeError (PIFPAF_E_OVERFLOW) from fetch -- raise this attribute before the first decode then.
     max_annotations = 512
 
     def __init__(self, n_keypoints, skeleton, *, device=0, n_cif_fields=None):
@@ -117,11 +118,20 @@ class CifCaf(metaclass=_Statics):
                 pass
 
     # --- native handle with capacities that only ever grow
+    def reserve(self, batch, h, w, stride):
+        """Size the native workspace up front (e.g. from a compiled net's max batch and head shape) so that it is
+        never re-created while results are in flight."""
+        self._ensure(int(batch), int(h), int(w), int(stride))
+
     def _ensure(self, batch, h, w, stride):
         caps = self._caps
         need = (batch, h, w, stride, self.max_annotations)
         if caps is not None and all(c >= n for c, n in zip(caps, need)):
             return self._handle
+        if getattr(self, '_begun', None):
+            # re-creating the handle would free the pinned result buffers and events of fetches in flight
+            raise RuntimeError('decoder capacity exceeded while results are pending: fetch_end() them first, or '
+                               'reserve() the largest batch / field shape before pipelining')
         if caps is not None:
             need = tuple(max(c, n) for c, n in zip(caps, need))
         self._free()
@@ -271,6 +281,14 @@ class CifCaf(metaclass=_Statics):
             self._handle, counts.ctypes.data, ann.ctypes.data, ids.ctypes.data, cap))
         return [(torch.from_numpy(ann[b, :counts[b]].copy()), torch.from_numpy(ids[b, :counts[b]].copy()))
                 for b in range(B)]
+
+    def last_stats(self):
+        """Work counters of the last decode over its batch (synchronises): hi-res pixels written, seeds, CAF list
+        entries, annotations before NMS."""
+        out = (ctypes.c_int64 * 4)()
+        _lib.check(_lib.lib().pifpaf_decoder_last_stats(self._handle, out, 4))
+        return {'cifhr_pixels_written': int(out[0]), 'seeds': int(out[1]), 'caf_entries': int(out[2]),
+                'annotations_before_nms': int(out[3])}
 
     def get_cifhr(self, image=0):
         """csrc/src/module.cpp:36-38: (accumulated [F,H,W] float32, revision)."""

@@ -119,6 +119,14 @@ def plan_from_shell(shell):
     base = shell.base_net
     if shell.training:
         raise RuntimeError('the Shell must be in eval() mode (BatchNorm is folded)')
+    # network/nets.py:12-13,36-46: optional pre/post-processing hooks -- not lowered, so refuse them loudly
+    if getattr(shell, 'process_input', None) is not None or getattr(shell, 'process_heads', None) is not None:
+        raise RuntimeError('Shell.process_input / process_heads are not supported by the compiled forward')
+    for m in base.modules():
+        # the kernels fuse max(x, 0); --shufflenetv2k-leaky-relu etc. would be folded wrongly
+        if isinstance(m, (torch.nn.LeakyReLU, torch.nn.ELU, torch.nn.PReLU, torch.nn.SiLU, torch.nn.GELU,
+                          torch.nn.Hardswish, torch.nn.InstanceNorm2d, torch.nn.GroupNorm)):
+            raise RuntimeError(f'unsupported module in the base network: {type(m).__name__} (only ReLU + BatchNorm)')
     if all(hasattr(base, a) for a in ('input_block', 'block2', 'block3', 'block4', 'block5')):
         return _plan_from_resnet(shell)
     if not all(hasattr(base, a) for a in ('input_block', 'stage2', 'stage3', 'stage4', 'conv5')):
@@ -152,6 +160,13 @@ def plan_from_shell(shell):
     plan['conv5'] = _fold(base.conv5[0], base.conv5[1])
     plan['heads'] = _heads_plan(shell, base)
     return plan
+
+
+def heads_only_plan(plan, c_in=None):
+    """The heads of `plan` as a net of their own (one GEMM with the CompositeField4 eval epilogue); compile it with
+    the FEATURE map size as in_h, in_w and run it with CompiledNet.forward_features."""
+    c = int(plan['heads'][0]['w'].shape[1]) if c_in is None else int(c_in)
+    return {'kind': 'heads_only', 'c_in': c, 'heads': plan['heads']}
 
 
 def random_plan(base_name='shufflenetv2k16', heads=((17, 1, 1, 1), (19, 1, 2, 2)), seed=0, confidence_bias=-4.0):
@@ -191,6 +206,51 @@ def random_plan(base_name='shufflenetv2k16', heads=((17, 1, 1, 1), (19, 1, 2, 2)
     for (nf, nconf, nvec, nsc) in heads:
         ncomp = 1 + nconf + 2 * nvec + nsc
         w = (rng.standard_normal((nf * ncomp, ch[4])) * np.sqrt(1.0 / ch[4])).astype(np.float32)
+        b = (rng.standard_normal(nf * ncomp) * 0.1).astype(np.float32)
+        b.reshape(nf, ncomp)[:, 1:1 + nconf] += np.float32(confidence_bias)
+        plan['heads'].append({'w': w, 'b': b, 'n_fields': nf, 'n_comp': ncomp,
+                              'ops': head_ops(nconf, nvec, nsc, (True,) * nvec), 'stride': 16})
+    return plan
+
+
+RESNET_CONFIGS = {      # torchvision.models.resnet: (block, layers); network/factory.py:57-58
+    'resnet18': ('basic', [2, 2, 2, 2]),
+    'resnet50': ('bottleneck', [3, 4, 6, 3]),
+}
+
+
+def random_resnet_plan(base_name='resnet50', heads=((17, 1, 1, 1), (19, 1, 2, 2)), seed=0, confidence_bias=-4.0):
+    """Random-init folded plan of the reference's Resnet base network (basenetworks.py:71-150: torchvision ResNet,
+    max-pool removed, stride 16; BasicBlock 3x3-3x3 / Bottleneck 1x1-3x3(stride)-1x1 with expansion 4, 1x1
+    downsample on the first block of a stage) -- the same dict layout `_plan_from_resnet` extracts from a Shell.
+    The last conv of a block and the downsample conv get half the He variance so that the residual sum keeps the
+    activation scale over 16 blocks."""
+    kind, layers = RESNET_CONFIGS[base_name]
+    rng = np.random.Generator(np.random.PCG64(seed))
+
+    def conv(cout, cin, k, stride, gain=2.0):
+        w = rng.standard_normal((cout, cin, k, k)).astype(np.float32) * np.float32(np.sqrt(gain / (cin * k * k)))
+        b = (rng.standard_normal(cout) * 0.05).astype(np.float32)
+        return {'w': w, 'b': b, 'kernel': k, 'stride': stride, 'pad': (k - 1) // 2}
+
+    stem = conv(64, 3, 7, 2)
+    plan = {'kind': 'resnet', 'input': {'w': stem['w'], 'b': stem['b'], 'stride': 2, 'pad': 3}, 'blocks': [], 'heads': []}
+    expansion = 1 if kind == 'basic' else 4
+    cin = 64
+    for si, (planes, n) in enumerate(zip((64, 128, 256, 512), layers)):
+        for bi in range(n):
+            stride = 2 if (bi == 0 and si > 0) else 1
+            cout = planes * expansion
+            if kind == 'basic':
+                convs = [conv(planes, cin, 3, stride), conv(planes, planes, 3, 1, gain=1.0)]
+            else:
+                convs = [conv(planes, cin, 1, 1), conv(planes, planes, 3, stride), conv(cout, planes, 1, 1, gain=1.0)]
+            down = conv(cout, cin, 1, stride, gain=1.0) if (stride != 1 or cin != cout) else None
+            plan['blocks'].append({'convs': convs, 'downsample': down})
+            cin = cout
+    for (nf, nconf, nvec, nsc) in heads:
+        ncomp = 1 + nconf + 2 * nvec + nsc
+        w = (rng.standard_normal((nf * ncomp, cin)) * np.sqrt(1.0 / cin)).astype(np.float32)
         b = (rng.standard_normal(nf * ncomp) * 0.1).astype(np.float32)
         b.reshape(nf, ncomp)[:, 1:1 + nconf] += np.float32(confidence_bias)
         plan['heads'].append({'w': w, 'b': b, 'n_fields': nf, 'n_comp': ncomp,
@@ -347,6 +407,11 @@ def build_ops(plan, in_h, in_w, layout=None):
     {'input_conv', 'conv1x1', 'dwconv', 'heads'} whose fields are the C ABI arguments."""
     if plan.get('kind') == 'resnet':
         return _build_ops_resnet(plan, in_h, in_w)
+    if plan.get('kind') == 'heads_only':
+        # in_h x in_w is the FEATURE map here; the feature tensor is filled through CompiledNet.forward_features
+        c_in = int(plan['c_in'])
+        return [(in_h, in_w, pad16(c_in))], [_heads_op(plan['heads'], 0, c_in)], \
+            {'block_outputs': [], 'feature': (0, _Layout(c_in, split=False))}
     if plan.get('kind') != 'shufflenetv2k':
         raise RuntimeError('unsupported plan kind')
     layout = default_layout() if layout is None else layout
@@ -578,12 +643,25 @@ class CompiledNet:
                                'h': hh.value, 'w': ww.value, 'stride': h['stride']})
 
     def __del__(self):
+        self.close()
+
+    def close(self):
+        """Free every device buffer of the net (idempotent)."""
         h, self.handle = getattr(self, 'handle', None), None
         if h:
             try:
                 self.lib.pifpaf_net_destroy(h)
             except Exception:
                 pass
+
+    def set_head_buffers(self, n):
+        """1: head outputs are valid until the next forward (default); 2: successive forwards alternate between two
+        sets, so a decode of forward i may run concurrently with forward i+1."""
+        _lib.check(self.lib.pifpaf_net_set_head_buffers(self.handle, int(n)))
+
+    def set_sm_limit(self, n_sm):
+        """Cap the persistent grids of the forward at n_sm SMs (0: all of them)."""
+        _lib.check(self.lib.pifpaf_net_set_sm_limit(self.handle, int(n_sm)))
 
     def _emit(self, ops):
         L, H = self.lib, self.handle
@@ -639,10 +717,31 @@ class CompiledNet:
 
     def _head_views(self, b):
         outs = []
-        for hd in self.heads:
-            arr = _DevArray(hd['ptr'], (b, hd['n_fields'], hd['n_comp'], hd['h'], hd['w']))
+        for i, hd in enumerate(self.heads):
+            ptr = ctypes.c_void_p()       # the buffer set the last forward wrote (set_head_buffers)
+            _lib.check(self.lib.pifpaf_net_head_output(self.handle, i, ctypes.byref(ptr), None, None, None, None))
+            arr = _DevArray(ptr.value, (b, hd['n_fields'], hd['n_comp'], hd['h'], hd['w']))
             outs.append(torch.as_tensor(arr, device=f'cuda:{self.device}'))
         return tuple(outs)
+
+    def forward_features(self, features, *, gemm_impl=0, stream=None):
+        """CompositeField4 heads alone (heads.py:330-378) on a given feature map: features [B,h,w,C] float32
+        (host numpy or tensor; rounded to bf16 on upload) -> head outputs.  For plans of kind 'heads_only'
+        (`heads_only_plan`): parity / accuracy tests feed the heads GEMM with controlled activations."""
+        if self.op_desc[0]['kind'] != 'heads':
+            raise RuntimeError('forward_features needs a heads_only plan')
+        f = np.ascontiguousarray(features.cpu().numpy() if isinstance(features, torch.Tensor) else features,
+                                 dtype=np.float32)
+        b = int(f.shape[0])
+        h, w, c = self.tensor_shapes[0]
+        if f.shape[1:3] != (h, w) or f.shape[3] > c or b > self.max_batch:
+            raise RuntimeError(f'expected features [B<={self.max_batch},{h},{w},<={c}]')
+        padded = np.zeros((b, h, w, c), dtype=np.float32)
+        padded[..., :f.shape[3]] = f
+        _lib.check(self.lib.pifpaf_net_set_tensor(self.handle, 0, b, _ptr(padded), padded.size))
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        _lib.check(self.lib.pifpaf_net_forward(self.handle, None, b, int(gemm_impl), ctypes.c_void_p(st.cuda_stream)))
+        return self._head_views(b)
 
     # the reference's eval preprocessing constants (transforms/__init__.py:26-33)
     IMAGE_MEAN = (0.485, 0.456, 0.406)

@@ -14,8 +14,10 @@ Two levels of drop-in:
     ``register()`` makes ``Multi.batch`` (what ``Predictor`` calls, predictor.py:131) delegate to it when
     it is the selected decoder.
 """
+import collections
 import logging
 import time
+import weakref
 
 import numpy as np
 import torch
@@ -35,6 +37,8 @@ def _build_class():
     class CifCafB200(Decoder):
         """CifCaf decoding on a B200 (same CLI knobs as the reference's CifCaf)."""
         fast_batch = True
+        #: compiled (model, input shape) entries kept alive; each owns every activation buffer of its max batch
+        compile_cache_size = 2
 
         def __init__(self, cif_metas, caf_metas):
             super().__init__()
@@ -49,51 +53,49 @@ def _build_class():
             self.priority += 1.0
             self.priority += sum(m.n_fields for m in cif_metas) / 1000.0
             self.priority += sum(m.n_fields for m in caf_metas) / 1000.0
-            self._compiled = {}
+            self._compiled = collections.OrderedDict()
 
         @classmethod
         def cli(cls, parser):
             group = parser.add_argument_group('CifCafB200 decoder')
             group.add_argument('--b200-no-fast-batch', dest='b200_fast_batch', default=True, action='store_false',
                                help='decode on the GPU but keep the reference model forward / host transfer')
+            group.add_argument('--b200-compile-cache', type=int, default=cls.compile_cache_size,
+                               help='number of (model, input shape) compilations kept on the GPU')
 
         @classmethod
         def configure(cls, args):
-            """Same argparse namespace the reference's CifCaf.configure consumes (decoder/cifcaf.py:174-211,
-            decoder/factory.py:52-82); values are snapshotted into the native statics."""
+            """Only this plugin's own flags.  Every decoding knob (thresholds, force-complete, greedy, ablations) is
+            owned by the reference: its CifCaf.configure / decoder.factory.configure (decoder/cifcaf.py:174-211,
+            decoder/factory.py:52-82) write the C++ statics of the reference extension, and `sync_statics` reads
+            them back before every decode -- one source of truth, independent of the order in which the members
+            of the DECODERS set are configured (CifCaf.configure mutates the argparse namespace)."""
             cls.fast_batch = getattr(args, 'b200_fast_batch', True)
-            C = b200_decoder.CifCaf
-            kp_th = getattr(args, 'keypoint_threshold', 0.15)
-            kp_th_rel = getattr(args, 'keypoint_threshold_rel', 0.5)
-            kp_th_nms = kp_th
-            force = getattr(args, 'force_complete_pose', False)
-            if force:
-                if not getattr(args, 'ablation_independent_kp', False):
-                    kp_th = 0.0
-                kp_th_rel = 0.0
-                kp_th_nms = 0.0
-            seed_th = getattr(args, 'seed_threshold', 0.2)
-            kp_th = min(kp_th, seed_th)
-            C.set_force_complete(force)
-            C.set_force_complete_caf_th(getattr(args, 'force_complete_caf_th', 0.001))
-            C.set_keypoint_threshold(kp_th)
-            C.set_keypoint_threshold_rel(kp_th_rel)
-            C.set_greedy(getattr(args, 'greedy', False))
-            C.set_block_joints(getattr(args, 'cifcaf_block_joints', False))
-            b200_decoder.NMSKeypoints.set_keypoint_threshold(kp_th_nms)
-            inst_th = getattr(args, 'instance_threshold', None)
-            if inst_th is None:
-                inst_th = 0.0 if force else 0.15
-            b200_decoder.NMSKeypoints.set_instance_threshold(inst_th)
-            b200_decoder.CifHr.set_threshold(getattr(args, 'cif_th', 0.3))
-            b200_decoder.CifSeeds.set_threshold(seed_th)
-            b200_decoder.CafScored.set_default_score_th(getattr(args, 'caf_th', 0.3))
-            b200_decoder.CifSeeds.set_ablation_nms(getattr(args, 'ablation_cifseeds_nms', False))
-            b200_decoder.CifSeeds.set_ablation_no_rescore(getattr(args, 'ablation_cifseeds_no_rescore', False))
-            b200_decoder.CafScored.set_ablation_no_rescore(getattr(args, 'ablation_caf_no_rescore', False))
+            cls.compile_cache_size = max(1, int(getattr(args, 'b200_compile_cache', cls.compile_cache_size)))
+
+        @classmethod
+        def sync_statics(cls):
+            """Snapshot the reference's process-global statics (csrc/src/module.cpp:26-32,76-117) into the native
+            decoder's statics; they go by value into every native call."""
+            ref = torch.classes.openpifpaf_decoder.CifCaf
+            utl = torch.classes.openpifpaf_decoder_utils
+            N = b200_decoder
+            for name in ('block_joints', 'greedy', 'keypoint_threshold', 'keypoint_threshold_rel', 'reverse_match',
+                         'force_complete', 'force_complete_caf_th'):
+                getattr(N.CifCaf, 'set_' + name)(getattr(ref, 'get_' + name)())
+            for name in ('neighbors', 'threshold', 'ablation_skip'):
+                getattr(N.CifHr, 'set_' + name)(getattr(utl.CifHr, 'get_' + name)())
+            for name in ('threshold', 'ablation_nms', 'ablation_no_rescore'):
+                getattr(N.CifSeeds, 'set_' + name)(getattr(utl.CifSeeds, 'get_' + name)())
+            for name in ('default_score_th', 'ablation_no_rescore'):
+                getattr(N.CafScored, 'set_' + name)(getattr(utl.CafScored, 'get_' + name)())
+            for name in ('suppression', 'instance_threshold', 'keypoint_threshold'):
+                getattr(N.NMSKeypoints, 'set_' + name)(getattr(utl.NMSKeypoints, 'get_' + name)())
 
         @classmethod
         def factory(cls, head_metas):
+            if openpifpaf.decoder.cifcaf.CifCafDense.dense_coupling:
+                return []     # --dense-connections asks for CifCafDense (decoder/cifcaf.py:214-216)
             return [
                 CifCafB200([meta], [meta_next])
                 for meta, meta_next in zip(head_metas[:-1], head_metas[1:])
@@ -126,6 +128,7 @@ def _build_class():
                     init_t[i, :, 2] = torch.from_numpy(ann_py.data[:, 1].astype(np.float32))
                     init_t[i, :, 3] = torch.from_numpy(np.asarray(ann_py.joint_scales, dtype=np.float32))
                     ids_t[i] = getattr(ann_py, 'id_', -1)
+            self.sync_statics()
             start = time.perf_counter()
             ann_t, ids = self.native.call_with_initial_annotations(
                 fields[self.cif_metas[0].head_index], self.cif_metas[0].stride,
@@ -133,20 +136,46 @@ def _build_class():
             LOG.debug('b200 annotations = %d (%.1fms)', len(ann_t), (time.perf_counter() - start) * 1000.0)
             return self._annotations(ann_t.numpy(), ids.numpy())
 
+        @staticmethod
+        def _weights_version(shell):
+            # torch bumps Tensor._version on every in-place write (optimizer step, load_state_dict, .copy_)
+            return sum(int(p._version) for p in shell.parameters()) + sum(int(b._version) for b in shell.buffers())
+
+        def _predictor_for(self, shell, batch, h, w, device):
+            """Compile `shell` for this input shape once; LRU of `compile_cache_size` entries.  An entry is reused only
+            for the same live module object (weak reference, so a recycled id() cannot alias), unchanged weights and a
+            batch that fits; evicted entries free their GPU buffers at once."""
+            key = (id(shell), h, w)
+            hit = self._compiled.get(key)
+            if hit is not None:
+                ref, version, pred = hit
+                if ref() is shell and version == self._weights_version(shell) and pred.net.max_batch >= batch:
+                    self._compiled.move_to_end(key)
+                    return pred
+                self._evict(key)
+            dev_index = torch.device(device).index if device is not None else None
+            if dev_index is None:
+                dev_index = torch.cuda.current_device()
+            pred = b200_predictor.from_shell(shell, h, w, max(batch, 1), device=dev_index,
+                                             cif_meta=self.cif_metas[0], caf_meta=self.caf_metas[0])
+            self._compiled[key] = (weakref.ref(shell), self._weights_version(shell), pred)
+            while len(self._compiled) > self.compile_cache_size:
+                self._evict(next(iter(self._compiled)))
+            return pred
+
+        def _evict(self, key):
+            _, _, pred = self._compiled.pop(key)
+            pred.close()
+
         def batch(self, model, image_batch, *, device=None, gt_anns_batch=None):
             """decoder/decoder.py:114-137 with everything on the GPU."""
             if not self.fast_batch or not torch.cuda.is_available():
                 return super().batch(model, image_batch, device=device, gt_anns_batch=gt_anns_batch)
+            self.sync_statics()
             start = time.perf_counter()
             shell = model.module if hasattr(model, 'module') else model     # DataParallel (predictor.py:33-37)
             b, _, h, w = image_batch.shape
-            key = (id(shell), h, w)
-            pred = self._compiled.get(key)
-            if pred is None or pred.net.max_batch < b:
-                dev_index = torch.device(device).index if device is not None else 0
-                pred = b200_predictor.from_shell(shell, h, w, max(b, 1), device=dev_index or 0)
-                pred.decoder = self.native if self.native.device == pred.decoder.device else pred.decoder
-                self._compiled[key] = pred
+            pred = self._predictor_for(shell, int(b), int(h), int(w), device)
             results = pred.batch(image_batch if image_batch.dtype == torch.float32 else image_batch.float())
             self.last_nn_time = self.last_decoder_time = time.perf_counter() - start
             return [self._annotations(a.numpy(), i.numpy()) for a, i in results]

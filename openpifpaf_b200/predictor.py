@@ -7,7 +7,9 @@ Mirror of the reference's hot loop (paths relative to /root/reference/src/openpi
 Differences by design: the head tensors never leave the GPU (the reference does
 ``heads.cpu()`` at decoder/decoder.py:98 and decodes on host cores); the whole
 batch is decoded by one batched launch sequence; only the final annotations
-(a few KB) are copied back.
+(a few KB) are copied back.  With ``overlap_decode`` the decode of batch i runs
+on its own stream (on SMs the forward's persistent grids leave free) under the
+forward of batch i+1; the head outputs are double buffered for that.
 """
 import time
 
@@ -19,22 +21,50 @@ from . import network as _network
 
 class Predictor:
     """:param net: `network.CompiledNet`
+    :param n_keypoints: number of keypoints of the CIF head
     :param skeleton: 1-based skeleton of the CAF head (``headmeta.Caf.skeleton``)
-    :param n_keypoints: number of keypoints of the CIF head"""
+    :param cif_head, caf_head: indices of the two heads in the model output (``headmeta.head_index``)
+    :param overlap_decode: decode on a second stream, concurrently with the next forward
+    :param reserve_sms: SMs kept free of the forward's persistent grids for the concurrent decode
+                        (None: one per image of the batch, at most 1/8 of the GPU)"""
 
-    def __init__(self, net, n_keypoints, skeleton, *, device=0):
+    def __init__(self, net, n_keypoints, skeleton, *, device=0, cif_head=0, caf_head=1,
+                 overlap_decode=False, reserve_sms=None):
         self.net = net
         self.device = torch.device('cuda', device)
         sk = torch.as_tensor(skeleton, dtype=torch.int64).reshape(-1, 2) - 1     # decoder/cifcaf.py:121
         self.decoder = _decoder.CifCaf(n_keypoints, sk, device=device)
-        self.cif_head, self.caf_head = 0, 1
+        # size the native handle once, from the net (never re-created while results are in flight)
+        hd = net.heads[cif_head]
+        self.decoder.reserve(net.max_batch, hd['h'], hd['w'], max(net.heads[cif_head]['stride'], net.heads[caf_head]['stride']))
+        self.cif_head, self.caf_head = int(cif_head), int(caf_head)
         self.stream = torch.cuda.Stream(device=self.device)
         self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.dec_stream = torch.cuda.Stream(device=self.device)
+        self.overlap_decode = bool(overlap_decode)
+        self._dec_done = [None, None]
+        self._step = 0
+        if self.overlap_decode:
+            net.set_head_buffers(2)
+            n_sm = torch.cuda.get_device_properties(self.device).multi_processor_count
+            if reserve_sms is None:
+                reserve_sms = min(net.max_batch, n_sm // 8)
+            net.set_sm_limit(n_sm - int(reserve_sms) if reserve_sms else 0)
         self._dev_images = None
         self.last_nn_time = 0.0
         self.last_decoder_time = 0.0
         self.image_mean = _network.CompiledNet.IMAGE_MEAN
         self.image_std = _network.CompiledNet.IMAGE_STD
+        #: benchmark hook: (cif [B,F,5,h,w], cif_stride, caf [B,C,8,h,w], caf_stride) CUDA tensors decoded INSTEAD of
+        #: the network's own head outputs (random-init weights emit no poses; planted fields give the decoder the
+        #: work of real images).  None in production.
+        self.decode_fields_override = None
+
+    def close(self):
+        """Free the GPU buffers of the compiled net and the decoder workspace now (not at garbage collection)."""
+        torch.cuda.synchronize(self.device)
+        self.decoder._free()
+        self.net.close()
 
     def fields_batch(self, image_batch):
         """decoder/decoder.py:76-112 without the .cpu(): returns device-resident head tensors."""
@@ -47,12 +77,47 @@ class Predictor:
             return self.net.forward_uint8(image_batch_dev, mean=self.image_mean, std=self.image_std)
         return self.net.forward(image_batch_dev)
 
+    def _decode_inputs(self, heads, batch):
+        if self.decode_fields_override is not None:
+            cif, cs, caf, fs = self.decode_fields_override
+            return cif[:batch], cs, caf[:batch], fs
+        return (heads[self.cif_head], self.net.heads[self.cif_head]['stride'],
+                heads[self.caf_head], self.net.heads[self.caf_head]['stride'])
+
     def batch_device(self, image_batch_dev):
-        """Device-resident images -> enqueue forward + decode on the current stream (no host sync)."""
+        """Device-resident images -> enqueue forward + decode (no host sync).  The forward goes to the current
+        stream; the decode to the current stream too, or, with overlap_decode, to the decode stream behind an event
+        (call join() before timing or reusing the current stream's results)."""
+        cur = torch.cuda.current_stream(self.device)
+        if not self.overlap_decode:
+            heads = self._forward(image_batch_dev)
+            cif, cs, caf, fs = self._decode_inputs(heads, int(image_batch_dev.shape[0]))
+            self.decoder.decode_batch_async(cif, cs, caf, fs)
+            return
+        slot = self._step & 1
+        self._step += 1
+        if self._dec_done[slot] is not None:
+            cur.wait_event(self._dec_done[slot])       # the head-output set this forward overwrites has been decoded
         heads = self._forward(image_batch_dev)
-        cif, caf = heads[self.cif_head], heads[self.caf_head]
-        self.decoder.decode_batch_async(cif, self.net.heads[self.cif_head]['stride'],
-                                        caf, self.net.heads[self.caf_head]['stride'])
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        self.dec_stream.wait_event(ready)
+        cif, cs, caf, fs = self._decode_inputs(heads, int(image_batch_dev.shape[0]))
+        self.decoder.decode_batch_async(cif, cs, caf, fs, stream=self.dec_stream)
+        done = torch.cuda.Event()
+        done.record(self.dec_stream)
+        self._dec_done[slot] = done
+
+    def result_stream(self):
+        """The stream the decode results are produced on."""
+        return self.dec_stream if self.overlap_decode else torch.cuda.current_stream(self.device)
+
+    def join(self):
+        """Make the current stream wait for every decode enqueued so far (overlap_decode)."""
+        cur = torch.cuda.current_stream(self.device)
+        for ev in self._dec_done:
+            if ev is not None:
+                cur.wait_event(ev)
 
     def batch(self, image_batch_host):
         """decoder/decoder.py:114-137: image batch (host, ideally pinned; float32 [B,3,H,W] normalised, or raw
@@ -65,7 +130,8 @@ class Predictor:
                 self._dev_images = torch.empty(image_batch_host.shape, dtype=image_batch_host.dtype, device=self.device)
             self._dev_images.copy_(image_batch_host, non_blocking=True)
             self.batch_device(self._dev_images)
-            result = self.decoder.fetch(stream=self.stream)
+            result = self.decoder.fetch(stream=self.result_stream())
+            self.join()
         self.last_nn_time = self.last_decoder_time = time.perf_counter() - t0
         return result
 
@@ -90,8 +156,8 @@ class Predictor:
                 self.stream.wait_event(copied[s])
                 self.batch_device(dev[s])
                 consumed[s] = torch.cuda.Event()
-                consumed[s].record(self.stream)
-                self.decoder.fetch_begin(stream=self.stream)
+                consumed[s].record(self.stream)        # the forward (the only reader of dev[s]) is on self.stream
+                self.decoder.fetch_begin(stream=self.result_stream())
             outstanding += 1
             if outstanding == 2:
                 yield self.decoder.fetch_end()
@@ -99,15 +165,26 @@ class Predictor:
         while outstanding:
             yield self.decoder.fetch_end()
             outstanding -= 1
+        with torch.cuda.stream(self.stream):
+            self.join()
 
 
-def from_shell(shell, in_h, in_w, max_batch, *, device=0):
-    """Compile a reference-style Shell (network/nets.py:7-48) whose heads are (Cif, Caf) into a Predictor."""
+def from_shell(shell, in_h, in_w, max_batch, *, device=0, cif_meta=None, caf_meta=None, **kwargs):
+    """Compile a reference-style Shell (network/nets.py:7-48) with a (Cif, Caf) head pair into a Predictor.
+    cif_meta / caf_meta: the head metas the decoder was built for (decoder/cifcaf.py:212-222); default: the
+    first Cif-like meta followed by a Caf-like one."""
     plan = _network.plan_from_shell(shell)
     net = _network.CompiledNet(plan, in_h, in_w, max_batch, device=device)
-    metas = shell.head_metas
-    cif_meta, caf_meta = metas[0], metas[1]
+    metas = list(shell.head_metas)
+    if cif_meta is None or caf_meta is None:
+        cif_meta, caf_meta = metas[0], metas[1]
     skeleton = getattr(caf_meta, 'skeleton', None)
     if skeleton is None:
         raise RuntimeError('CAF head meta has no skeleton')
-    return Predictor(net, cif_meta.n_fields, skeleton, device=device)
+
+    def index_of(meta, default):
+        hi = getattr(meta, 'head_index', None)
+        return int(hi) if hi is not None else default
+
+    return Predictor(net, cif_meta.n_fields, skeleton, device=device,
+                     cif_head=index_of(cif_meta, 0), caf_head=index_of(caf_meta, 1), **kwargs)

@@ -46,5 +46,39 @@ def build(force=False, verbose=False):
     return OUT_SO
 
 
+REF_PY = '/root/reference/src/openpifpaf'
+PKG_DIR = os.path.join(HERE, '_ref_pkg')
+
+
+def stage_package(force=False):
+    """Stage the UNMODIFIED reference Python package next to its compiled extension so that it travels to the GPU
+    box (like oracle/_ref, this directory is git-ignored but not gpurun-ignored; nothing of it enters the history):
+
+      oracle/_ref_pkg/openpifpaf/        <- copy of /root/reference/src/openpifpaf (csrc/ sources left out)
+      oracle/_ref_pkg/openpifpaf/_cpp.so <- oracle/_ref/refcpp.so (what cpp_extension.py:6-26 looks for)
+      oracle/_ref_pkg/pysparkling.py     <- one-line stub of the optional dependency (gotcha 2)
+
+    Users: the -m gpu plugin test (the reference's own Predictor / Multi.batch with CifCafB200 selected) and
+    bench.py --impl reference (the reference's own Shell + Decoder.batch on the host cores)."""
+    marker = os.path.join(PKG_DIR, 'openpifpaf', '_cpp.so')
+    if os.path.exists(marker) and not force:
+        return PKG_DIR
+    if not os.path.isdir(REF_PY):
+        raise FileNotFoundError(f'{REF_PY} not present (GPU box?): oracle/_ref_pkg must be staged beforehand')
+    so = build()
+    shutil.rmtree(PKG_DIR, ignore_errors=True)
+    shutil.copytree(REF_PY, os.path.join(PKG_DIR, 'openpifpaf'),
+                    ignore=shutil.ignore_patterns('csrc', '__pycache__', '*.pyc'))
+    shutil.copy(so, marker)
+    with open(os.path.join(PKG_DIR, 'pysparkling.py'), 'w') as f:
+        f.write('class Context:\n    pass\n')
+    return PKG_DIR
+
+
+def package_available():
+    return os.path.exists(os.path.join(PKG_DIR, 'openpifpaf', '_cpp.so'))
+
+
 if __name__ == '__main__':
     print(build(force='--force' in sys.argv, verbose=True))
+    print(stage_package(force='--force' in sys.argv))

@@ -210,9 +210,14 @@ def model_defaults(net):
             m.momentum = 0.01
 
 
-def make_shell(base_name='shufflenetv2k16', n_keypoints=17, n_connections=19, seed=0, randomize_bn=True):
+def make_shell(base_name='shufflenetv2k16', n_keypoints=17, n_connections=19, seed=0, randomize_bn=True,
+               he_init=False):
     """From-scratch Shell like network/factory.py:276-295 (eval mode).  randomize_bn gives the BatchNorm
-    layers non-trivial running statistics/affine parameters so that BN folding is actually exercised."""
+    layers non-trivial running statistics/affine parameters so that BN folding is actually exercised.
+    he_init re-draws every backbone convolution with std sqrt(2 / fan_in): with torch's default init (gain
+    1/sqrt(3)) and eval-mode BatchNorm the signal of a 58-layer ShuffleNetV2K dies out -- its features are the same
+    for any input to 7 digits (measured) -- whereas the variance-preserving init keeps them input dependent
+    (std over positions ~ 0.45 of the rms, effective rank ~230 at 21x21), like a trained network's."""
     g = torch.Generator().manual_seed(seed)
     torch.manual_seed(seed)
     base = make_base(base_name)
@@ -227,5 +232,11 @@ def make_shell(base_name='shufflenetv2k16', n_keypoints=17, n_connections=19, se
                 m.running_var.copy_(torch.rand(m.num_features, generator=g) * 0.5 + 0.75)
                 m.weight.data.copy_(torch.rand(m.num_features, generator=g) * 0.5 + 0.75)
                 m.bias.data.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+    if he_init:
+        with torch.no_grad():
+            for m in shell.base_net.modules():
+                if isinstance(m, torch.nn.Conv2d):
+                    fan_in = m.weight.shape[1] * m.weight.shape[2] * m.weight.shape[3]
+                    m.weight.copy_(torch.randn(m.weight.shape, generator=g) * (2.0 / fan_in) ** 0.5)
     shell.eval()
     return shell

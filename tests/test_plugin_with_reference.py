@@ -2,24 +2,27 @@
 compiled extension of oracle/_ref) and is selected by the reference's decoder factory.  Skipped when the
 reference is not available (e.g. on the GPU box)."""
 import os
-import shutil
 import subprocess
 import sys
 import textwrap
 
 import pytest
 
-REF = '/root/reference/src/openpifpaf'
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF_SO = os.path.join(ROOT, 'oracle', '_ref', 'refcpp.so')
+PKG = os.path.join(ROOT, 'oracle', '_ref_pkg')        # staged by oracle/build_ref.py::stage_package
 
 
-@pytest.mark.skipif(not (os.path.isdir(REF) and os.path.exists(REF_SO)), reason='reference not available')
+def _staged():
+    if not os.path.exists(os.path.join(PKG, 'openpifpaf', '_cpp.so')) and os.path.isdir('/root/reference/src/openpifpaf'):
+        sys.path.insert(0, ROOT)
+        from oracle import build_ref
+        build_ref.stage_package()
+    return os.path.exists(os.path.join(PKG, 'openpifpaf', '_cpp.so'))
+
+
+@pytest.mark.skipif(not _staged(), reason='reference package not staged')
 def test_plugin_registers_and_is_selected(tmp_path):
-    stage = tmp_path / 'stage'
-    shutil.copytree(REF, stage / 'openpifpaf')
-    shutil.copy(REF_SO, stage / 'openpifpaf' / '_cpp.so')
-    (stage / 'pysparkling.py').write_text('class Context: pass\n')     # optional dependency stub (SURVEY 8c)
+    stage = PKG
     script = textwrap.dedent('''
         import sys, warnings
         warnings.filterwarnings('ignore')
@@ -46,6 +49,9 @@ def test_plugin_registers_and_is_selected(tmp_path):
         args = parser.parse_args(['--force-complete-pose', '--seed-threshold=0.1'])
         openpifpaf.decoder.configure(args)
         from openpifpaf_b200 import decoder as d
+        # the reference's own statics are the single source of truth; the plugin snapshots them per decode
+        assert d.CifCaf.params().force_complete == 0
+        type(top).sync_statics()
         p = d.CifCaf.params()
         assert (p.force_complete, p.keypoint_threshold, p.keypoint_threshold_rel, p.seed_threshold,
                 p.nms_instance_threshold, p.nms_keypoint_threshold) == (1, 0.0, 0.0, 0.1, 0.0, 0.0), \\
