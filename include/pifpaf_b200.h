@@ -148,6 +148,12 @@ int pifpaf_decoder_tap_seeds(pifpaf_decoder_t* dec, int32_t b, int64_t* out_f, f
 int pifpaf_decoder_tap_caf(pifpaf_decoder_t* dec, int32_t b, float* out_fwd, int64_t* n_fwd,
                            float* out_bwd, int64_t* n_bwd);
 
+/* Tests only: move the handle's validity tags next to their wrap-around points.  Occupancy::clear and the fresh
+ * CifHr buffer of a new reference instance (csrc/src/occupancy.cpp:71-77, csrc/src/cif_hr.cpp:97-121) are epoch
+ * tags here (a byte per occupancy cell, a word per CifHr tile); when a tag would wrap the maps are really cleared
+ * once.  occupancy_epoch: odd, 1..255 (two tags per decode); cifhr_epoch: any 32-bit value. */
+int pifpaf_decoder_debug_set_epochs(pifpaf_decoder_t* dec, uint32_t occupancy_epoch, uint32_t cifhr_epoch);
+
 /* Work counters of the last decode, summed over its batch (synchronises; bench.py's decoder roofline):
  * stats[0] hi-res CifHr pixels written (the map is tile-sparse), [1] seeds (CifSeeds.get), [2] CAF list entries
  * (forward + backward, CafScored.get; of the force-complete refill if that ran), [3] annotations before NMS. */
@@ -222,6 +228,18 @@ int pifpaf_net_dwconv(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off, 
                       int32_t kernel, int32_t stride, int32_t pad, const float* weight, const float* bias,
                       int32_t relu, int32_t out_tensor, int32_t out_col_off);
 
+/* Depthwise 5x5 (stride 1) -> BatchNorm -> 1x1 conv -> BatchNorm -> ReLU, the tail of InvertedResidualK.branch2
+ * (basenetworks.py:219-226), as ONE kernel: the depthwise result is produced tile by tile straight into the
+ * shared-memory A operand of the tcgen05 GEMM and never visits HBM.  Arguments: those of pifpaf_net_dwconv
+ * (dw_weight [channels][5][5], dw_bias: folded BN) followed by those of pifpaf_net_conv1x1_scatter (weight
+ * [n_out][channels] over the depthwise output channels; n_out a multiple of 16, at most 512). */
+int pifpaf_net_dw_conv1x1_scatter(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off, int32_t channels,
+                                  int32_t kernel, int32_t stride, int32_t pad,
+                                  const float* dw_weight, const float* dw_bias, int32_t dw_relu,
+                                  int32_t n_out, const float* weight, const float* bias, int32_t relu,
+                                  int32_t n_pieces, const int32_t* piece_col0, const int32_t* piece_count,
+                                  const int32_t* piece_tensor, const int32_t* piece_tensor_col);
+
 /* All CompositeField4 heads as ONE GEMM with the eval epilogue fused (heads.py:330-378):
  * head i has n_fields[i] x n_comp[i] output channels (channel = f*n_comp + comp);
  * comp_ops (concatenated per head, length sum n_comp): 0 raw, 1 sigmoid, 2 +x index, 3 +y index,
@@ -256,7 +274,7 @@ int pifpaf_net_forward_u8(pifpaf_net_t* net, const uint8_t* images_nhwc_dev, int
 
 /* Same as pifpaf_net_forward but brackets every op with CUDA events on `stream` and, after a final
  * synchronise, writes per-op milliseconds to op_ms[num_ops] (profiling leg of bench.py; never the
- * headline timing).  op_kind[i]: 0 input conv, 1 tcgen05 GEMM, 2 depthwise conv; op_flops/op_bytes are
+ * headline timing).  op_kind[i]: 0 input conv, 1 tcgen05 GEMM, 2 depthwise conv, 3 fused depthwise -> GEMM; op_flops/op_bytes are
  * the algorithmic FLOPs and bytes (inputs + outputs + weights, each once) of op i for this batch. */
 int pifpaf_net_forward_timed(pifpaf_net_t* net, const float* images_dev, int32_t batch, int32_t gemm_impl,
                              void* stream, float* op_ms, int32_t* op_kind, double* op_flops, double* op_bytes);

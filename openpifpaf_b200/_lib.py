@@ -52,6 +52,7 @@ SYMBOLS = {
     'pifpaf_decoder_tap_cifhr': (ctypes.c_int, [VP, c_i32, VP, c_i64]),
     'pifpaf_decoder_tap_seeds': (ctypes.c_int, [VP, c_i32, VP, VP, c_i64, P(c_i64)]),
     'pifpaf_decoder_tap_caf': (ctypes.c_int, [VP, c_i32, VP, VP, VP, VP]),
+    'pifpaf_decoder_debug_set_epochs': (ctypes.c_int, [VP, ctypes.c_uint32, ctypes.c_uint32]),
     'pifpaf_decoder_last_stats': (ctypes.c_int, [VP, VP, c_i32]),
     'pifpaf_net_create': (ctypes.c_int, [P(VP), c_i32, c_i32]),
     'pifpaf_net_destroy': (None, [VP]),
@@ -59,6 +60,8 @@ SYMBOLS = {
     'pifpaf_net_input_conv': (ctypes.c_int, [VP, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, VP, VP, c_i32, c_i32]),
     'pifpaf_net_conv1x1': (ctypes.c_int, [VP, c_i32, c_i32, c_i32, c_i32, VP, VP, c_i32, c_i32, c_i32, c_i32, c_i32]),
     'pifpaf_net_conv1x1_scatter': (ctypes.c_int, [VP, c_i32, c_i32, c_i32, c_i32, VP, VP, c_i32, c_i32, VP, VP, VP, VP]),
+    'pifpaf_net_dw_conv1x1_scatter': (ctypes.c_int, [VP, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, VP, VP, c_i32,
+                                                      c_i32, VP, VP, c_i32, c_i32, VP, VP, VP, VP]),
     'pifpaf_net_conv': (ctypes.c_int, [VP, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, VP, VP, c_i32, c_i32, c_i32,
                                        c_i32, c_i32]),
     'pifpaf_net_dwconv': (ctypes.c_int, [VP, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, VP, VP, c_i32, c_i32, c_i32]),

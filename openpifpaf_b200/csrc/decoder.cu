@@ -1657,6 +1657,15 @@ int pifpaf_decoder_tap_caf(pifpaf_decoder_t* dec, int32_t b, float* out_fwd, int
     return PIFPAF_OK;
 }
 
+int pifpaf_decoder_debug_set_epochs(pifpaf_decoder_t* dec, uint32_t occupancy_epoch, uint32_t cifhr_epoch) {
+    PIFPAF_CHECK_ARG(dec != nullptr, "decoder handle is null");
+    PIFPAF_CHECK_ARG(occupancy_epoch >= 1 && occupancy_epoch <= 255 && (occupancy_epoch & 1u) == 1u,
+                     "occupancy epoch must be odd and in [1, 255]");
+    dec->epoch = occupancy_epoch;
+    dec->hr_epoch = cifhr_epoch;
+    return PIFPAF_OK;
+}
+
 int pifpaf_decoder_last_stats(pifpaf_decoder_t* dec, int64_t* stats, int32_t n_stats) {
     PIFPAF_CHECK_ARG(dec != nullptr && dec->has_last, "no decode to report on");
     PIFPAF_CHECK_ARG(stats != nullptr && n_stats >= 4, "stats must hold at least 4 values");

@@ -932,6 +932,269 @@ __global__ void __launch_bounds__(256) k_dwconv(DwArgs a) {
     }
 }
 
+
+// ------------------------------------------------------------------ fused depthwise 5x5 -> 1x1 GEMM
+// InvertedResidualK branch2 tail (basenetworks.py:219-226: dw5x5, BN, 1x1, BN, ReLU) as ONE kernel: the depthwise
+// output never visits HBM.  Per CTA (persistent over 8 x 16 output-pixel patches == 128-row M tiles), per 64-channel
+// K block:
+//   warp 0     TMA producer: the patch's input window (12 x 20 pixels x 64 channels, zero fill == conv padding) into
+//              a window ring, and the K block of the 1x1 weights [n_pad x 64] into a B ring
+//   warps 2-9  depthwise: one warp = a 4 x 4 block of output pixels, one lane = a channel pair (the register-blocked
+//              FMA loop of k_dwconv5_tma); results go as bf16 straight into a 128B-swizzled K-major A stage
+//              (row = pixel of the patch, the layout TMA would have produced), fence.proxy.async + mbarrier arrive
+//   warp 1     tcgen05.mma issuer: D[128 x n_pad] += A-stage x B-stage^T in TMEM; tcgen05.commit frees the stages
+//   warps 10-13 epilogue: TMEM -> registers -> bias + ReLU -> bf16 -> scatter / plain stores (epilogue_chunk)
+// n_pad <= 512 TMEM columns; n_pad > 256 runs as two UMMA halves; two accumulator stages when 2 * n_pad <= 512.
+constexpr int FD_DW_WARPS = 8, FD_EPI_WARPS = 4;
+constexpr int FD_THREADS = 32 * (2 + FD_DW_WARPS + FD_EPI_WARPS);     // 448
+
+struct FusedArgs {
+    const float* dw_weight;      // [25][C] f32, tap-major
+    const float* dw_bias;        // [C]
+    int C;                       // physical channels of the depthwise input (multiple of 8)
+    int dw_relu, pad;
+    int ws, as, bs;              // ring depths: windows, A stages, B stages
+    int n_pad, n_halves, half_n; // n_pad = n_halves * half_n, half_n <= 256, multiple of 16
+    int acc_stages;
+};
+
+__device__ __forceinline__ void fence_proxy_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int S>
+__global__ void __launch_bounds__(FD_THREADS, 1)
+k_dw_gemm(const __grid_constant__ CUtensorMap tmap_win, const __grid_constant__ CUtensorMap tmap_b, GemmArgs g, FusedArgs f) {
+    using T = DwTile<S, PH, PW, 4, 1>;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int a_bytes = BM * BK * 2;                     // 16 KB
+    const int b_bytes = f.n_pad * BK * 2;                // multiple of 1024 (n_pad % 16 == 0)
+    unsigned char* a_st = smem;
+    unsigned char* b_st = a_st + (size_t)f.as * a_bytes;
+    unsigned char* win = b_st + (size_t)f.bs * b_bytes;
+    float* bias_s = reinterpret_cast<float*>(win + (size_t)f.ws * T::BYTES);
+    DestGroup* dest_s = reinterpret_cast<DestGroup*>(bias_s + f.n_pad);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(dest_s + f.n_pad / CHUNK);
+    uint64_t* win_full = bars;                 uint64_t* win_empty = win_full + f.ws;
+    uint64_t* a_full = win_empty + f.ws;       uint64_t* a_empty = a_full + f.as;
+    uint64_t* b_full = a_empty + f.as;         uint64_t* b_empty = b_full + f.bs;
+    uint64_t* tmem_full = b_empty + f.bs;      uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t need_cols = (uint32_t)(f.acc_stages * f.n_pad);
+    const uint32_t tmem_cols = need_cols <= 32 ? 32 : need_cols <= 64 ? 64 : need_cols <= 128 ? 128 : need_cols <= 256 ? 256 : 512;
+
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_win); tma_prefetch_desc(&tmap_b); }
+    for (int i = threadIdx.x; i < f.n_pad; i += FD_THREADS) bias_s[i] = g.bias[i];
+    if (g.mode == MODE_SCATTER)
+        for (int i = threadIdx.x; i < f.n_pad / CHUNK; i += FD_THREADS) dest_s[i] = g.dest[i];
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < f.ws; i++) { mbar_init(&win_full[i], 1); mbar_init(&win_empty[i], FD_DW_WARPS); }
+            for (int i = 0; i < f.as; i++) { mbar_init(&a_full[i], FD_DW_WARPS); mbar_init(&a_empty[i], 1); }
+            for (int i = 0; i < f.bs; i++) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+            for (int i = 0; i < 2; i++) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], FD_EPI_WARPS); }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_ptr, tmem_cols);
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const int per_img = g.tiles_x * g.tiles_y;
+    const int nkb = g.num_k_blocks;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int wi = 0; uint32_t wph = 0; int bi = 0; uint32_t bph = 0;
+            for (int tile = blockIdx.x; tile < g.m_blocks; tile += gridDim.x) {
+                const int img = tile / per_img, t = tile - img * per_img;
+                const int cy = (t / g.tiles_x) * PH * S - f.pad, cx = (t % g.tiles_x) * PW * S - f.pad;
+                for (int kb = 0; kb < nkb; kb++) {
+                    mbar_wait(&win_empty[wi], wph ^ 1);
+                    mbar_expect_tx(&win_full[wi], (uint32_t)T::BYTES);
+                    tma_load_4d(win + (size_t)wi * T::BYTES, &tmap_win, &win_full[wi], kb * 64, cx, cy, img);
+                    if (++wi == f.ws) { wi = 0; wph ^= 1; }
+                    mbar_wait(&b_empty[bi], bph ^ 1);
+                    mbar_expect_tx(&b_full[bi], (uint32_t)b_bytes);
+                    for (int h = 0; h < f.n_halves; h++)
+                        tma_load_2d(b_st + (size_t)bi * b_bytes + (size_t)h * f.half_n * BK * 2, &tmap_b, &b_full[bi],
+                                    kb * BK, h * f.half_n);
+                    if (++bi == f.bs) { bi = 0; bph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = make_instr_desc(BM, f.half_n);
+            int ai = 0; uint32_t aph = 0; int bi = 0; uint32_t bph = 0; int acc = 0; uint32_t acc_ph = 0;
+            for (int tile = blockIdx.x; tile < g.m_blocks; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * f.n_pad);
+                for (int kb = 0; kb < nkb; kb++) {
+                    mbar_wait(&a_full[ai], aph);
+                    mbar_wait(&b_full[bi], bph);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(a_st + (size_t)ai * a_bytes);
+                    const uint32_t sb = smem_u32(b_st + (size_t)bi * b_bytes);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; k++) {
+                        const uint64_t adesc = make_smem_desc(sa + k * UMMA_K * 2);
+                        for (int h = 0; h < f.n_halves; h++) {
+                            const uint64_t bdesc = make_smem_desc(sb + (uint32_t)(h * f.half_n * BK * 2) + k * UMMA_K * 2);
+                            umma_bf16(d_tmem + (uint32_t)(h * f.half_n), adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&a_empty[ai]);
+                    umma_commit(&b_empty[bi]);
+                    if (++ai == f.as) { ai = 0; aph ^= 1; }
+                    if (++bi == f.bs) { bi = 0; bph ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);
+                if (++acc == f.acc_stages) { acc = 0; acc_ph ^= 1; }
+            }
+        }
+    } else if (warp < 2 + FD_DW_WARPS) {
+        // ===== depthwise warps =====
+        const int dwi = warp - 2;
+        const int by = dwi / (PW / 4), bx = dwi % (PW / 4);        // 4 x 4 output block of this warp inside the patch
+        int wi = 0; uint32_t wph = 0; int ai = 0; uint32_t aph = 0;
+        for (int tile = blockIdx.x; tile < g.m_blocks; tile += gridDim.x) {
+            const int img = tile / per_img, t = tile - img * per_img;
+            const int oy0 = (t / g.tiles_x) * PH + by * 4, ox0 = (t % g.tiles_x) * PW + bx * 4;
+            const bool inside = oy0 < g.Ho && ox0 < g.Wo;            // blocks past the image edge: rows nobody stores
+            (void)img;
+            for (int kb = 0; kb < nkb; kb++) {
+                const int c0 = kb * 64 + lane * 2;
+                const bool cok = c0 < f.C;
+                float wgt[25][2];
+                float bias0 = 0.f, bias1 = 0.f;
+                if (inside) {
+#pragma unroll
+                    for (int tp = 0; tp < 25; tp++) {
+                        const float2 wv = cok ? __ldg(reinterpret_cast<const float2*>(f.dw_weight + (size_t)tp * f.C + c0))
+                                              : make_float2(0.f, 0.f);
+                        wgt[tp][0] = wv.x; wgt[tp][1] = wv.y;
+                    }
+                    if (cok) { const float2 bv = __ldg(reinterpret_cast<const float2*>(f.dw_bias + c0)); bias0 = bv.x; bias1 = bv.y; }
+                }
+                float acc[4][4][2];
+                mbar_wait(&win_full[wi], wph);
+                if (inside) {
+                    const unsigned char* tile_p = win + (size_t)wi * T::BYTES + lane * 4 +
+                                                  ((by * 4 * S) * T::IW + bx * 4 * S) * 128;
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) { acc[i][j][0] = bias0; acc[i][j][1] = bias1; }
+#pragma unroll
+                    for (int ry = 0; ry < T::WIN_Y; ry++) {
+                        float v2[T::WIN_X][2];
+#pragma unroll
+                        for (int cx = 0; cx < T::WIN_X; cx++) {
+                            const uint32_t v = *reinterpret_cast<const uint32_t*>(tile_p + (ry * T::IW + cx) * 128);
+                            v2[cx][0] = __uint_as_float(v << 16);
+                            v2[cx][1] = __uint_as_float(v & 0xffff0000u);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const int ky = ry - i * S;                    // compile-time after unrolling
+                            if (ky < 0 || ky >= 5) continue;
+#pragma unroll
+                            for (int kx = 0; kx < 5; kx++) {
+#pragma unroll
+                                for (int j = 0; j < 4; j++) {
+                                    acc[i][j][0] = fmaf(v2[j * S + kx][0], wgt[ky * 5 + kx][0], acc[i][j][0]);
+                                    acc[i][j][1] = fmaf(v2[j * S + kx][1], wgt[ky * 5 + kx][1], acc[i][j][1]);
+                                }
+                            }
+                        }
+                    }
+                    if (f.dw_relu) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                acc[i][j][0] = fmaxf(acc[i][j][0], 0.f); acc[i][j][1] = fmaxf(acc[i][j][1], 0.f);
+                            }
+                    }
+                }
+                // the window slot is free as soon as its values sit in registers
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&win_empty[wi]);
+                if (++wi == f.ws) { wi = 0; wph ^= 1; }
+                // A stage: row = pixel of the patch, 16-byte chunk index XOR (row & 7) (SWIZZLE_128B, K-major)
+                mbar_wait(&a_empty[ai], aph ^ 1);
+                if (inside) {
+                    unsigned char* a_base = a_st + (size_t)ai * a_bytes + (lane & 3) * 4;
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const int row = (by * 4 + i) * PW + bx * 4 + j;
+                            *reinterpret_cast<uint32_t*>(a_base + row * 128 + ((((lane >> 2) ^ (row & 7))) << 4)) =
+                                pack_bf16(acc[i][j][0], acc[i][j][1]);
+                        }
+                }
+                fence_proxy_async_shared();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_full[ai]);
+                if (++ai == f.as) { ai = 0; aph ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue warps: TMEM lane quadrant = warp % 4 =====
+        const int q = warp & 3;
+        const int n_chunks = f.n_pad / CHUNK;
+        int acc = 0; uint32_t acc_ph = 0;
+        for (int tile = blockIdx.x; tile < g.m_blocks; tile += gridDim.x) {
+            mbar_wait(&tmem_full[acc], acc_ph);
+            tcgen05_fence_after();
+            const int m = tile_row_to_m(g, tile, q * 32 + lane);
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (uint32_t)(acc * f.n_pad);
+            uint32_t va[CHUNK], vb[CHUNK];
+            auto process = [&](int ci, const uint32_t* v) {
+                float accf[CHUNK];
+#pragma unroll
+                for (int j = 0; j < CHUNK; j++) accf[j] = __uint_as_float(v[j]);
+                const int n0 = ci * CHUNK;
+                if (n0 < ((g.N + 7) & ~7)) epilogue_chunk(g, m, n0, accf, bias_s + n0, nullptr, dest_s);
+            };
+            tmem_ld16_async(t_row, va);
+            for (int ci = 0; ci < n_chunks; ci += 2) {
+                tmem_ld_wait(va);
+                if (ci + 1 < n_chunks) tmem_ld16_async(t_row + (uint32_t)((ci + 1) * CHUNK), vb);
+                process(ci, va);
+                if (ci + 1 < n_chunks) {
+                    tmem_ld_wait(vb);
+                    if (ci + 2 < n_chunks) tmem_ld16_async(t_row + (uint32_t)((ci + 2) * CHUNK), va);
+                    process(ci + 1, vb);
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == f.acc_stages) { acc = 0; acc_ph ^= 1; }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+size_t fused_smem_bytes(int ws, int as, int bs, int n_pad) {
+    return 1024 + (size_t)as * BM * BK * 2 + (size_t)bs * n_pad * BK * 2 + (size_t)ws * DwTile<1, PH, PW, 4, 1>::BYTES +
+           (size_t)n_pad * 5 + (size_t)(2 * (ws + as + bs) + 4) * 8 + 64;
+}
+
 // ------------------------------------------------------------------ input conv: f32 NCHW [B,3,H,W] -> bf16 NHWC
 struct InConvArgs {
     const float* in; __nv_bfloat16* out; int ld_out;
@@ -1136,7 +1399,7 @@ int make_tmap_dw(CUtensorMap* map, const void* base, uint64_t c, uint64_t w, uin
 
 struct Tensor { int h, w, c; __nv_bfloat16* data; };
 
-enum OpKind { OP_INPUT_CONV, OP_GEMM, OP_DW };
+enum OpKind { OP_INPUT_CONV, OP_GEMM, OP_DW, OP_FUSED };
 
 struct Op {
     OpKind kind;
@@ -1148,6 +1411,8 @@ struct Op {
     // dw
     DwArgs dw{};
     CUtensorMap tmap_dw{}; bool dw_tma = false;
+    // fused depthwise -> GEMM (OP_FUSED): g + tmap_dw (windows) + tmap_b
+    FusedArgs fu{};
     // input conv
     InConvArgs ic{};
     int n_out_pixels = 0;
@@ -1339,6 +1604,7 @@ int pifpaf_net_create(pifpaf_net_t** out, int32_t device, int32_t max_batch) {
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, DwS1::SMEM));
     PIFPAF_CUDA_TRY(cudaFuncSetAttribute(k_dwconv5_tma<2, DW2_TH, DW2_TW, 4, 2>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, DwS2::SMEM));
+    PIFPAF_CUDA_TRY(cudaFuncSetAttribute(k_dw_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     *out = net;
     return PIFPAF_OK;
 }
@@ -1612,6 +1878,107 @@ int pifpaf_net_dwconv(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off, 
     return PIFPAF_OK;
 }
 
+int pifpaf_net_dw_conv1x1_scatter(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off, int32_t channels,
+                                  int32_t kernel, int32_t stride, int32_t pad,
+                                  const float* dw_weight, const float* dw_bias, int32_t dw_relu,
+                                  int32_t n_out, const float* weight, const float* bias, int32_t relu,
+                                  int32_t n_pieces, const int32_t* piece_col0, const int32_t* piece_count,
+                                  const int32_t* piece_tensor, const int32_t* piece_tensor_col) {
+    PIFPAF_CHECK_ARG(net != nullptr && dw_weight != nullptr && weight != nullptr && piece_col0 && piece_count &&
+                     piece_tensor && piece_tensor_col, "null argument");
+    const int nt = (int)net->tensors.size();
+    PIFPAF_CHECK_ARG(in_tensor >= 0 && in_tensor < nt, "bad tensor id");
+    PIFPAF_CHECK_ARG(kernel == 5 && stride == 1 && pad == 2, "the fused depthwise -> 1x1 op covers 5x5, stride 1, pad 2");
+    PIFPAF_CHECK_ARG(n_out >= 16 && n_out % 16 == 0 && n_out <= 512 && n_pieces >= 1, "n_out: multiple of 16, at most 512");
+    const Tensor& tin = net->tensors[in_tensor];
+    const int C = pad8(channels);
+    PIFPAF_CHECK_ARG(in_col_off % 8 == 0 && in_col_off + C <= tin.c, "depthwise column window");
+    PIFPAF_CUDA_TRY(cudaSetDevice(net->device));
+    Op op; op.kind = OP_FUSED;
+    // depthwise weights [C][25] -> tap-major [25][C]
+    std::vector<float> dww((size_t)25 * C, 0.f), dwb(C, 0.f);
+    for (int c = 0; c < channels; c++) {
+        for (int t = 0; t < 25; t++) dww[(size_t)t * C + c] = dw_weight[(size_t)c * 25 + t];
+        dwb[c] = dw_bias ? dw_bias[c] : 0.f;
+    }
+    float *d_dww = nullptr, *d_dwb = nullptr;
+    int rc = net_upload(net, &d_dww, dww); if (rc != PIFPAF_OK) return rc;
+    rc = net_upload(net, &d_dwb, dwb); if (rc != PIFPAF_OK) return rc;
+    // 1x1 weights [n_out][channels] -> bf16 [n_pad][k_pad]
+    FusedArgs& f = op.fu;
+    f.n_halves = n_out > 256 ? 2 : 1;
+    f.n_pad = f.n_halves == 2 ? (n_out + 31) / 32 * 32 : n_out;
+    f.half_n = f.n_pad / f.n_halves;
+    f.acc_stages = 2 * f.n_pad <= 512 ? 2 : 1;
+    f.dw_weight = d_dww; f.dw_bias = d_dwb; f.C = C; f.dw_relu = dw_relu; f.pad = pad;
+    const int k_pad = C;
+    std::vector<__nv_bfloat16> w((size_t)f.n_pad * k_pad, __float2bfloat16(0.f));
+    long long nnz = 0; int n_real = 0;
+    for (int n = 0; n < n_out; n++) {
+        bool row = bias != nullptr && bias[n] != 0.f;
+        for (int k = 0; k < channels; k++) {
+            const float v = weight[(size_t)n * channels + k];
+            w[(size_t)n * k_pad + k] = __float2bfloat16(v);
+            if (v != 0.f) { nnz++; row = true; }
+        }
+        n_real += row ? 1 : 0;
+    }
+    std::vector<float> b(f.n_pad, 0.f);
+    for (int n = 0; n < n_out; n++) b[n] = bias ? bias[n] : 0.f;
+    __nv_bfloat16* d_w = nullptr; float* d_b = nullptr;
+    rc = net_upload(net, &d_w, w); if (rc != PIFPAF_OK) return rc;
+    rc = net_upload(net, &d_b, b); if (rc != PIFPAF_OK) return rc;
+    // scatter table
+    std::vector<DestGroup> groups((size_t)f.n_pad / 16, DestGroup{nullptr, 0, 0});
+    int expect = 0;
+    for (int i = 0; i < n_pieces; i++) {
+        PIFPAF_CHECK_ARG(piece_col0[i] == expect && piece_count[i] >= 16 && piece_count[i] % 16 == 0,
+                         "pieces must tile [0, n_out) in order, in multiples of 16 columns");
+        PIFPAF_CHECK_ARG(piece_tensor[i] >= 0 && piece_tensor[i] < nt, "bad piece tensor id");
+        const Tensor& to = net->tensors[piece_tensor[i]];
+        PIFPAF_CHECK_ARG(to.h == tin.h && to.w == tin.w, "stride 1 keeps the spatial shape");
+        PIFPAF_CHECK_ARG(piece_tensor_col[i] >= 0 && piece_tensor_col[i] % 16 == 0 &&
+                         piece_tensor_col[i] + piece_count[i] <= to.c, "piece window outside its tensor");
+        for (int c = 0; c < piece_count[i]; c += 16)
+            groups[(size_t)(expect + c) / 16] = DestGroup{to.data + piece_tensor_col[i] + c, to.c, 0};
+        expect += piece_count[i];
+    }
+    PIFPAF_CHECK_ARG(expect == n_out, "pieces must cover all n_out columns");
+    DestGroup* d_groups = nullptr;
+    rc = net_upload(net, &d_groups, groups); if (rc != PIFPAF_OK) return rc;
+
+    GemmArgs& g = op.g;
+    g.N = n_out; g.K = C; g.block_n = f.n_pad; g.n_blocks = 1;
+    g.num_k_blocks = (C + BK - 1) / BK;
+    g.bias = d_b; g.mode = MODE_SCATTER; g.relu = relu; g.dest = d_groups;
+    g.conv_k = kernel; g.conv_stride = stride; g.conv_pad = pad; g.conv_cblocks = g.num_k_blocks;
+    g.Hi = tin.h; g.Wi = tin.w; g.Ho = tin.h; g.Wo = tin.w;
+    g.tiles_x = (g.Wo + PW - 1) / PW; g.tiles_y = (g.Ho + PH - 1) / PH;
+    op.a_tensor = in_tensor; op.rows_per_image = g.Ho * g.Wo; op.tiles_per_image = g.tiles_x * g.tiles_y;
+    // ring depths: as deep as the shared memory allows, windows first (their TMA has the longest latency)
+    const int cand[][3] = {{3, 3, 2}, {3, 2, 2}, {2, 2, 2}, {2, 2, 1}, {1, 1, 1}};
+    bool fits = false;
+    for (const auto& c : cand) {
+        if (fused_smem_bytes(c[0], c[1], c[2], f.n_pad) <= GEMM_SMEM_BUDGET) {
+            f.ws = c[0]; f.as = c[1]; f.bs = c[2]; fits = true; break;
+        }
+    }
+    PIFPAF_CHECK_ARG(fits, "fused depthwise -> 1x1 op does not fit in shared memory");
+    op.smem = fused_smem_bytes(f.ws, f.as, f.bs, f.n_pad);
+    op.n_real = n_real;
+    op.flops_per_image = 2.0 * (double)op.rows_per_image * ((double)nnz + 25.0 * channels);
+    op.bytes_per_image = (double)op.rows_per_image * (channels + n_real) * 2.0;     // dw input once + 1x1 output once
+    op.weight_bytes = (double)nnz * 2.0 + 25.0 * channels * 4.0;
+    using T = DwTile<1, PH, PW, 4, 1>;
+    rc = make_tmap_dw(&op.tmap_dw, tin.data + in_col_off, (uint64_t)C, (uint64_t)tin.w, (uint64_t)tin.h,
+                      (uint64_t)net->max_batch, (uint64_t)tin.c, T::IW, T::IH);
+    if (rc != PIFPAF_OK) return rc;
+    rc = make_tmap(&op.tmap_b, d_w, (uint64_t)f.n_pad, (uint64_t)k_pad, (uint64_t)k_pad, (uint32_t)f.half_n);
+    if (rc != PIFPAF_OK) return rc;
+    net->ops.push_back(op);
+    return PIFPAF_OK;
+}
+
 int pifpaf_net_heads(pifpaf_net_t* net, int32_t in_tensor, int32_t k_cols, int32_t n_heads,
                      const int32_t* n_fields, const int32_t* n_comp, const int32_t* comp_ops,
                      const float* weight, const float* bias) {
@@ -1699,6 +2066,14 @@ static int net_forward_impl(pifpaf_net_t* net, const float* images_dev, int32_t 
             else if (a.kernel == 5) k_input_conv<5, false><<<grid, 256, smem, st>>>(a);
             else k_input_conv<1, false><<<grid, 256, smem, st>>>(a);
             PIFPAF_LAUNCH_CHECK();
+        } else if (op.kind == OP_FUSED) {
+            PIFPAF_CHECK_ARG(gemm_impl == 0, "the fused depthwise -> 1x1 op has no SIMT debug variant (compile the net with fuse_dw=False)");
+            GemmArgs g = op.g;
+            g.M = batch * op.rows_per_image;
+            g.m_blocks = batch * op.tiles_per_image;
+            const int grid = std::min(g.m_blocks, n_sm);
+            k_dw_gemm<1><<<grid, FD_THREADS, op.smem, st>>>(op.tmap_dw, op.tmap_b, g, op.fu);
+            PIFPAF_LAUNCH_CHECK();
         } else if (op.kind == OP_DW) {
             DwArgs a = op.dw;
             a.B = batch;
@@ -1785,7 +2160,7 @@ int pifpaf_net_forward_timed(pifpaf_net_t* net, const float* images_dev, int32_t
     for (size_t i = 0; i < n && rc == PIFPAF_OK; i++) {
         cudaEventElapsedTime(&op_ms[i], ev[i], ev[i + 1]);
         const Op& op = net->ops[i];
-        if (op_kind) op_kind[i] = op.kind == OP_INPUT_CONV ? 0 : (op.kind == OP_GEMM ? 1 : 2);
+        if (op_kind) op_kind[i] = op.kind == OP_INPUT_CONV ? 0 : (op.kind == OP_GEMM ? 1 : (op.kind == OP_DW ? 2 : 3));
         if (op_flops) op_flops[i] = op.flops_per_image * batch;
         if (op_bytes) op_bytes[i] = op.bytes_per_image * batch + op.weight_bytes;
     }

@@ -400,7 +400,13 @@ def default_layout():
     return os.environ.get('PIFPAF_LAYOUT', 'bins')
 
 
-def build_ops(plan, in_h, in_w, layout=None):
+def default_fuse_dw():
+    """Fuse depthwise 5x5 (stride 1) with the 1x1 conv that follows it into one kernel (k_dw_gemm); PIFPAF_FUSE_DW=0
+    keeps them as two launches."""
+    return os.environ.get('PIFPAF_FUSE_DW', '1') != '0'
+
+
+def build_ops(plan, in_h, in_w, layout=None, fuse_dw=None):
     """Lower a plan to the op list of libpifpaf_b200 (pure Python; no GPU needed).
 
     Returns (tensors, ops): tensors[i] = (h, w, c_phys); ops are dicts with a 'kind' in
@@ -417,6 +423,7 @@ def build_ops(plan, in_h, in_w, layout=None):
     layout = default_layout() if layout is None else layout
     if layout not in ('bins', 'shuffle'):
         raise RuntimeError("layout must be 'bins' or 'shuffle'")
+    fuse_dw = default_fuse_dw() if fuse_dw is None else bool(fuse_dw)
     tensors, ops = [], []
 
     def tensor(h, w, c):
@@ -449,6 +456,28 @@ def build_ops(plan, in_h, in_w, layout=None):
         ops.append({'kind': 'conv1x1', 'in': tin, 'in_off': 0, 'k_cols': k_cols, 'n_out': len(order),
                     'w': wp, 'b': bp, 'relu': int(relu), 'out': pieces[0][2], 'out_off': pieces[0][3],
                     'shuffle_src': -1, 'shuffle_off': 0, 'pieces': [tuple(int(v) for v in pc) for pc in pieces]})
+
+    def dw_conv1x1_scatter(tin, width, dw_wb, kernel, stride, pad, wb, relu, order, pieces):
+        """depthwise kxk on the first len(dw) channels of tin, then the scatter 1x1 conv of conv1x1_scatter on its
+        output -- one fused kernel, no intermediate tensor"""
+        dw_w, dw_b = dw_wb
+        c = dw_w.shape[0]
+        dwp = np.zeros((width, kernel * kernel), dtype=np.float32)
+        dbp = np.zeros((width,), dtype=np.float32)
+        dwp[:c] = dw_w.reshape(c, kernel * kernel)
+        dbp[:c] = dw_b
+        w, b = wb
+        w = w.reshape(w.shape[0], -1)
+        assert w.shape[1] == c
+        real = order >= 0
+        wp = np.zeros((len(order), width), dtype=np.float32)
+        wp[np.ix_(np.nonzero(real)[0], np.arange(c))] = w[order[real]]
+        bp = np.zeros((len(order),), dtype=np.float32)
+        bp[real] = b[order[real]]
+        ops.append({'kind': 'dw_conv1x1', 'in': tin, 'in_off': 0, 'channels': width, 'kernel': kernel,
+                    'stride': stride, 'pad': pad, 'dw_w': dwp, 'dw_b': dbp, 'dw_relu': 0, 'n_out': len(order),
+                    'w': wp, 'b': bp, 'relu': int(relu), 'out': pieces[0][2],
+                    'pieces': [tuple(int(v) for v in pc) for pc in pieces]})
 
     def dwconv(tin, cols, width, wb, kernel, stride, pad, tout):
         w, b = wb
@@ -504,9 +533,13 @@ def build_ops(plan, in_h, in_w, layout=None):
             width = tensors[t_bin[t]][2]
             t_c = tensor(h, w, hp)
             conv1x1(t_bin[t], 0, in_cols, width, e['b2_pw1'], True, t_c)
+            order = producers[t + 1]['order']
+            if fuse_dw and e['kernel'] == 5 and e['pad'] == 2 and len(order) <= 512:
+                dw_conv1x1_scatter(t_c, hp, e['b2_dw'], 5, 1, 2, e['b2_pw2'], True, order, pieces_of(t + 1))
+                continue
             t_d = tensor(h, w, hp)
             dwconv(t_c, np.arange(bf), hp, e['b2_dw'], e['kernel'], 1, e['pad'], t_d)
-            conv1x1_scatter(t_d, np.arange(bf), hp, e['b2_pw2'], True, producers[t + 1]['order'], pieces_of(t + 1))
+            conv1x1_scatter(t_d, np.arange(bf), hp, e['b2_pw2'], True, order, pieces_of(t + 1))
         logical = final['logical']
         phys = np.empty((2 * bf,), dtype=np.int64)
         phys[logical[logical >= 0]] = np.nonzero(logical >= 0)[0]
@@ -621,12 +654,15 @@ def _build_ops_resnet(plan, in_h, in_w):
 class CompiledNet:
     """A plan compiled to libpifpaf_b200 ops for a fixed input size and maximum batch."""
 
-    def __init__(self, plan, in_h, in_w, max_batch, device=0, layout=None):
+    def __init__(self, plan, in_h, in_w, max_batch, device=0, layout=None, fuse_dw=None):
         self.lib = _lib.lib()
         self.device = int(device)
         self.max_batch = int(max_batch)
         self.in_h, self.in_w = int(in_h), int(in_w)
-        self.tensor_shapes, ops, self.info = build_ops(plan, self.in_h, self.in_w, layout=layout)
+        if plan.get('kind') == 'shufflenetv2k':
+            self.tensor_shapes, ops, self.info = build_ops(plan, self.in_h, self.in_w, layout=layout, fuse_dw=fuse_dw)
+        else:
+            self.tensor_shapes, ops, self.info = build_ops(plan, self.in_h, self.in_w)
         self.op_desc = [{k: v for k, v in o.items() if not isinstance(v, np.ndarray)} for o in ops]
         self.handle = ctypes.c_void_p()
         _lib.check(self.lib.pifpaf_net_create(ctypes.byref(self.handle), self.device, self.max_batch))
@@ -672,6 +708,12 @@ class CompiledNet:
             if o['kind'] == 'input_conv':
                 _lib.check(L.pifpaf_net_input_conv(H, o['in_h'], o['in_w'], o['kernel'], o['stride'], o['pad'],
                                                    o['c_out'], _ptr(o['w']), _ptr(o['b']), o['relu'], o['out']))
+            elif o['kind'] == 'dw_conv1x1':
+                pcs = np.ascontiguousarray(np.asarray(o['pieces'], dtype=np.int32).T)
+                _lib.check(L.pifpaf_net_dw_conv1x1_scatter(
+                    H, o['in'], o['in_off'], o['channels'], o['kernel'], o['stride'], o['pad'], _ptr(o['dw_w']),
+                    _ptr(o['dw_b']), o['dw_relu'], o['n_out'], _ptr(o['w']), _ptr(o['b']), o['relu'], pcs.shape[1],
+                    _ptr(pcs[0]), _ptr(pcs[1]), _ptr(pcs[2]), _ptr(pcs[3])))
             elif o['kind'] == 'conv1x1' and 'pieces' in o:
                 pcs = np.ascontiguousarray(np.asarray(o['pieces'], dtype=np.int32).T)     # rows: col0, count, tensor, col
                 _lib.check(L.pifpaf_net_conv1x1_scatter(H, o['in'], o['in_off'], o['k_cols'], o['n_out'],
@@ -768,7 +810,8 @@ class CompiledNet:
         return self._head_views(b)
 
     def forward_timed(self, image_batch, *, gemm_impl=0):
-        """Profiling pass: per-op (ms, kind, flops, bytes); kind 0 input conv, 1 tcgen05 GEMM, 2 depthwise."""
+        """Profiling pass: per-op (ms, kind, flops, bytes); kind 0 input conv, 1 tcgen05 GEMM, 2 depthwise,
+        3 fused depthwise -> GEMM."""
         b, n = int(image_batch.shape[0]), self.num_ops
         ms = np.zeros((n,), dtype=np.float32)
         kind = np.zeros((n,), dtype=np.int32)

@@ -52,6 +52,20 @@ def run_ops(tensors, ops, images, bf16=False):
             if o['relu']:
                 y = F.relu(y)
             acts[o['out']][..., o['out_off']:o['out_off'] + o['n_out']] = q(y)
+        elif kind == 'dw_conv1x1':
+            c = o['channels']
+            a = acts[o['in']][..., o['in_off']:o['in_off'] + c].permute(0, 3, 1, 2)
+            wdw = torch.from_numpy(o['dw_w']).reshape(c, 1, o['kernel'], o['kernel'])
+            y = F.conv2d(a, wdw, torch.from_numpy(o['dw_b']), o['stride'], o['pad'], groups=c)
+            if o['dw_relu']:
+                y = F.relu(y)
+            y = q(y.permute(0, 2, 3, 1))                    # the bf16 A operand of the fused GEMM
+            y = y @ q(torch.from_numpy(o['w'])).t() + torch.from_numpy(o['b'])
+            if o['relu']:
+                y = F.relu(y)
+            y = q(y)
+            for (c0, cnt, t_id, t_col) in o['pieces']:
+                acts[t_id][..., t_col:t_col + cnt] = y[..., c0:c0 + cnt]
         elif kind == 'dwconv':
             c = o['channels']
             a = acts[o['in']][..., o['in_off']:o['in_off'] + c].permute(0, 3, 1, 2)

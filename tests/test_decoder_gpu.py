@@ -166,3 +166,40 @@ def test_wholebody_wide_caf_batch():
         oa, _ = oc.decode(batch['cif'][b], 16, batch['caf'][b], 16, batch['skeleton'], 133, params=p)
         helpers.assert_annotations_close(res[b][0].numpy(), oa, f'wholebody image {b}')
         assert len(oa) == 2
+
+
+def test_three_hundred_decodes_on_one_handle_cross_every_tag_wrap():
+    """State-machine edges of a long-lived handle (a Predictor keeps ONE for its lifetime): the byte-wide occupancy
+    tags wrap every 127 decodes (real clear of the map), the 32-bit CifHr tile epoch wraps once in 2^32 decodes
+    (moved next to the wrap through the debug entry point).  Every decode must equal the first, bit for bit --
+    annotations, seeds and the CifHr map -- and pipelined fetches (two outstanding) must stay in order."""
+    from openpifpaf_b200 import _lib
+    fa = synth.make_fields('cocokp', 17, 21, 3, 901, n_distractors=4)
+    fb = synth.make_fields('cocokp', 17, 21, 2, 902, n_distractors=4)
+    d = make_decoder(fa)
+    cif = torch.from_numpy(np.stack([fa['cif'], fb['cif']])).cuda()
+    caf = torch.from_numpy(np.stack([fa['caf'], fb['caf']])).cuda()
+    first = d.decode_batch(cif, 16, caf, 16)
+    hr0 = d.tap_cifhr(0).clone()
+    p = oc.default_params(seed_sort_stable=1)
+    for b, f in enumerate((fa, fb)):
+        oa, _ = oc.decode(f['cif'], 16, f['caf'], 16, f['skeleton'], 17, params=p)
+        helpers.assert_annotations_close(first[b][0].numpy(), oa, f'image {b}')
+        assert len(oa) >= 2
+    # CifHr epoch: 3 decodes before the 32-bit wrap
+    _lib.check(_lib.lib().pifpaf_decoder_debug_set_epochs(d._handle, 1, 0xFFFFFFFD))
+    for i in range(300):
+        if i % 3 == 2:          # pipelined: two decodes in flight, fetched in order
+            d.decode_batch_async(cif, 16, caf, 16)
+            d.fetch_begin()
+            d.decode_batch_async(cif.flip(0).contiguous(), 16, caf.flip(0).contiguous(), 16)
+            d.fetch_begin()
+            r1, r2 = d.fetch_end(), d.fetch_end()
+            for b in range(2):
+                assert torch.equal(r1[b][0], first[b][0]) and torch.equal(r2[1 - b][0], first[b][0]), i
+        else:
+            res = d.decode_batch(cif, 16, caf, 16)
+            for b in range(2):
+                assert torch.equal(res[b][0], first[b][0]) and torch.equal(res[b][1], first[b][1]), i
+        if i in (1, 2, 3, 4, 126, 127, 128, 254, 299):
+            assert torch.equal(d.tap_cifhr(0), hr0), i

@@ -23,17 +23,19 @@ def small():
     return shell, plan
 
 
-@pytest.mark.parametrize('layout', ['bins', 'shuffle'])
-def test_every_op_matches_bf16_emulation(small, layout):
+@pytest.mark.parametrize('layout,fuse', [('bins', True), ('bins', False), ('shuffle', False)])
+def test_every_op_matches_bf16_emulation(small, layout, fuse):
     """each fused op against a CPU emulation that rounds to bf16 at the same points (tcgen05 and SIMT debug),
-    for both activation layouts (scatter GEMMs into per-block bins / fused cat+shuffle epilogue)."""
+    for both activation layouts (scatter GEMMs into per-block bins / fused cat+shuffle epilogue) and with the
+    depthwise -> 1x1 pairs of the stride-1 blocks as one kernel (k_dw_gemm) or two."""
     shell, plan = small
     h, w, B = 97, 129, 2
     x = torch.randn(B, 3, h, w, generator=torch.Generator().manual_seed(0))
-    tensors, ops, _ = network.build_ops(plan, h, w, layout=layout)
+    tensors, ops, _ = network.build_ops(plan, h, w, layout=layout, fuse_dw=fuse)
+    assert any(o['kind'] == 'dw_conv1x1' for o in ops) == fuse
     emu_heads, emu_acts = ops_emulator.run_ops(tensors, ops, x, bf16=True)
-    net = network.CompiledNet(plan, h, w, B, layout=layout)
-    for impl in (1, 0):
+    net = network.CompiledNet(plan, h, w, B, layout=layout, fuse_dw=fuse)
+    for impl in ((0,) if fuse else (1, 0)):
         heads = net.forward(x.cuda(), gemm_impl=impl)
         torch.cuda.synchronize()
         for o in ops:
@@ -63,6 +65,31 @@ def test_fields_match_fp32_pytorch_full_size():
         assert hg.shape == hr.shape == (4, hr.shape[1], hr.shape[2], 41, 41)
         err = float((hg - hr).abs().max())
         assert err < FIELD_TOL_REL * float(hr.std()) + 1e-3, err
+
+
+def test_fused_depthwise_gemm_equals_two_kernels_bitwise():
+    """k_dw_gemm writes the depthwise result as bf16 into the GEMM's A operand exactly as the standalone depthwise
+    kernel writes it to HBM, and both GEMMs accumulate the same K blocks in the same order: the fields of the fused
+    and the two-kernel schedules are identical bit for bit -- at a size with partial edge tiles in both directions,
+    many tiles per CTA (ring wrap-around) and batch > 1, for the k16 (N <= 208, two accumulator stages; N <= 416, two
+    UMMA halves, one stage) and k30 (N = 256 / 512) channel widths."""
+    for base, heads in (('shufflenetv2k16', ((17, 1, 1, 1), (19, 1, 2, 2))), ('shufflenetv2k30', ((17, 1, 1, 1), (19, 1, 2, 2)))):
+        plan = network.random_plan(base, heads=heads, seed=7)
+        B, H, W = 5, 337, 401
+        x = torch.randn(B, 3, H, W, generator=torch.Generator().manual_seed(12)).cuda()
+        fused = network.CompiledNet(plan, H, W, B, fuse_dw=True)
+        plain = network.CompiledNet(plan, H, W, B, fuse_dw=False)
+        assert any(o['kind'] == 'dw_conv1x1' for o in fused.op_desc) and not any(o['kind'] == 'dw_conv1x1' for o in plain.op_desc)
+        hf = [t.clone() for t in fused.forward(x)]
+        hp = [t.clone() for t in plain.forward(x)]
+        torch.cuda.synchronize()
+        for a, b in zip(hf, hp):
+            assert torch.isfinite(a).all()
+            assert torch.equal(a, b), float((a - b).abs().max())
+        # every stage output too (the tensors the fused ops scatter into)
+        for (tf, lf), (tp, lp) in zip(fused.info['block_outputs'], plain.info['block_outputs']):
+            np.testing.assert_array_equal(fused.tap(tf, B)[..., lf.cols()], plain.tap(tp, B)[..., lp.cols()])
+        fused.close(); plain.close()
 
 
 def test_linearity_property_of_conv_path():

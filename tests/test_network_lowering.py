@@ -204,9 +204,28 @@ def test_random_plan_has_reference_architecture():
             gmac += hh * ww * o['w'].size / 1e9
         elif o['kind'] == 'dwconv':
             gmac += hh * ww * np.count_nonzero(o['w']) / 1e9
+        elif o['kind'] == 'dw_conv1x1':         # fused depthwise -> 1x1 (k_dw_gemm)
+            gmac += hh * ww * (np.count_nonzero(o['w']) + np.count_nonzero(o['dw_w'])) / 1e9
         elif o['kind'] == 'input_conv':
             gmac += hh * ww * o['w'].size / 1e9
     assert abs(gmac - 36.58) < 0.2, gmac       # 36.58 GMAC / image @641
+    assert sum(o['kind'] == 'dw_conv1x1' for o in ops) == 3 + 7        # stride-1 blocks of stages 2 and 3 (N <= 512)
+
+
+@pytest.mark.parametrize('fuse', [True, False])
+def test_fused_and_unfused_lowerings_compute_the_same_network(fuse):
+    """the fused depthwise -> 1x1 op is a pure scheduling change: the op list with and without it reproduces the
+    oracle network (fp32 emulation)"""
+    shell = net_oracle.make_shell('shufflenetv2k16', seed=3)
+    x = torch.randn(1, 3, 97, 129)
+    with torch.no_grad():
+        want = shell(x)
+    plan = network.plan_from_shell(shell)
+    tensors, ops, _ = network.build_ops(plan, 97, 129, fuse_dw=fuse)
+    assert any(o['kind'] == 'dw_conv1x1' for o in ops) == fuse
+    got, _ = ops_emulator.run_ops(tensors, ops, x)
+    for g, wnt in zip(got, want):
+        assert float((g - wnt).abs().max()) < 2e-5 * max(1.0, float(wnt.abs().max()))
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_SRC), reason='/root/reference absent')
