@@ -32,7 +32,6 @@ constexpr int NT = 256;            // threads per CTA for the streaming kernels
 constexpr int NW = NT / 32;
 constexpr int SORT_NT = 1024;
 constexpr int TILE = 32;           // CifHr tile edge in hi-res pixels
-constexpr int SC_CAP = 1024;       // per-warp score cache entries in k_grow
 constexpr int LIST_SMEM_ENTRIES = 8192;   // CAF list entries (c,x,y) staged in shared memory per image (96 KB)
 
 struct Dims {
@@ -44,8 +43,6 @@ struct Dims {
     int tiles_x, tiles_y;
     int max_ann;
 };
-
-struct Joint { double v, x, y, s; };
 
 struct GrowParams {
     double keypoint_threshold, keypoint_threshold_rel;
@@ -513,74 +510,48 @@ __global__ void __launch_bounds__(NT) k_caf_scored(const float* __restrict__ caf
 }
 
 // ---------------------------------------------------------------------------
-// grow_connection_blend (src/cifcaf.cpp:32-103), one warp per call.  L is the
-// SoA list base (component stride `cap`), n its length.  The sequential top-2
-// rule of the reference (">=" shifts 1->2, ">" replaces 2) is reproduced exactly:
-//   i1 = LAST index of the maximum score M;
-//   second = the running maximum of the prefix [0,i1) (last index on ties) unless
-//   a suffix element is strictly larger (first index on ties).
+// grow_connection_blend (src/cifcaf.cpp:32-103), one warp per call.  L is the SoA list base (component stride
+// `cap`), n its length; C0/X1/Y1 point at the scanned components (c, x_src, y_src), in shared memory when staged.
+// The reference's loop is order dependent (">=" shifts 1 -> 2, ">" replaces 2).  It is reproduced literally: the
+// warp evaluates 32 entries at a time, then every lane replays the entries that passed the box filter -- in index
+// order, values broadcast by shuffle -- through the same two-register update.  Few entries pass (the filter box is
+// one joint scale wide), so the replay is short; no score cache, no reduction tree, any list length.
+struct Joint { double v, x, y, s; };
+
 __device__ Joint warp_blend(const float* __restrict__ L, int cap, int n,
                             const float* C0, const float* X1, const float* Y1,
-                            double x, double y,
-                            double xy_scale, double filter_sigmas, bool only_max,
-                            float* cache, int lane) {
+                            double x, double y, double xy_scale, double filter_sigmas, bool only_max, int lane) {
     Joint zero; zero.v = 0.0; zero.x = 0.0; zero.y = 0.0; zero.s = 0.0;
     xy_scale = fmax(xy_scale, 0.5);
     const float sigma_filter = (float)(filter_sigmas * xy_scale / 2.0);
     const float sigma2 = (float)(0.25 * xy_scale * xy_scale);
     const double xlo = x - (double)sigma_filter, xhi = x + (double)sigma_filter;
     const double ylo = y - (double)sigma_filter, yhi = y + (double)sigma_filter;
-    auto score_at = [&](int i) -> float {
-        const float ex = X1[i], ey = Y1[i];
-        if ((double)ex < xlo) return -1.0f;
-        if ((double)ex > xhi) return -1.0f;
-        if ((double)ey < ylo) return -1.0f;
-        if ((double)ey > yhi) return -1.0f;
-        const double dx = (double)ex - x, dy = (double)ey - y;
-        const float d2 = (float)(dx * dx + dy * dy);
-        return (float)(exp(-0.5 * (double)d2 / (double)sigma2) * (double)C0[i]);
-    };
-
-    float best = -1.0f; int besti = -1;
-    for (int i = lane; i < n; i += 32) {
-        const float s = score_at(i);
-        if (i < SC_CAP) cache[i] = s;
-        if (s >= 0.0f && s >= best) { best = s; besti = i; }
+    float score_1 = 0.0f, score_2 = 0.0f;
+    int i1 = 0, i2 = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        bool pass = false;
+        float sc = 0.0f;
+        if (i < n) {
+            const float ex = X1[i], ey = Y1[i];
+            pass = !((double)ex < xlo) && !((double)ex > xhi) && !((double)ey < ylo) && !((double)ey > yhi);
+            if (pass) {
+                const double dx = (double)ex - x, dy = (double)ey - y;
+                const float d2 = (float)(dx * dx + dy * dy);
+                sc = (float)(exp(-0.5 * (double)d2 / (double)sigma2) * (double)C0[i]);
+            }
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, pass);
+        while (mask) {
+            const int l = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float v = __shfl_sync(0xffffffffu, sc, l);
+            if (v >= score_1) { score_2 = score_1; i2 = i1; score_1 = v; i1 = base + l; }
+            else if (v > score_2) { score_2 = v; i2 = base + l; }
+        }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-        if (ob > best || (ob == best && oi > besti)) { best = ob; besti = oi; }
-    }
-    if (besti < 0 || best == 0.0f) return zero;
-    __syncwarp();
-    const int i1 = besti;
-    const float score_1 = best;
-
-    float p = -1.0f; int pi = -1;          // prefix: max score, ties -> larger index
-    float q = -1.0f; int qi = INT_MAX;     // suffix: max score, ties -> smaller index
-    for (int i = lane; i < n; i += 32) {
-        if (i == i1) continue;
-        const float s = (i < SC_CAP) ? cache[i] : score_at(i);
-        if (s < 0.0f) continue;
-        if (i < i1) { if (s >= p) { p = s; pi = i; } }
-        else { if (s > q) { q = s; qi = i; } }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float op = __shfl_xor_sync(0xffffffffu, p, o);
-        const int opi = __shfl_xor_sync(0xffffffffu, pi, o);
-        if (op > p || (op == p && opi > pi)) { p = op; pi = opi; }
-        const float oq = __shfl_xor_sync(0xffffffffu, q, o);
-        const int oqi = __shfl_xor_sync(0xffffffffu, qi, o);
-        if (oq > q || (oq == q && oqi < qi)) { q = oq; qi = oqi; }
-    }
-    __syncwarp();
-    float score_2 = (pi >= 0) ? p : 0.0f;
-    int i2 = (pi >= 0) ? pi : 0;
-    if (qi != INT_MAX && q > score_2) { score_2 = q; i2 = qi; }
-
+    if (score_1 == 0.0f) return zero;
     const float e1x = L[3 * (size_t)cap + i1], e1y = L[4 * (size_t)cap + i1];
     const float e1s = fmaxf(0.0f, L[6 * (size_t)cap + i1]);
     Joint r;
@@ -602,37 +573,60 @@ __device__ Joint warp_blend(const float* __restrict__ L, int cap, int n,
     return r;
 }
 
-// Shared-memory working set of one image's grow CTA.
-struct GrowCtx {
-    Joint* joints;          // [K]
-    Joint* eval_joint;      // [2C] eagerly evaluated _connection_value per directed edge
-    float* heap_score;      // [2C + 1]
-    int* heap_item;         // [2C + 1]: edge | computed << 30
-    unsigned char* in_frontier;   // [2C] by pair id
-    int* new_edges;         // [2C]
-    float* score_cache;     // [NW][SC_CAP]
-    int* ctl;               // [8]: 0 heap_n, 1 n_new, 2 done
-    // the scanned components (c, x_src, y_src) of this image's CAF lists staged in shared memory
-    float* s_cxy;           // [3][LIST_SMEM_ENTRIES]
-    int* s_loff;            // [2C]: offset of list (caf_i*2 + dir) in s_cxy, or -1 if it did not fit
-    // graph (global)
-    const int* skeleton;    // [C][2]
+// A joint as the workers keep it: x, y, s of the reference's double Joint (cifcaf.hpp:21-28) only ever hold float
+// values (they come from float fields, float initial annotations or the float blend above), v is a true double.
+struct WJoint { double v; float x, y, s; int pad; };
+static_assert(sizeof(WJoint) == 24, "WJoint layout");
+
+// Image-wide read-only context of a grow CTA (graph tables and CAF lists staged in shared memory).
+struct GrowShared {
+    const int* skeleton;    // [2C]
     const int* adj_start;   // [K+1]
     const int* adj_edge;    // [<=2C] directed edge ids (2*c + dir, start = skeleton[c][dir]) in skeleton order
     const int* edge_lookup; // [2C]: caf_i*2 + forward  (first-match rule of src/cifcaf.cpp:360-373)
     const int* pair_id;     // [2C]: canonical id of the (start,end) pair for in_frontier
-    // lists
+    const float* s_cxy;     // [3][list_cap] staged (c, x_src, y_src)
+    const int* s_loff;      // [2C] offset in s_cxy or -1
+    int list_cap;
     const float* lists;     // image base: [C][2][7][hw]
     const int* list_counts; // image base: [C][2]
     int K, C, F, hw;
     GrowParams gp;
 };
 
+// One warp's private working set: the annotation being grown and its frontier (src/cifcaf.hpp:91-94).
+struct Worker {
+    WJoint* joints;         // [K]
+    WJoint* eval;           // [2C] eagerly evaluated _connection_value per directed edge
+    float* heap_score;      // [2C + 1]
+    int* heap_item;         // [2C + 1]: edge | computed << 30
+    int* new_edges;         // [2C]
+    unsigned char* in_frontier;   // [2C] by pair id
+    int heap_n, n_new;      // lane 0's registers
+};
+
+__host__ __device__ inline size_t worker_bytes(int K, int C) {
+    size_t b = sizeof(WJoint) * (size_t)K + sizeof(WJoint) * 2 * (size_t)C + (sizeof(float) + 2 * sizeof(int)) * (2 * (size_t)C + 2)
+               + 2 * (size_t)C;
+    return (b + 15) & ~(size_t)15;
+}
+
+__device__ inline void worker_init(Worker& w, unsigned char* base, int K, int C) {
+    size_t off = 0;
+    w.joints = reinterpret_cast<WJoint*>(base + off); off += sizeof(WJoint) * K;
+    w.eval = reinterpret_cast<WJoint*>(base + off); off += sizeof(WJoint) * 2 * C;
+    w.heap_score = reinterpret_cast<float*>(base + off); off += sizeof(float) * (2 * C + 2);
+    w.heap_item = reinterpret_cast<int*>(base + off); off += sizeof(int) * (2 * C + 2);
+    w.new_edges = reinterpret_cast<int*>(base + off); off += sizeof(int) * (2 * C + 2);
+    w.in_frontier = base + off;
+    w.heap_n = 0; w.n_new = 0;
+}
+
 __device__ __forceinline__ bool heap_less(float a, float b) { return a < b; }   // src/cifcaf.cpp:27-29
 
 // libstdc++ std::push_heap / std::pop_heap restated (bits/stl_heap.h), single thread.
-__device__ void heap_push(GrowCtx& g, float score, int item) {
-    int hole = g.ctl[0]++;
+__device__ void heap_push(Worker& g, float score, int item) {
+    int hole = g.heap_n++;
     int parent = (hole - 1) / 2;
     while (hole > 0 && heap_less(g.heap_score[parent], score)) {
         g.heap_score[hole] = g.heap_score[parent];
@@ -644,10 +638,10 @@ __device__ void heap_push(GrowCtx& g, float score, int item) {
     g.heap_item[hole] = item;
 }
 
-__device__ void heap_pop(GrowCtx& g, float& top_score, int& top_item) {
+__device__ void heap_pop(Worker& g, float& top_score, int& top_item) {
     top_score = g.heap_score[0];
     top_item = g.heap_item[0];
-    const int n = g.ctl[0];
+    const int n = g.heap_n;
     if (n > 1) {
         const int len = n - 1;
         const float vs = g.heap_score[len];
@@ -676,123 +670,121 @@ __device__ void heap_pop(GrowCtx& g, float& top_score, int& top_item) {
         g.heap_score[hole] = vs;
         g.heap_item[hole] = vi;
     }
-    g.ctl[0] = n - 1;
+    g.heap_n = n - 1;
 }
 
 // src/cifcaf.cpp:316-346 (single thread)
-__device__ void frontier_add_from(GrowCtx& g, int start_i) {
-    const float max_score = (float)sqrt(g.joints[start_i].v);
+__device__ void frontier_add_from(const GrowShared& g, Worker& w, int start_i) {
+    const float max_score = (float)sqrt(w.joints[start_i].v);
     for (int a = g.adj_start[start_i]; a < g.adj_start[start_i + 1]; a++) {
         const int edge = g.adj_edge[a];
         const int c = edge >> 1, dir = edge & 1;
         const int end_i = g.skeleton[2 * c + (1 - dir)];
-        if (g.joints[end_i].v > 0.0) continue;
+        if (w.joints[end_i].v > 0.0) continue;
         const int pid = g.pair_id[edge];
-        if (g.in_frontier[pid]) continue;
-        heap_push(g, max_score, edge);
-        g.in_frontier[pid] = 1;
-        g.new_edges[g.ctl[1]++] = edge;
+        if (w.in_frontier[pid]) continue;
+        heap_push(w, max_score, edge);
+        w.in_frontier[pid] = 1;
+        w.new_edges[w.n_new++] = edge;
     }
 }
 
 // src/cifcaf.cpp:349-411, one warp
-__device__ Joint warp_connection_value(GrowCtx& g, int edge, bool reverse_match_, double filter_sigmas,
-                                       float* cache, int lane) {
+__device__ WJoint warp_connection_value(const GrowShared& g, const Worker& w, int edge, bool reverse_match_,
+                                        double filter_sigmas, int lane) {
     const int c = edge >> 1, dir = edge & 1;
     const int start_i = g.skeleton[2 * c + dir];
     const int lk = g.edge_lookup[edge];
     const int caf_i = lk >> 1;
     const int forward = lk & 1;
-    const float* Lf = g.lists + ((size_t)(caf_i * 2 + (forward ? 0 : 1)) * 7) * g.hw;
-    const float* Lb = g.lists + ((size_t)(caf_i * 2 + (forward ? 1 : 0)) * 7) * g.hw;
-    const int nf = g.list_counts[caf_i * 2 + (forward ? 0 : 1)];
-    const int nb = g.list_counts[caf_i * 2 + (forward ? 1 : 0)];
-    const Joint start_j = g.joints[start_i];
     const int lif = caf_i * 2 + (forward ? 0 : 1), lib = caf_i * 2 + (forward ? 1 : 0);
+    const float* Lf = g.lists + ((size_t)lif * 7) * g.hw;
+    const float* Lb = g.lists + ((size_t)lib * 7) * g.hw;
+    const int nf = g.list_counts[lif], nb = g.list_counts[lib];
+    const WJoint sj = w.joints[start_i];
     const int of = g.s_loff[lif], ob = g.s_loff[lib];
     const float* fC = of >= 0 ? g.s_cxy + of : Lf;
-    const float* fX = of >= 0 ? g.s_cxy + LIST_SMEM_ENTRIES + of : Lf + g.hw;
-    const float* fY = of >= 0 ? g.s_cxy + 2 * LIST_SMEM_ENTRIES + of : Lf + 2 * (size_t)g.hw;
-    const float* bC = ob >= 0 ? g.s_cxy + ob : Lb;
-    const float* bX = ob >= 0 ? g.s_cxy + LIST_SMEM_ENTRIES + ob : Lb + g.hw;
-    const float* bY = ob >= 0 ? g.s_cxy + 2 * LIST_SMEM_ENTRIES + ob : Lb + 2 * (size_t)g.hw;
-    Joint new_j = warp_blend(Lf, g.hw, nf, fC, fX, fY, start_j.x, start_j.y, start_j.s, filter_sigmas, false, cache, lane);
-    if (new_j.v == 0.0) return new_j;
-    new_j.v = sqrt(new_j.v * start_j.v);
-    if (new_j.v < g.gp.keypoint_threshold || new_j.v < start_j.v * g.gp.keypoint_threshold_rel) {
-        new_j.v = 0.0;
-        return new_j;
-    }
+    const float* fX = of >= 0 ? g.s_cxy + g.list_cap + of : Lf + g.hw;
+    const float* fY = of >= 0 ? g.s_cxy + 2 * g.list_cap + of : Lf + 2 * (size_t)g.hw;
+    WJoint out; out.v = 0.0; out.x = 0.f; out.y = 0.f; out.s = 0.f; out.pad = 0;
+    const Joint nj = warp_blend(Lf, g.hw, nf, fC, fX, fY, (double)sj.x, (double)sj.y, (double)sj.s, filter_sigmas, false, lane);
+    if (nj.v == 0.0) return out;
+    double v = sqrt(nj.v * sj.v);
+    if (v < g.gp.keypoint_threshold || v < sj.v * g.gp.keypoint_threshold_rel) return out;
     if (g.gp.reverse_match && reverse_match_ && start_i < g.F) {
-        const Joint rev = warp_blend(Lb, g.hw, nb, bC, bX, bY, new_j.x, new_j.y, new_j.s, filter_sigmas, false, cache, lane);
-        if (rev.v == 0.0) { new_j.v = 0.0; return new_j; }
-        if (fabs(start_j.x - rev.x) + fabs(start_j.y - rev.y) > start_j.s) { new_j.v = 0.0; return new_j; }
+        const float* bC = ob >= 0 ? g.s_cxy + ob : Lb;
+        const float* bX = ob >= 0 ? g.s_cxy + g.list_cap + ob : Lb + g.hw;
+        const float* bY = ob >= 0 ? g.s_cxy + 2 * g.list_cap + ob : Lb + 2 * (size_t)g.hw;
+        const Joint rev = warp_blend(Lb, g.hw, nb, bC, bX, bY, nj.x, nj.y, nj.s, filter_sigmas, false, lane);
+        if (rev.v == 0.0) return out;
+        if (fabs((double)sj.x - rev.x) + fabs((double)sj.y - rev.y) > (double)sj.s) return out;
     }
-    return new_j;
+    out.v = v; out.x = (float)nj.x; out.y = (float)nj.y; out.s = (float)nj.s;
+    return out;
 }
 
-// src/cifcaf.cpp:265-313 (_grow) and :429-449 (_flood_fill when flood == true).
-// Called by the whole CTA; g.joints holds the annotation.
-__device__ void cta_grow(GrowCtx& g, bool reverse_match_, double filter_sigmas, bool flood) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __syncthreads();
-    for (int i = tid; i < 2 * g.C; i += NT) g.in_frontier[i] = 0;
-    __syncthreads();
-    if (tid == 0) {
-        g.ctl[0] = 0; g.ctl[1] = 0; g.ctl[2] = 0;
+// src/cifcaf.cpp:265-313 (_grow) and :429-449 (_flood_fill when flood == true).  One WARP grows one annotation
+// (w.joints): lane 0 drives the libstdc++-order heap, the whole warp evaluates the CAF scans behind the frontier
+// entries as they are added.  Warp-synchronous: no CTA barrier inside.
+__device__ void warp_grow(const GrowShared& g, Worker& w, bool reverse_match_, double filter_sigmas, bool flood, int lane) {
+    __syncwarp();
+    for (int i = lane; i < 2 * g.C; i += 32) w.in_frontier[i] = 0;
+    __syncwarp();
+    w.heap_n = 0; w.n_new = 0;
+    if (lane == 0) {
         for (int j = 0; j < g.K; j++) {
-            if (g.joints[j].v == 0.0) continue;
-            frontier_add_from(g, j);
+            if (w.joints[j].v == 0.0) continue;
+            frontier_add_from(g, w, j);
         }
     }
     for (;;) {
-        __syncthreads();
-        const int n_new = g.ctl[1];
+        __syncwarp();
+        const int n_new = __shfl_sync(0xffffffffu, w.n_new, 0);
         if (!flood) {
-            for (int e = warp; e < n_new; e += NW) {
-                const int edge = g.new_edges[e];
-                const Joint r = warp_connection_value(g, edge, reverse_match_, filter_sigmas,
-                                                      g.score_cache + warp * SC_CAP, lane);
-                if (lane == 0) g.eval_joint[edge] = r;
+            for (int e = 0; e < n_new; e++) {
+                const int edge = w.new_edges[e];
+                const WJoint r = warp_connection_value(g, w, edge, reverse_match_, filter_sigmas, lane);
+                if (lane == 0) w.eval[edge] = r;
             }
         }
-        __syncthreads();
-        if (tid == 0) {
-            g.ctl[1] = 0;
-            while (g.ctl[0] > 0 && g.ctl[1] == 0) {
+        __syncwarp();
+        int done = 0;
+        if (lane == 0) {
+            w.n_new = 0;
+            while (w.heap_n > 0 && w.n_new == 0) {
                 float score; int item;
-                heap_pop(g, score, item);
+                heap_pop(w, score, item);
                 const int edge = item & 0x3fffffff;
                 const bool computed = (item >> 30) & 1;
                 const int c = edge >> 1, dir = edge & 1;
                 const int start_i = g.skeleton[2 * c + dir];
                 const int end_i = g.skeleton[2 * c + (1 - dir)];
-                if (g.joints[end_i].v > 0.0) continue;
+                if (w.joints[end_i].v > 0.0) continue;
                 if (flood) {
-                    Joint nj = g.joints[start_i];
+                    WJoint nj = w.joints[start_i];
                     nj.v = 0.00001;
-                    g.joints[end_i] = nj;
-                    frontier_add_from(g, end_i);
-                    g.ctl[1] = 0;          // nothing to evaluate in flood mode
+                    w.joints[end_i] = nj;
+                    frontier_add_from(g, w, end_i);
+                    w.n_new = 0;           // nothing to evaluate in flood mode
                     continue;
                 }
-                const Joint nj = g.eval_joint[edge];
+                const WJoint nj = w.eval[edge];
                 if (!computed) {
                     if (nj.v == 0.0) continue;     // block_joints has no effect (src/cifcaf.cpp:291-295)
                     if (!g.gp.greedy) {
-                        heap_push(g, (float)nj.v, edge | (1 << 30));
+                        heap_push(w, (float)nj.v, edge | (1 << 30));
                         continue;
                     }
                 }
-                g.joints[end_i] = nj;
-                frontier_add_from(g, end_i);
+                w.joints[end_i] = nj;
+                frontier_add_from(g, w, end_i);
             }
-            g.ctl[2] = (g.ctl[0] == 0 && g.ctl[1] == 0) ? 1 : 0;
+            done = (w.heap_n == 0 && w.n_new == 0) ? 1 : 0;
         }
-        __syncthreads();
-        if (g.ctl[2]) break;
+        done = __shfl_sync(0xffffffffu, done, 0);
+        if (done) break;
     }
-    __syncthreads();
+    __syncwarp();
 }
 
 // Occupancy (src/occupancy.cpp:13-43) on a byte map with epoch tags.
@@ -803,81 +795,135 @@ struct Occ {
     unsigned char tag;
 };
 
+__device__ __forceinline__ void occ_cell(const Occ& o, double x, double y, long long& xi, long long& yi) {
+    if (o.reduction != 1.0) { x /= o.reduction; y /= o.reduction; }
+    xi = clamp_ll((long long)x, 0, o.Wo - 1);
+    yi = clamp_ll((long long)y, 0, o.Ho - 1);
+}
+
 __device__ __forceinline__ bool occ_get(const Occ& o, long long f, double x, double y) {
     if (f >= o.F) return true;
-    if (o.reduction != 1.0) { x /= o.reduction; y /= o.reduction; }
-    const long long xi = clamp_ll((long long)x, 0, o.Wo - 1);
-    const long long yi = clamp_ll((long long)y, 0, o.Ho - 1);
+    long long xi, yi;
+    occ_cell(o, x, y, xi, yi);
     return reinterpret_cast<const volatile unsigned char*>(o.map)[((size_t)f * o.Ho + yi) * o.Wo + xi] == o.tag;
 }
 
-// one warp fills the box
-__device__ __forceinline__ void occ_set_warp(const Occ& o, long long f, double x, double y, double sigma, int lane) {
+__device__ __forceinline__ void occ_box(const Occ& o, double x, double y, double sigma,
+                                        long long& minx, long long& miny, long long& maxx, long long& maxy) {
     if (o.reduction != 1.0) {
         x /= o.reduction; y /= o.reduction;
         sigma = fmax(o.min_scale_reduced, sigma / o.reduction);
     }
-    const long long minx = clamp_ll((long long)(x - sigma), 0, o.Wo - 1);
-    const long long miny = clamp_ll((long long)(y - sigma), 0, o.Ho - 1);
-    const long long maxx = clamp_ll((long long)(x + sigma), minx + 1, o.Wo);
-    const long long maxy = clamp_ll((long long)(y + sigma), miny + 1, o.Ho);
+    minx = clamp_ll((long long)(x - sigma), 0, o.Wo - 1);
+    miny = clamp_ll((long long)(y - sigma), 0, o.Ho - 1);
+    maxx = clamp_ll((long long)(x + sigma), minx + 1, o.Wo);
+    maxy = clamp_ll((long long)(y + sigma), miny + 1, o.Ho);
+}
+
+// one warp fills the box
+__device__ __forceinline__ void occ_set_warp(const Occ& o, long long f, double x, double y, double sigma, int lane) {
+    long long minx, miny, maxx, maxy;
+    occ_box(o, x, y, sigma, minx, miny, maxx, maxy);
     const int bw = (int)(maxx - minx), bh = (int)(maxy - miny);
     volatile unsigned char* base = o.map + ((size_t)f * o.Ho + miny) * o.Wo + minx;
     for (int k = lane; k < bw * bh; k += 32) base[(size_t)(k / bw) * o.Wo + (k % bw)] = o.tag;
 }
 
-__device__ void grow_ctx_init(GrowCtx& g, unsigned char* smem, int K, int C) {
-    size_t off = 0;
-    g.joints = reinterpret_cast<Joint*>(smem + off); off += sizeof(Joint) * K;
-    g.eval_joint = reinterpret_cast<Joint*>(smem + off); off += sizeof(Joint) * 2 * C;
-    g.score_cache = reinterpret_cast<float*>(smem + off); off += sizeof(float) * NW * SC_CAP;
-    g.heap_score = reinterpret_cast<float*>(smem + off); off += sizeof(float) * (2 * C + 2);
-    g.heap_item = reinterpret_cast<int*>(smem + off); off += sizeof(int) * (2 * C + 2);
-    g.new_edges = reinterpret_cast<int*>(smem + off); off += sizeof(int) * (2 * C + 2);
-    g.ctl = reinterpret_cast<int*>(smem + off); off += sizeof(int) * 8;
-    g.s_loff = reinterpret_cast<int*>(smem + off); off += sizeof(int) * (2 * C + 2);
-    g.s_cxy = reinterpret_cast<float*>(smem + off); off += sizeof(float) * 3 * LIST_SMEM_ENTRIES;
-    g.in_frontier = smem + off;
+// would occupancy.get(f, x, y) see a cell that occupancy.set of joint j (field f) marks?  (exact box arithmetic)
+__device__ __forceinline__ bool occ_joint_covers(const Occ& o, const WJoint& j, double x, double y) {
+    if (j.v == 0.0) return false;
+    long long xi, yi, minx, miny, maxx, maxy;
+    occ_cell(o, x, y, xi, yi);
+    occ_box(o, (double)j.x, (double)j.y, (double)j.s, minx, miny, maxx, maxy);
+    return xi >= minx && xi < maxx && yi >= miny && yi < maxy;
 }
 
-// Copy the scanned components of the image's CAF lists into shared memory (whole CTA; lists that do not fit stay
-// in global memory).  Must be called after g.lists / g.list_counts are set.
-__device__ void grow_stage_lists(GrowCtx& g) {
-    if (threadIdx.x == 0) {
-        int run = 0;
-        for (int li = 0; li < 2 * g.C; li++) {
-            const int n = g.list_counts[li];
-            if (run + n <= LIST_SMEM_ENTRIES) { g.s_loff[li] = run; run += n; }
-            else g.s_loff[li] = -1;
-        }
-    }
-    __syncthreads();
-    for (int li = 0; li < 2 * g.C; li++) {
-        const int off = g.s_loff[li];
-        if (off < 0) continue;
-        const int n = g.list_counts[li];
-        const float* L = g.lists + ((size_t)li * 7) * g.hw;
-        for (int i = threadIdx.x; i < n; i += NT) {
-            g.s_cxy[off + i] = L[i];
-            g.s_cxy[LIST_SMEM_ENTRIES + off + i] = L[g.hw + i];
-            g.s_cxy[2 * LIST_SMEM_ENTRIES + off + i] = L[2 * (size_t)g.hw + i];
-        }
-    }
-    __syncthreads();
+constexpr int GROW_MAX_WORKERS = 16;       // warps per grow CTA == annotations grown concurrently per image
+
+struct GrowLayout { int workers, list_cap; size_t smem; };
+
+// shared memory plan of a grow CTA: graph tables | list offsets | staged lists | per-warp workers | control
+__host__ __device__ inline size_t grow_fixed_bytes(int K, int C) {
+    return (((size_t)(8 * C + K + 1 + 2 * C + 8) * sizeof(int)) + 15) & ~(size_t)15;
 }
 
-size_t grow_smem_bytes(int K, int C) {
-    return sizeof(Joint) * K + sizeof(Joint) * 2 * C + sizeof(float) * NW * SC_CAP
-           + (sizeof(float) + 2 * sizeof(int)) * (2 * C + 2) + sizeof(int) * 8 + sizeof(int) * (2 * C + 2)
-           + sizeof(float) * 3 * LIST_SMEM_ENTRIES + 2 * C + 16;
+inline GrowLayout plan_grow(int K, int C) {
+    const size_t budget = 200 * 1024, fixed = grow_fixed_bytes(K, C) + 64 * sizeof(int) + 256;
+    const size_t wb = worker_bytes(K, C);
+    GrowLayout l;
+    l.list_cap = LIST_SMEM_ENTRIES;
+    size_t lists = sizeof(float) * 3 * (size_t)l.list_cap;
+    if (fixed + lists + 4 * wb > budget) { l.list_cap = LIST_SMEM_ENTRIES / 2; lists /= 2; }
+    long w = (long)((budget - fixed - lists) / wb);
+    l.workers = (int)std::max(1L, std::min((long)GROW_MAX_WORKERS, w));
+    l.smem = fixed + lists + (size_t)l.workers * wb;
+    return l;
 }
 
 struct Graph {
     const int* skeleton; const int* adj_start; const int* adj_edge; const int* edge_lookup; const int* pair_id;
 };
 
-// Seed loop of CifCaf::call_with_initial_annotations (src/cifcaf.cpp:173-231).  One CTA per image.
-__global__ void __launch_bounds__(NT) k_grow(Dims d, Graph gr, GrowParams gp,
+// carve the CTA's shared memory, stage the graph tables and the scanned list components; whole CTA
+__device__ void grow_shared_init(GrowShared& g, unsigned char* smem, const Graph& gr, const Dims& d, int list_cap,
+                                 const float* lists, const int* list_counts, const GrowParams& gp,
+                                 unsigned char** workers_base, int** ctl) {
+    const int K = d.K, C = d.C;
+    int* tab = reinterpret_cast<int*>(smem);
+    int* s_skel = tab;                    // 2C
+    int* s_adj_start = s_skel + 2 * C;    // K + 1
+    int* s_adj_edge = s_adj_start + K + 1;   // 2C
+    int* s_lookup = s_adj_edge + 2 * C;   // 2C
+    int* s_pair = s_lookup + 2 * C;       // 2C
+    int* s_loff = s_pair + 2 * C;         // 2C
+    int* s_ctl = s_loff + 2 * C;          // 8
+    unsigned char* p = smem + grow_fixed_bytes(K, C);
+    float* s_cxy = reinterpret_cast<float*>(p);
+    p += sizeof(float) * 3 * (size_t)list_cap;
+    *workers_base = p;
+    *ctl = s_ctl;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+        s_skel[i] = gr.skeleton[i]; s_lookup[i] = gr.edge_lookup[i]; s_pair[i] = gr.pair_id[i];
+    }
+    for (int i = threadIdx.x; i <= K; i += blockDim.x) s_adj_start[i] = gr.adj_start[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < s_adj_start[K]; i += blockDim.x) s_adj_edge[i] = gr.adj_edge[i];
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int li = 0; li < 2 * C; li++) {
+            const int n = list_counts[li];
+            if (run + n <= list_cap) { s_loff[li] = run; run += n; }
+            else s_loff[li] = -1;
+        }
+    }
+    __syncthreads();
+    for (int li = 0; li < 2 * C; li++) {
+        const int off = s_loff[li];
+        if (off < 0) continue;
+        const int n = list_counts[li];
+        const float* L = lists + ((size_t)li * 7) * d.hw;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            s_cxy[off + i] = L[i];
+            s_cxy[list_cap + off + i] = L[d.hw + i];
+            s_cxy[2 * list_cap + off + i] = L[2 * (size_t)d.hw + i];
+        }
+    }
+    g.skeleton = s_skel; g.adj_start = s_adj_start; g.adj_edge = s_adj_edge; g.edge_lookup = s_lookup; g.pair_id = s_pair;
+    g.s_cxy = s_cxy; g.s_loff = s_loff; g.list_cap = list_cap;
+    g.lists = lists; g.list_counts = list_counts;
+    g.K = K; g.C = C; g.F = d.F; g.hw = d.hw; g.gp = gp;
+    __syncthreads();
+}
+
+// Seed loop of CifCaf::call_with_initial_annotations (src/cifcaf.cpp:173-231).  One CTA per image, one WARP per
+// annotation in flight.  The reference is sequential only through the occupancy map: a seed is skipped if an earlier
+// annotation covers it, and _grow itself reads nothing but the seed and the (static) CAF lists.  So every round
+//   1. selects the next W seeds, in order, that the occupancy map does not cover yet,
+//   2. grows all W speculatively, one per warp,
+//   3. commits them in seed order: seed i is dropped iff a joint of an annotation committed earlier IN THIS ROUND
+//      covers it (the same box arithmetic as Occupancy::set/get), else it marks the map and is stored,
+// which yields exactly the annotations, in exactly the order, of the sequential loop.
+__global__ void __launch_bounds__(32 * GROW_MAX_WORKERS) k_grow(Dims d, Graph gr, GrowParams gp, int list_cap,
                                              const int* __restrict__ seed_f, const float4* __restrict__ seed_vxys,
                                              const int* __restrict__ n_seeds,
                                              const float* __restrict__ lists, const int* __restrict__ list_counts,
@@ -887,16 +933,21 @@ __global__ void __launch_bounds__(NT) k_grow(Dims d, Graph gr, GrowParams gp,
                                              Joint* __restrict__ anns, long long* __restrict__ ann_ids,
                                              int* __restrict__ n_anns, int* __restrict__ flags) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ int s_next;
+    __shared__ int s_sel[GROW_MAX_WORKERS];       // seed index (or initial-annotation index) per worker
+    __shared__ int s_slot[GROW_MAX_WORKERS];      // output slot, or -1 if dropped
+    __shared__ int s_wc[GROW_MAX_WORKERS];
+    __shared__ int s_nsel, s_ptr, s_nann, s_over;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    GrowCtx g;
-    grow_ctx_init(g, smem, d.K, d.C);
-    g.skeleton = gr.skeleton; g.adj_start = gr.adj_start; g.adj_edge = gr.adj_edge;
-    g.edge_lookup = gr.edge_lookup; g.pair_id = gr.pair_id;
-    g.lists = lists + ((size_t)b * d.C * 2 * 7) * d.hw;
-    g.list_counts = list_counts + (size_t)b * d.C * 2;
-    g.K = d.K; g.C = d.C; g.F = d.F; g.hw = d.hw; g.gp = gp;
-    grow_stage_lists(g);
+    const int W = blockDim.x >> 5;
+    GrowShared g;
+    unsigned char* workers_base; int* ctl;
+    grow_shared_init(g, smem, gr, d, list_cap, lists + ((size_t)b * d.C * 2 * 7) * d.hw,
+                     list_counts + (size_t)b * d.C * 2, gp, &workers_base, &ctl);
+    (void)ctl;
+    Worker w;
+    worker_init(w, workers_base + (size_t)warp * worker_bytes(d.K, d.C), d.K, d.C);
+    // every warp can read every worker's joints at commit time
+    auto joints_of = [&](int wk) { return reinterpret_cast<const WJoint*>(workers_base + (size_t)wk * worker_bytes(d.K, d.C)); };
 
     Occ occ;
     occ.map = occ_map + (size_t)b * d.F * d.Ho * d.Wo;
@@ -906,95 +957,152 @@ __global__ void __launch_bounds__(NT) k_grow(Dims d, Graph gr, GrowParams gp,
 
     Joint* my_anns = anns + (size_t)b * d.max_ann * d.K;
     long long* my_ids = ann_ids + (size_t)b * d.max_ann;
-    int n_ann = 0;
-    bool overflow = false;
-
-    auto finish_annotation = [&](long long id) {
-        // occupancy.set for every joint (src/cifcaf.cpp:196-200, 225-229) + store
-        __syncthreads();
-        for (int of = warp; of < d.F && of < d.K; of += NW) {
-            const Joint j = g.joints[of];
-            if (j.v == 0.0) continue;
-            occ_set_warp(occ, of, j.x, j.y, j.s, lane);
-        }
-        for (int k = tid; k < d.K; k += NT) my_anns[(size_t)n_ann * d.K + k] = g.joints[k];
-        if (tid == 0) my_ids[n_ann] = id;
-        n_ann++;
-        __syncthreads();
-    };
-
-    // initial annotations (src/cifcaf.cpp:177-202)
-    const int n_init = (init_ann != nullptr && init_counts != nullptr) ? init_counts[b] : 0;
-    for (int a = 0; a < n_init; a++) {
-        if (n_ann >= d.max_ann) { overflow = true; break; }
-        __syncthreads();
-        for (int k = tid; k < d.K; k += NT) {
-            const float* s = init_ann + (((size_t)b * init_cap + a) * d.K + k) * 4;
-            Joint j; j.v = s[0]; j.x = s[1]; j.y = s[2]; j.s = s[3];
-            g.joints[k] = j;
-        }
-        cta_grow(g, true, 1.0, false);
-        finish_annotation(init_ids[(size_t)b * init_cap + a]);
-    }
-
     const int ns = n_seeds[b];
     const int* sf = seed_f + (size_t)b * d.F * d.hw;
     const float4* sv = seed_vxys + (size_t)b * d.F * d.hw;
-    int ptr = 0;
-    while (ptr < ns && !overflow) {
-        __syncthreads();
-        if (tid == 0) s_next = INT_MAX;
-        __syncthreads();
-        const int idx = ptr + tid;
-        if (idx < ns) {
-            const float4 s = sv[idx];
-            if (!occ_get(occ, sf[idx], (double)s.y, (double)s.z)) atomicMin(&s_next, idx);
+    const int n_init = (init_ann != nullptr && init_counts != nullptr) ? init_counts[b] : 0;
+    if (tid == 0) { s_ptr = 0; s_nann = 0; s_over = 0; }
+    __syncthreads();
+
+    // store + occupancy marks of the annotation this warp grew (src/cifcaf.cpp:196-201, 225-230)
+    auto commit_mine = [&](int slot, long long id) {
+        for (int of = 0; of < d.F && of < d.K; of++) {
+            const WJoint j = w.joints[of];
+            if (j.v == 0.0) continue;
+            occ_set_warp(occ, of, (double)j.x, (double)j.y, (double)j.s, lane);
+        }
+        for (int k = lane; k < d.K; k += 32) {
+            const WJoint j = w.joints[k];
+            Joint o; o.v = j.v; o.x = (double)j.x; o.y = (double)j.y; o.s = (double)j.s;
+            my_anns[(size_t)slot * d.K + k] = o;
+        }
+        if (lane == 0) my_ids[slot] = id;
+    };
+
+    // ---- initial annotations (src/cifcaf.cpp:177-202): always kept, W at a time
+    for (int a0 = 0; a0 < n_init && !s_over; a0 += W) {
+        const int a = a0 + warp;
+        const bool mine = a < n_init && s_nann + warp < d.max_ann;
+        if (mine) {
+            for (int k = lane; k < d.K; k += 32) {
+                const float* s = init_ann + (((size_t)b * init_cap + a) * d.K + k) * 4;
+                WJoint j; j.v = (double)s[0]; j.x = s[1]; j.y = s[2]; j.s = s[3]; j.pad = 0;
+                w.joints[k] = j;
+            }
+            warp_grow(g, w, true, 1.0, false, lane);
+            commit_mine(s_nann + warp, init_ids[(size_t)b * init_cap + a]);
         }
         __syncthreads();
-        const int next = s_next;
-        if (next == INT_MAX) { ptr += NT; continue; }
-        ptr = next + 1;
-        if (n_ann >= d.max_ann) { overflow = true; break; }
-        const float4 s = sv[next];
-        const int f = sf[next];
-        for (int k = tid; k < d.K; k += NT) {
-            Joint j; j.v = 0.0; j.x = 0.0; j.y = 0.0; j.s = 0.0;
-            if (k == f) { j.v = (double)s.x; j.x = (double)s.y; j.y = (double)s.z; j.s = (double)s.w; }
-            g.joints[k] = j;
+        if (tid == 0) {
+            const int n = min(W, n_init - a0);
+            if (s_nann + n > d.max_ann) { s_over = 1; s_nann = d.max_ann; } else s_nann += n;
         }
-        cta_grow(g, true, 1.0, false);
-        finish_annotation(-1);
+        __syncthreads();
+    }
+
+    // ---- seeds
+    while (!s_over) {
+        // 1. the next W seeds (index >= s_ptr) the occupancy map does not cover
+        if (tid == 0) s_nsel = 0;
+        __syncthreads();
+        int ptr = s_ptr;
+        while (ptr < ns) {
+            const int idx = ptr + tid;
+            bool flag = false;
+            if (idx < ns) {
+                const float4 s = sv[idx];
+                flag = !occ_get(occ, sf[idx], (double)s.y, (double)s.z);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, flag);
+            if (lane == 0) s_wc[warp] = __popc(m);
+            __syncthreads();
+            int before = s_nsel, total = 0;
+            for (int w2 = 0; w2 < W; w2++) { if (w2 < warp) before += s_wc[w2]; total += s_wc[w2]; }
+            const int pos = before + __popc(m & ((1u << lane) - 1u));
+            if (flag && pos < W) s_sel[pos] = idx;
+            __syncthreads();
+            if (tid == 0) s_nsel = min(W, s_nsel + total);
+            __syncthreads();
+            if (s_nsel == W) break;
+            ptr += blockDim.x;
+        }
+        const int n_sel = s_nsel;
+        if (n_sel == 0) break;
+        // 2. grow, one warp per selected seed
+        if (warp < n_sel) {
+            const int si = s_sel[warp];
+            const float4 s = sv[si];
+            const int f = sf[si];
+            for (int k = lane; k < d.K; k += 32) {
+                WJoint j; j.v = 0.0; j.x = 0.f; j.y = 0.f; j.s = 0.f; j.pad = 0;
+                if (k == f) { j.v = (double)s.x; j.x = s.y; j.y = s.z; j.s = s.w; }
+                w.joints[k] = j;
+            }
+            warp_grow(g, w, true, 1.0, false, lane);
+        }
+        __syncthreads();
+        // 3. commit decisions in seed order (thread 0; W <= 16 seeds x earlier kept annotations)
+        if (tid == 0) {
+            int n_keep = 0;
+            for (int i = 0; i < n_sel; i++) {
+                const int si = s_sel[i];
+                const float4 s = sv[si];
+                const int f = sf[si];
+                bool covered = false;
+                for (int a = 0; a < i && !covered; a++) {
+                    if (s_slot[a] < 0) continue;
+                    if (f < d.F && f < d.K) covered = occ_joint_covers(occ, joints_of(a)[f], (double)s.y, (double)s.z);
+                }
+                if (covered) { s_slot[i] = -1; continue; }
+                if (s_nann + n_keep >= d.max_ann) { s_over = 1; s_slot[i] = -1; continue; }
+                s_slot[i] = s_nann + n_keep;
+                n_keep++;
+            }
+            s_nann += n_keep;
+            s_ptr = s_sel[n_sel - 1] + 1;
+        }
+        __syncthreads();
+        if (warp < n_sel && s_slot[warp] >= 0) commit_mine(s_slot[warp], -1);
+        __syncthreads();          // occupancy marks visible to the next selection
+        if (n_sel < W) break;     // the seed list is exhausted
     }
     if (tid == 0) {
-        n_anns[b] = n_ann;
-        flags[b] = overflow ? 1 : 0;
+        n_anns[b] = s_nann;
+        flags[b] = s_over ? 1 : 0;
     }
 }
 
-// _force_complete + _flood_fill (src/cifcaf.cpp:233-236, 414-449); lists were
-// refilled at force_complete_caf_th by k_caf_scored.
-__global__ void __launch_bounds__(NT) k_force_complete(Dims d, Graph gr, GrowParams gp,
+// _force_complete + _flood_fill (src/cifcaf.cpp:233-236, 414-449); lists were refilled at force_complete_caf_th by
+// k_caf_scored.  Annotations are independent here: one warp each, W at a time.
+__global__ void __launch_bounds__(32 * GROW_MAX_WORKERS) k_force_complete(Dims d, Graph gr, GrowParams gp, int list_cap,
                                                        const float* __restrict__ lists,
                                                        const int* __restrict__ list_counts,
                                                        Joint* __restrict__ anns, const int* __restrict__ n_anns) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int b = blockIdx.x, tid = threadIdx.x;
-    GrowCtx g;
-    grow_ctx_init(g, smem, d.K, d.C);
-    g.skeleton = gr.skeleton; g.adj_start = gr.adj_start; g.adj_edge = gr.adj_edge;
-    g.edge_lookup = gr.edge_lookup; g.pair_id = gr.pair_id;
-    g.lists = lists + ((size_t)b * d.C * 2 * 7) * d.hw;
-    g.list_counts = list_counts + (size_t)b * d.C * 2;
-    g.K = d.K; g.C = d.C; g.F = d.F; g.hw = d.hw; g.gp = gp;
-    grow_stage_lists(g);
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int W = blockDim.x >> 5;
+    GrowShared g;
+    unsigned char* workers_base; int* ctl;
+    grow_shared_init(g, smem, gr, d, list_cap, lists + ((size_t)b * d.C * 2 * 7) * d.hw,
+                     list_counts + (size_t)b * d.C * 2, gp, &workers_base, &ctl);
+    (void)ctl;
+    Worker w;
+    worker_init(w, workers_base + (size_t)warp * worker_bytes(d.K, d.C), d.K, d.C);
     Joint* my_anns = anns + (size_t)b * d.max_ann * d.K;
     const int n = n_anns[b];
-    for (int a = 0; a < n; a++) {
-        __syncthreads();
-        for (int k = tid; k < d.K; k += NT) g.joints[k] = my_anns[(size_t)a * d.K + k];
-        cta_grow(g, false, 4.0, false);
-        cta_grow(g, false, 4.0, true);     // per-annotation order is equivalent: annotations are independent here
-        for (int k = tid; k < d.K; k += NT) my_anns[(size_t)a * d.K + k] = g.joints[k];
+    for (int a = warp; a < n; a += W) {
+        for (int k = lane; k < d.K; k += 32) {
+            const Joint j = my_anns[(size_t)a * d.K + k];
+            WJoint o; o.v = j.v; o.x = (float)j.x; o.y = (float)j.y; o.s = (float)j.s; o.pad = 0;
+            w.joints[k] = o;
+        }
+        warp_grow(g, w, false, 4.0, false, lane);
+        warp_grow(g, w, false, 4.0, true, lane);
+        for (int k = lane; k < d.K; k += 32) {
+            const WJoint j = w.joints[k];
+            Joint o; o.v = j.v; o.x = (double)j.x; o.y = (double)j.y; o.s = (double)j.s;
+            my_anns[(size_t)a * d.K + k] = o;
+        }
     }
 }
 
@@ -1134,8 +1242,7 @@ __global__ void __launch_bounds__(NT) k_pack(Dims d, const float4* __restrict__ 
 
 __global__ void k_blend_single(const float* __restrict__ L, int n, double x, double y, double s,
                                double filter_sigmas, int only_max, double* __restrict__ out) {
-    __shared__ float cache[SC_CAP];
-    const Joint j = warp_blend(L, n, n, L, L + n, L + 2 * (size_t)n, x, y, s, filter_sigmas, only_max != 0, cache,
+    const Joint j = warp_blend(L, n, n, L, L + n, L + 2 * (size_t)n, x, y, s, filter_sigmas, only_max != 0,
                                threadIdx.x & 31);
     if (threadIdx.x == 0) { out[0] = j.x; out[1] = j.y; out[2] = j.s; out[3] = j.v; }
 }
@@ -1184,6 +1291,7 @@ struct pifpaf_decoder {
     int* d_in_init_count = nullptr; int in_init_cap = 0;
     // pinned staging
     cudaStream_t own_stream = nullptr;
+    GrowLayout grow{};                // warps (annotations in flight) per image and shared-memory plan of k_grow
     unsigned epoch = 1;               // occupancy tags: epoch (seed loop), epoch+1 (NMS)
     Dims last{};
     bool has_last = false;
@@ -1370,9 +1478,9 @@ int pifpaf_decoder_create(pifpaf_decoder_t** out, int32_t device, int32_t n_keyp
     ALLOC(dec->d_in_init, A * K * 4); ALLOC(dec->d_in_init_ids, A); ALLOC(dec->d_in_init_count, 1);
     TRY_D(cudaStreamCreateWithFlags(&dec->own_stream, cudaStreamNonBlocking));
 
-    const size_t gs = grow_smem_bytes(K, C);
-    TRY_D(cudaFuncSetAttribute(k_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs));
-    TRY_D(cudaFuncSetAttribute(k_force_complete, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs));
+    dec->grow = plan_grow(K, C);
+    TRY_D(cudaFuncSetAttribute(k_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec->grow.smem));
+    TRY_D(cudaFuncSetAttribute(k_force_complete, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec->grow.smem));
     const size_t ns = (sizeof(double) + 2 * sizeof(int)) * A + 16;
     TRY_D(cudaFuncSetAttribute(k_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ns));
     const size_t ss = sizeof(int) * (((size_t)F + 1 + 3) / 4 * 4 + 256 + 256 + 8) + 2 * 32 * 256 + 16;
@@ -1457,8 +1565,9 @@ int pifpaf_decoder_decode_device(pifpaf_decoder_t* dec, const float* cif_dev, co
                                                     dec->d_lists, dec->d_list_counts);
         PIFPAF_LAUNCH_CHECK();
     }
-    const size_t gs = grow_smem_bytes(d.K, d.C);
-    k_grow<<<d.B, NT, gs, st>>>(d, gr, gp, dec->d_seed_f, dec->d_seed_vxys, dec->d_n_seeds, dec->d_lists,
+    const size_t gs = dec->grow.smem;
+    const int grow_threads = 32 * dec->grow.workers;
+    k_grow<<<d.B, grow_threads, gs, st>>>(d, gr, gp, dec->grow.list_cap, dec->d_seed_f, dec->d_seed_vxys, dec->d_n_seeds, dec->d_lists,
                                 dec->d_list_counts, dec->d_occ, tag_seed, init_ann_dev,
                                 reinterpret_cast<const long long*>(init_ids_dev), init_counts_dev, init_cap,
                                 dec->d_anns, dec->d_ann_ids, dec->d_n_anns, dec->d_flags);
@@ -1469,7 +1578,7 @@ int pifpaf_decoder_decode_device(pifpaf_decoder_t* dec, const float* cif_dev, co
         k_caf_scored<<<dim3(d.C, d.B), NT, 0, st>>>(caf_dev, d, dec->d_skeleton, dec->d_cifhr, dec->d_tile_epoch,
                                                     hr_epoch, p.cifhr_revision, th, 0.1, p.caf_ablation_no_rescore, dec->d_lists, dec->d_list_counts);
         PIFPAF_LAUNCH_CHECK();
-        k_force_complete<<<d.B, NT, gs, st>>>(d, gr, gp, dec->d_lists, dec->d_list_counts, dec->d_anns, dec->d_n_anns);
+        k_force_complete<<<d.B, grow_threads, gs, st>>>(d, gr, gp, dec->grow.list_cap, dec->d_lists, dec->d_list_counts, dec->d_anns, dec->d_n_anns);
         PIFPAF_LAUNCH_CHECK();
     }
     const size_t ns = (sizeof(double) + 2 * sizeof(int)) * (size_t)d.max_ann + 16;

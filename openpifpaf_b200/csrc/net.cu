@@ -1221,8 +1221,11 @@ __global__ void __launch_bounds__(256) k_input_conv(InConvArgs a) {
     // (bit-identical to torchvision's ToTensor + Normalize on the host) -> one byte load + one table read per sample
     float* s_lut = s_w + n_w + C;                     // [3][256]
     if (U8)
-        for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x)
-            s_lut[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)(i & 255), 255.f), a.mean[i >> 8]), a.stdev[i >> 8]);
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+            const float x = __fdiv_rn((float)i, 255.f);
+#pragma unroll
+            for (int c = 0; c < 3; c++) s_lut[c * 256 + i] = __fdiv_rn(__fsub_rn(x, a.mean[c]), a.stdev[c]);
+        }
     __syncthreads();
     const long long total = (long long)a.B * a.Hout * a.Wout;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -1232,25 +1235,36 @@ __global__ void __launch_bounds__(256) k_input_conv(InConvArgs a) {
         const int oy = (int)(p % a.Hout);
         const int b = (int)(p / a.Hout);
         float in[TAPS];
-#pragma unroll
-        for (int ci = 0; ci < 3; ci++) {
-            const float* plane = a.in + ((size_t)b * 3 + ci) * a.Hin * a.Win;
+        if (U8) {
+            // HWC bytes: the three channels of a pixel are adjacent; one row pointer per ky, one pixel pointer per kx
 #pragma unroll
             for (int ky = 0; ky < KS; ky++) {
                 const int iy = oy * a.stride - a.pad + ky;
+                const bool oky = iy >= 0 && iy < a.Hin;
+                const uint8_t* rowp = a.in_u8 + ((size_t)b * a.Hin + (oky ? iy : 0)) * a.Win * 3;
 #pragma unroll
                 for (int kx = 0; kx < KS; kx++) {
                     const int ix = ox * a.stride - a.pad + kx;
-                    const bool ok = iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win;
-                    float v = 0.f;
-                    if (ok) {
-                        if (U8) {
-                            v = s_lut[ci * 256 + __ldg(a.in_u8 + (((size_t)b * a.Hin + iy) * a.Win + ix) * 3 + ci)];
-                        } else {
-                            v = __ldg(plane + (size_t)iy * a.Win + ix);
-                        }
+                    const bool ok = oky && ix >= 0 && ix < a.Win;
+                    const uint8_t* px = rowp + (ok ? ix : 0) * 3;
+#pragma unroll
+                    for (int ci = 0; ci < 3; ci++)
+                        in[(ci * KS + ky) * KS + kx] = ok ? s_lut[ci * 256 + __ldg(px + ci)] : 0.f;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int ci = 0; ci < 3; ci++) {
+                const float* plane = a.in + ((size_t)b * 3 + ci) * a.Hin * a.Win;
+#pragma unroll
+                for (int ky = 0; ky < KS; ky++) {
+                    const int iy = oy * a.stride - a.pad + ky;
+#pragma unroll
+                    for (int kx = 0; kx < KS; kx++) {
+                        const int ix = ox * a.stride - a.pad + kx;
+                        const bool ok = iy >= 0 && iy < a.Hin && ix >= 0 && ix < a.Win;
+                        in[(ci * KS + ky) * KS + kx] = ok ? __ldg(plane + (size_t)iy * a.Win + ix) : 0.f;
                     }
-                    in[(ci * KS + ky) * KS + kx] = v;
                 }
             }
         }
