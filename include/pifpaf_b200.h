@@ -166,6 +166,51 @@ int pifpaf_grow_connection_blend(const float* caf, int64_t n, double x, double y
 
 
 /* ------------------------------------------------------------------------ */
+/* CifDet decoder.  Replaces torch.classes.openpifpaf_decoder.CifDet
+ * (csrc/src/cifdet.cpp:24-80, module.cpp:57-62; CifDetHr csrc/src/cif_hr.cpp:124-150, CifDetSeeds
+ * csrc/src/cif_seeds.cpp:69-90,117-139) and, with params.nms != 0, the post-processing of the reference's Python
+ * wrapper (decoder/cifdet.py:55-64: torchvision batched_nms / nms, score suppression, instance threshold).       */
+typedef struct pifpaf_cifdet pifpaf_cifdet_t;
+
+typedef struct {
+    int64_t cifhr_neighbors;           /* CifHr::neighbors [16]  csrc/src/cif_hr.cpp:13 */
+    double cifhr_threshold;            /* CifHr::threshold [0.3] csrc/src/cif_hr.cpp:14 */
+    double seed_threshold;             /* CifDetSeeds::threshold [0.2] csrc/src/cif_seeds.cpp:12 */
+    double occ_reduction;              /* Occupancy(2.0, 4.0): include/openpifpaf/decoder/cifdet.hpp:40 */
+    double occ_min_scale;
+    double cifhr_revision;             /* [1.0] revision of a fresh instance's first call */
+    int64_t max_detections_before_nms; /* CifDet::max_detections_before_nms [120] csrc/src/cifdet.cpp:16 */
+    int32_t nms;                       /* 0: raw output of CifDet::call; 1: + decoder/cifdet.py:55-64 */
+    int32_t nms_by_category;           /* CifDet.nms_by_category [1] decoder/cifdet.py:20 */
+    double iou_threshold;              /* [0.5]  decoder/cifdet.py:17 */
+    double suppression;                /* [0.1]  decoder/cifdet.py:22 */
+    double instance_threshold;         /* [0.15] decoder/cifdet.py:18 */
+} pifpaf_cifdet_params_t;
+
+int pifpaf_cifdet_default_params(pifpaf_cifdet_params_t* params);
+
+/* Capacities like pifpaf_decoder_create; max_detections bounds max_detections_before_nms. */
+int pifpaf_cifdet_create(pifpaf_cifdet_t** out, int32_t device, int32_t n_categories,
+                         int32_t max_batch, int32_t max_h, int32_t max_w, int32_t max_stride,
+                         int32_t max_detections);
+void pifpaf_cifdet_destroy(pifpaf_cifdet_t* det);
+
+/* Batched decode of DEVICE-resident fields [B][F][6][h][w] f32 (intensity, confidence, x, y, w, h), enqueued on
+ * `stream`.  Results stay on the device until pifpaf_cifdet_fetch(). */
+int pifpaf_cifdet_decode_device(pifpaf_cifdet_t* det, const float* field_dev, int32_t batch, int32_t h, int32_t w,
+                                int32_t stride, const pifpaf_cifdet_params_t* params, void* stream);
+
+/* counts [B]; records [B][cap][8] f32 per detection: category (1-based, as a float), score, x1, y1, x2, y2
+ * (csrc/src/cifdet.cpp:61-63), score after NMS suppression, kept flag (1.0 = score after NMS > instance
+ * threshold); without params.nms the last two are (score, 1.0).  Synchronises `stream`. */
+int pifpaf_cifdet_fetch(pifpaf_cifdet_t* det, int32_t* counts, float* records, int32_t cap, void* stream);
+
+/* Single image, HOST field [F][6][h][w]: the call the reference's binding makes (CifDet::call). */
+int pifpaf_cifdet_call(pifpaf_cifdet_t* det, const float* field, int32_t stride, int32_t h, int32_t w,
+                       const pifpaf_cifdet_params_t* params, float* records, int32_t cap, int32_t* n_out);
+
+
+/* ------------------------------------------------------------------------ */
 /* Network forward: backbone + CompositeField4 heads (network/nets.py:35-48,
  * network/basenetworks.py:186-355, network/heads.py:272-378), as a list of fused
  * ops over NHWC bf16 activation tensors.  The host mirror of the reference

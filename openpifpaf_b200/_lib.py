@@ -31,6 +31,16 @@ class DecoderParams(ctypes.Structure):
     ]
 
 
+class CifDetParams(ctypes.Structure):
+    """pifpaf_cifdet_params_t"""
+    _fields_ = [
+        ('cifhr_neighbors', c_i64), ('cifhr_threshold', c_f64), ('seed_threshold', c_f64),
+        ('occ_reduction', c_f64), ('occ_min_scale', c_f64), ('cifhr_revision', c_f64),
+        ('max_detections_before_nms', c_i64), ('nms', c_i32), ('nms_by_category', c_i32),
+        ('iou_threshold', c_f64), ('suppression', c_f64), ('instance_threshold', c_f64),
+    ]
+
+
 # every symbol include/pifpaf_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     'pifpaf_last_error': (ctypes.c_char_p, []),
@@ -54,6 +64,12 @@ SYMBOLS = {
     'pifpaf_decoder_tap_caf': (ctypes.c_int, [VP, c_i32, VP, VP, VP, VP]),
     'pifpaf_decoder_debug_set_epochs': (ctypes.c_int, [VP, ctypes.c_uint32, ctypes.c_uint32]),
     'pifpaf_decoder_last_stats': (ctypes.c_int, [VP, VP, c_i32]),
+    'pifpaf_cifdet_default_params': (ctypes.c_int, [P(CifDetParams)]),
+    'pifpaf_cifdet_create': (ctypes.c_int, [P(VP), c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32]),
+    'pifpaf_cifdet_destroy': (None, [VP]),
+    'pifpaf_cifdet_decode_device': (ctypes.c_int, [VP, VP, c_i32, c_i32, c_i32, c_i32, P(CifDetParams), VP]),
+    'pifpaf_cifdet_fetch': (ctypes.c_int, [VP, VP, VP, c_i32, VP]),
+    'pifpaf_cifdet_call': (ctypes.c_int, [VP, VP, c_i32, c_i32, c_i32, P(CifDetParams), VP, c_i32, P(c_i32)]),
     'pifpaf_net_create': (ctypes.c_int, [P(VP), c_i32, c_i32]),
     'pifpaf_net_destroy': (None, [VP]),
     'pifpaf_net_tensor': (ctypes.c_int, [VP, c_i32, c_i32, c_i32, P(c_i32)]),

@@ -121,7 +121,9 @@ __device__ __forceinline__ float cifhr_value(const HrView& v, double revision, l
 // ---------------------------------------------------------------------------
 // CifHr step 1: compact the cells that contribute (src/cif_hr.cpp:36-51), in
 // (j,i) order, with their add_gauss box (src/cif_hr.cpp:61-64).
-__global__ void __launch_bounds__(NT) k_cif_compact(const float* __restrict__ cif, Dims d,
+// det != 0: CifDetHr::accumulate (src/cif_hr.cpp:124-150) on a [F][6][h][w] field -- width / height at components
+// 4 / 5, both tested against min_scale, sigma = max(1, 0.1 * min(w, h) * stride).
+__global__ void __launch_bounds__(NT) k_cif_compact(const float* __restrict__ cif, Dims d, int det,
                                                     double threshold, long long neighbors,
                                                     float min_scale_f, double factor,
                                                     float4* __restrict__ cells, int4* __restrict__ boxes,
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(NT) k_cif_compact(const float* __restrict__ ci
                                                     int* __restrict__ worklist, int* __restrict__ work_count) {
     __shared__ int wc[NW];
     const int f = blockIdx.x, b = blockIdx.y;
-    const float* cf = cif + ((size_t)(b * d.F + f) * 5) * d.hw;
+    const float* cf = cif + ((size_t)(b * d.F + f) * (det ? 6 : 5)) * d.hw;
     float4* out_c = cells + (size_t)(b * d.F + f) * d.hw;
     int4* out_b = boxes + (size_t)(b * d.F + f) * d.hw;
     int base = 0, dummy = 0;
@@ -143,6 +145,11 @@ __global__ void __launch_bounds__(NT) k_cif_compact(const float* __restrict__ ci
             if (!((double)v < threshold)) {
                 scale = cf[4 * d.hw + idx];
                 if (!(scale < min_scale_f)) flag = true;
+                if (det) {
+                    const float bh = cf[5 * d.hw + idx];
+                    if (bh < min_scale_f) flag = false;
+                    scale = fminf(scale, bh);
+                }
             }
         }
         int pos, pos1;
@@ -150,7 +157,7 @@ __global__ void __launch_bounds__(NT) k_cif_compact(const float* __restrict__ ci
         if (flag) {
             const float x = cf[2 * d.hw + idx] * (float)d.cif_stride;
             const float y = cf[3 * d.hw + idx] * (float)d.cif_stride;
-            const float sigma = fmaxf(1.0f, (float)(0.5 * (double)scale * (double)d.cif_stride));
+            const float sigma = fmaxf(1.0f, (float)((det ? 0.1 : 0.5) * (double)scale * (double)d.cif_stride));
             const float vn = (float)((double)(v / (float)neighbors) * factor);
             const float truncate = 1.0f;
             const long long minx = clamp_ll((long long)(x - truncate * sigma), 0, d.W - 1);
@@ -268,12 +275,13 @@ __global__ void __launch_bounds__(NT) k_seed_candidates(const float* __restrict_
                                                         const float* __restrict__ cifhr,
                                                         const unsigned* __restrict__ tile_epoch, unsigned epoch,
                                                         double revision,
-                                                        double threshold, int ablation_nms, int no_rescore,
+                                                        double threshold, int ablation_nms, int no_rescore, int det,
                                                         float* __restrict__ seg_v, float4* __restrict__ seg_xys,
                                                         int* __restrict__ seg_counts) {
+    // det != 0: CifDetSeeds::fill (src/cif_seeds.cpp:69-90) on a [F][6][h][w] field; seg_xys = (x, y, w, h)
     __shared__ int wc[NW];
     const int f = blockIdx.x, b = blockIdx.y;
-    const float* cf = cif + ((size_t)(b * d.F + f) * 5) * d.hw;
+    const float* cf = cif + ((size_t)(b * d.F + f) * (det ? 6 : 5)) * d.hw;
     HrView hv;
     hv.hr = cifhr + (size_t)b * d.F * d.H * d.Wp;
     hv.tiles_x = d.tiles_x; hv.tiles = d.tiles_x * d.tiles_y;
@@ -316,7 +324,7 @@ __global__ void __launch_bounds__(NT) k_seed_candidates(const float* __restrict_
         if (flag) {
             const float s = cf[4 * d.hw + idx] * (float)d.cif_stride;
             out_v[pos] = c;
-            out_x[pos] = make_float4(x, y, s, 0.f);
+            out_x[pos] = make_float4(x, y, s, det ? cf[5 * d.hw + idx] * (float)d.cif_stride : 0.f);
         }
     }
     if (threadIdx.x == 0) seg_counts[b * d.F + f] = base;
@@ -338,6 +346,7 @@ __global__ void __launch_bounds__(SORT_NT) k_seed_sort(Dims d, const int* __rest
                                                        unsigned* __restrict__ keys_a, unsigned* __restrict__ vals_a,
                                                        unsigned* __restrict__ keys_b, unsigned* __restrict__ vals_b,
                                                        int* __restrict__ seed_f, float4* __restrict__ seed_vxys,
+                                                       float* __restrict__ seed_extra,     // DetSeed::h, or null
                                                        int* __restrict__ n_seeds) {
     extern __shared__ unsigned char smem_raw[];
     int* s_off = reinterpret_cast<int*>(smem_raw);                 // F + 1
@@ -444,6 +453,7 @@ __global__ void __launch_bounds__(SORT_NT) k_seed_sort(Dims d, const int* __rest
         const float4 xs = in_x[src];
         seed_f[img + i] = (int)(src / (unsigned)d.hw);
         seed_vxys[img + i] = make_float4(in_v[src], xs.x, xs.y, xs.z);
+        if (seed_extra != nullptr) seed_extra[img + i] = xs.w;
     }
     if (tid == 0) n_seeds[b] = n;
 }
@@ -1539,7 +1549,7 @@ int pifpaf_decoder_decode_device(pifpaf_decoder_t* dec, const float* cif_dev, co
     if (!p.cifhr_ablation_skip) {
         const float min_scale_f = (float)(0.0 / (double)cif_stride);
         PIFPAF_CUDA_TRY(cudaMemsetAsync(dec->d_work_count, 0, sizeof(int), st));
-        k_cif_compact<<<dim3(d.F, d.B), NT, 0, st>>>(cif_dev, d, p.cifhr_threshold, (long long)p.cifhr_neighbors,
+        k_cif_compact<<<dim3(d.F, d.B), NT, 0, st>>>(cif_dev, d, 0, p.cifhr_threshold, (long long)p.cifhr_neighbors,
                                                      min_scale_f, 1.0, dec->d_cells, dec->d_boxes, dec->d_cell_counts,
                                                      dec->d_tile_epoch, hr_epoch, dec->d_worklist, dec->d_work_count);
         PIFPAF_LAUNCH_CHECK();
@@ -1550,13 +1560,13 @@ int pifpaf_decoder_decode_device(pifpaf_decoder_t* dec, const float* cif_dev, co
     // seeds (src/cifcaf.cpp:144-148)
     k_seed_candidates<<<dim3(d.F, d.B), NT, 0, st>>>(cif_dev, d, dec->d_cifhr, dec->d_tile_epoch, hr_epoch,
                                                      p.cifhr_revision, p.seed_threshold,
-                                                     p.seeds_ablation_nms, p.seeds_ablation_no_rescore,
+                                                     p.seeds_ablation_nms, p.seeds_ablation_no_rescore, 0,
                                                      dec->d_seg_v, dec->d_seg_xys, dec->d_seg_counts);
     PIFPAF_LAUNCH_CHECK();
     const size_t ss = sizeof(int) * (((size_t)d.F + 1 + 3) / 4 * 4 + 256 + 256 + 8) + 2 * 32 * 256 + 16;
     k_seed_sort<<<d.B, SORT_NT, ss, st>>>(d, dec->d_seg_counts, dec->d_seg_v, dec->d_seg_xys, dec->d_keys_a,
                                           dec->d_vals_a, dec->d_keys_b, dec->d_vals_b, dec->d_seed_f,
-                                          dec->d_seed_vxys, dec->d_n_seeds);
+                                          dec->d_seed_vxys, nullptr, dec->d_n_seeds);
     PIFPAF_LAUNCH_CHECK();
     // caf scored (src/cifcaf.cpp:153-161: CafScored(cifhr, rev, -1.0, 0.1))
     if (d.C > 0) {
@@ -1815,6 +1825,353 @@ int pifpaf_grow_connection_blend(const float* caf, int64_t n, double x, double y
     cudaFree(d_l); cudaFree(d_o);
     if (e != cudaSuccess) { pifpaf::set_error("grow_connection_blend failed: %s", cudaGetErrorString(e)); return PIFPAF_E_CUDA; }
     return PIFPAF_OK;
+}
+
+}  // extern "C"
+
+// =====================================================================================================================
+// CifDet decoder.  Replaces torch.classes.openpifpaf_decoder.CifDet
+// (csrc/src/cifdet.cpp:24-80, module.cpp:57-62) and, optionally, the torchvision NMS + score filter the reference's
+// Python wrapper runs afterwards (decoder/cifdet.py:55-71).  CifDetHr / CifDetSeeds share the CIF kernels above
+// (k_cif_compact / k_cifhr_tiles / k_seed_candidates / k_seed_sort in their det mode).
+namespace {
+
+constexpr int DET_REC = 8;     // floats per detection record: category, score, x1, y1, x2, y2, score after NMS, kept
+
+// src/cifdet.cpp:50-66: walk the sorted seeds, keep those whose cell is free, mark 0.1 * min(w, h) around them.
+// One warp per image: 32 seeds are tested against the map at once; the first free one (seed order) is accepted,
+// marks the map, and the remaining lanes of the group are re-tested.
+__global__ void __launch_bounds__(32) k_det_select(Dims d, GrowParams gp, int max_det,
+                                                   const int* __restrict__ seed_f, const float4* __restrict__ seed_vxyw,
+                                                   const float* __restrict__ seed_h, const int* __restrict__ n_seeds,
+                                                   unsigned char* __restrict__ occ_map, unsigned char occ_tag,
+                                                   float* __restrict__ records, int* __restrict__ counts) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    Occ occ;
+    occ.map = occ_map + (size_t)b * d.F * d.Ho * d.Wo;
+    occ.F = d.F; occ.Ho = d.Ho; occ.Wo = d.Wo;
+    occ.reduction = gp.occ_reduction; occ.min_scale_reduced = gp.occ_min_scale_reduced;
+    occ.tag = occ_tag;
+    const size_t img = (size_t)b * d.F * d.hw;
+    float* rec = records + (size_t)b * max_det * DET_REC;
+    const int ns = n_seeds[b];
+    int n_det = 0;
+    for (int base = 0; base < ns && n_det < max_det; base += 32) {
+        const int idx = base + lane;
+        bool alive = idx < ns;
+        int f = 0; float4 s = make_float4(0.f, 0.f, 0.f, 0.f); float bh = 0.f;
+        if (alive) { f = seed_f[img + idx]; s = seed_vxyw[img + idx]; bh = seed_h[img + idx]; }
+        while (n_det < max_det) {
+            const bool is_free = alive && !occ_get(occ, f, (double)s.y, (double)s.z);
+            const unsigned m = __ballot_sync(0xffffffffu, is_free);
+            if (m == 0u) break;
+            const int l = __ffs(m) - 1;
+            const int fl = __shfl_sync(0xffffffffu, f, l);
+            const float v = __shfl_sync(0xffffffffu, s.x, l), x = __shfl_sync(0xffffffffu, s.y, l);
+            const float y = __shfl_sync(0xffffffffu, s.z, l), bw = __shfl_sync(0xffffffffu, s.w, l);
+            const float hh = __shfl_sync(0xffffffffu, bh, l);
+            occ_set_warp(occ, fl, (double)x, (double)y, 0.1 * (double)fminf(bw, hh), lane);
+            __syncwarp();
+            if (lane == 0) {
+                float* r = rec + (size_t)n_det * DET_REC;
+                r[0] = (float)(fl + 1); r[1] = v;
+                r[2] = x - 0.5f * bw; r[3] = y - 0.5f * hh; r[4] = x + 0.5f * bw; r[5] = y + 0.5f * hh;
+                r[6] = v; r[7] = 1.0f;
+            }
+            n_det++;
+            alive = alive && lane > l;
+        }
+    }
+    if (lane == 0) counts[b] = n_det;
+}
+
+// decoder/cifdet.py:55-64: torchvision.ops.batched_nms (coordinate trick: boxes shifted by category * (max + 1)) or
+// torchvision.ops.nms, then scores *= suppression except for the kept ones, kept flag = score > instance_threshold.
+// torchvision's CPU kernel restated: stable descending order, IoU = inter / (area_i + area_j - inter) > threshold.
+constexpr int DET_NMS_NT = 128;
+__global__ void __launch_bounds__(DET_NMS_NT) k_det_nms(int max_det, float iou_threshold, int by_category,
+                                                        float suppression, float instance_threshold,
+                                                        float* __restrict__ records, const int* __restrict__ counts) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float4* box = reinterpret_cast<float4*>(smem);                    // [max_det] shifted boxes
+    float* area = reinterpret_cast<float*>(box + max_det);            // [max_det]
+    float* score = area + max_det;                                    // [max_det]
+    int* order = reinterpret_cast<int*>(score + max_det);             // [max_det]
+    unsigned char* sup = reinterpret_cast<unsigned char*>(order + max_det);   // [max_det]
+    __shared__ float s_red[DET_NMS_NT / 32];
+    __shared__ float s_max;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int n = counts[b];
+    float* rec = records + (size_t)b * max_det * DET_REC;
+    if (n == 0) return;
+    float m = -INFINITY;
+    for (int i = tid; i < n; i += DET_NMS_NT) {
+        const float* r = rec + (size_t)i * DET_REC;
+        m = fmaxf(m, fmaxf(fmaxf(r[2], r[3]), fmaxf(r[4], r[5])));
+        score[i] = r[1];
+        sup[i] = 0;
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0) s_red[tid >> 5] = m;
+    __syncthreads();
+    if (tid == 0) {
+        float mm = s_red[0];
+        for (int i = 1; i < DET_NMS_NT / 32; i++) mm = fmaxf(mm, s_red[i]);
+        s_max = mm;
+    }
+    __syncthreads();
+    const float shift = s_max + 1.0f;                                  // max_coordinate + 1
+    for (int i = tid; i < n; i += DET_NMS_NT) {
+        const float* r = rec + (size_t)i * DET_REC;
+        const float off = by_category ? r[0] * shift : 0.0f;          // idxs.to(boxes) * (max_coordinate + 1)
+        const float4 bx = make_float4(r[2] + off, r[3] + off, r[4] + off, r[5] + off);
+        box[i] = bx;
+        area[i] = (bx.z - bx.x) * (bx.w - bx.y);
+        int rank = 0;                                                  // stable descending sort position
+        for (int j = 0; j < n; j++) {
+            const float sj = rec[(size_t)j * DET_REC + 1];
+            if (sj > r[1] || (sj == r[1] && j < i)) rank++;
+        }
+        order[rank] = i;
+    }
+    __syncthreads();
+    for (int oi = 0; oi < n; oi++) {
+        const int i = order[oi];
+        if (!sup[i]) {
+            const float4 bi = box[i];
+            const float ai = area[i];
+            for (int oj = oi + 1 + tid; oj < n; oj += DET_NMS_NT) {
+                const int j = order[oj];
+                if (sup[j]) continue;
+                const float4 bj = box[j];
+                const float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
+                const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
+                const float w = fmaxf(0.0f, xx2 - xx1), h = fmaxf(0.0f, yy2 - yy1);
+                const float inter = w * h;
+                const float ovr = inter / (ai + area[j] - inter);
+                if (ovr > iou_threshold) sup[j] = 1;
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < n; i += DET_NMS_NT) {
+        float* r = rec + (size_t)i * DET_REC;
+        const float sc = sup[i] ? score[i] * suppression : score[i];
+        r[6] = sc;
+        r[7] = sc > instance_threshold ? 1.0f : 0.0f;
+    }
+}
+
+size_t det_nms_smem(int max_det) { return (size_t)max_det * (sizeof(float4) + 2 * sizeof(float) + sizeof(int) + 1) + 16; }
+
+}  // namespace
+
+struct pifpaf_cifdet {
+    int device = 0, F = 0;
+    int max_batch = 0, max_h = 0, max_w = 0, max_stride = 0, max_det = 0;
+    int n_sm = 148;
+    float* d_cifhr = nullptr;
+    float4* d_cells = nullptr; int4* d_boxes = nullptr; int* d_cell_counts = nullptr;
+    unsigned* d_tile_epoch = nullptr; int* d_worklist = nullptr; int* d_work_count = nullptr;
+    unsigned hr_epoch = 0; size_t tile_epoch_elems = 0;
+    float* d_seg_v = nullptr; float4* d_seg_xys = nullptr; int* d_seg_counts = nullptr;
+    unsigned *d_keys_a = nullptr, *d_vals_a = nullptr, *d_keys_b = nullptr, *d_vals_b = nullptr;
+    int* d_seed_f = nullptr; float4* d_seed_vxyw = nullptr; float* d_seed_h = nullptr; int* d_n_seeds = nullptr;
+    unsigned char* d_occ = nullptr; size_t occ_bytes = 0; unsigned epoch = 1;
+    float* d_records = nullptr; int* d_counts = nullptr;
+    float* h_records = nullptr; int* h_counts = nullptr;       // pinned
+    float* d_in_field = nullptr;
+    cudaStream_t own_stream = nullptr;
+    Dims last{}; bool has_last = false;
+};
+
+extern "C" {
+
+int pifpaf_cifdet_default_params(pifpaf_cifdet_params_t* p) {
+    PIFPAF_CHECK_ARG(p != nullptr, "params is null");
+    std::memset(p, 0, sizeof(*p));
+    p->cifhr_neighbors = 16; p->cifhr_threshold = 0.3;       // csrc/src/cif_hr.cpp:13-14
+    p->seed_threshold = 0.2;                                  // CifDetSeeds::threshold, csrc/src/cif_seeds.cpp:12
+    p->occ_reduction = 2.0; p->occ_min_scale = 4.0;           // include/openpifpaf/decoder/cifdet.hpp:40
+    p->cifhr_revision = 1.0;
+    p->max_detections_before_nms = 120;                       // csrc/src/cifdet.cpp:16
+    p->nms = 0; p->nms_by_category = 1;
+    p->iou_threshold = 0.5; p->suppression = 0.1; p->instance_threshold = 0.15;   // decoder/cifdet.py:17-21
+    return PIFPAF_OK;
+}
+
+void pifpaf_cifdet_destroy(pifpaf_cifdet_t* det) {
+    if (!det) return;
+    cudaSetDevice(det->device);
+    void* dev_ptrs[] = {det->d_cifhr, det->d_cells, det->d_boxes, det->d_cell_counts, det->d_tile_epoch, det->d_worklist,
+        det->d_work_count, det->d_seg_v, det->d_seg_xys, det->d_seg_counts, det->d_keys_a, det->d_vals_a, det->d_keys_b,
+        det->d_vals_b, det->d_seed_f, det->d_seed_vxyw, det->d_seed_h, det->d_n_seeds, det->d_occ, det->d_records,
+        det->d_counts, det->d_in_field};
+    for (void* p : dev_ptrs) if (p) cudaFree(p);
+    if (det->h_records) cudaFreeHost(det->h_records);
+    if (det->h_counts) cudaFreeHost(det->h_counts);
+    if (det->own_stream) cudaStreamDestroy(det->own_stream);
+    delete det;
+}
+
+int pifpaf_cifdet_create(pifpaf_cifdet_t** out, int32_t device, int32_t n_categories,
+                         int32_t max_batch, int32_t max_h, int32_t max_w, int32_t max_stride, int32_t max_detections) {
+    PIFPAF_CHECK_ARG(out != nullptr, "out is null");
+    *out = nullptr;
+    PIFPAF_CHECK_ARG(n_categories >= 1, "bad category count");
+    PIFPAF_CHECK_ARG(max_batch >= 1 && max_h >= 1 && max_w >= 1 && max_stride >= 1, "bad capacity");
+    PIFPAF_CHECK_ARG(max_detections >= 1 && max_detections <= 4096, "max_detections must be in [1, 4096]");
+    int n_dev = 0;
+    PIFPAF_CUDA_TRY(cudaGetDeviceCount(&n_dev));
+    PIFPAF_CHECK_ARG(device >= 0 && device < n_dev, "no such CUDA device");
+    PIFPAF_CUDA_TRY(cudaSetDevice(device));
+    pifpaf_cifdet* det = new pifpaf_cifdet();
+    det->device = device; det->F = n_categories;
+    det->max_batch = max_batch; det->max_h = max_h; det->max_w = max_w; det->max_stride = max_stride;
+    det->max_det = max_detections;
+    int rc = PIFPAF_OK;
+#define ALLOC(ptr, n) do { rc = dev_alloc(&(ptr), (n)); if (rc != PIFPAF_OK) { pifpaf_cifdet_destroy(det); return rc; } } while (0)
+#define TRY_D(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { pifpaf::set_error("%s failed: %s", #expr, cudaGetErrorString(e__)); pifpaf_cifdet_destroy(det); return PIFPAF_E_CUDA; } } while (0)
+    const size_t B = max_batch, F = n_categories, hw = (size_t)max_h * max_w;
+    const size_t Hm = (size_t)(max_h - 1) * max_stride + 1, Wm = (size_t)(max_w - 1) * max_stride + 1;
+    const size_t Wpm = (Wm + TILE - 1) / TILE * TILE;
+    ALLOC(det->d_cifhr, B * F * Hm * Wpm);
+    ALLOC(det->d_cells, B * F * hw); ALLOC(det->d_boxes, B * F * hw); ALLOC(det->d_cell_counts, B * F);
+    const size_t tiles_max = (Wpm / TILE) * ((Hm + TILE - 1) / TILE);
+    det->tile_epoch_elems = B * F * tiles_max;
+    ALLOC(det->d_tile_epoch, det->tile_epoch_elems); ALLOC(det->d_worklist, det->tile_epoch_elems);
+    ALLOC(det->d_work_count, 1);
+    TRY_D(cudaMemset(det->d_tile_epoch, 0, sizeof(unsigned) * det->tile_epoch_elems));
+    cudaDeviceProp prop;
+    TRY_D(cudaGetDeviceProperties(&prop, device));
+    det->n_sm = prop.multiProcessorCount;
+    ALLOC(det->d_seg_v, B * F * hw); ALLOC(det->d_seg_xys, B * F * hw); ALLOC(det->d_seg_counts, B * F);
+    ALLOC(det->d_keys_a, B * F * hw); ALLOC(det->d_vals_a, B * F * hw);
+    ALLOC(det->d_keys_b, B * F * hw); ALLOC(det->d_vals_b, B * F * hw);
+    ALLOC(det->d_seed_f, B * F * hw); ALLOC(det->d_seed_vxyw, B * F * hw); ALLOC(det->d_seed_h, B * F * hw);
+    ALLOC(det->d_n_seeds, B);
+    det->occ_bytes = B * F * (Hm + 1) * (Wm + 1);
+    ALLOC(det->d_occ, det->occ_bytes);
+    TRY_D(cudaMemset(det->d_occ, 0, det->occ_bytes));
+    ALLOC(det->d_records, B * (size_t)max_detections * DET_REC); ALLOC(det->d_counts, B);
+    TRY_D(cudaMallocHost(reinterpret_cast<void**>(&det->h_records), sizeof(float) * B * (size_t)max_detections * DET_REC));
+    TRY_D(cudaMallocHost(reinterpret_cast<void**>(&det->h_counts), sizeof(int) * B));
+    ALLOC(det->d_in_field, F * 6 * hw);
+    TRY_D(cudaStreamCreateWithFlags(&det->own_stream, cudaStreamNonBlocking));
+    const size_t ss = sizeof(int) * (((size_t)F + 1 + 3) / 4 * 4 + 256 + 256 + 8) + 2 * 32 * 256 + 16;
+    TRY_D(cudaFuncSetAttribute(k_seed_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(ss, (size_t)48 * 1024)));
+    TRY_D(cudaFuncSetAttribute(k_det_nms, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)std::max(det_nms_smem(max_detections), (size_t)48 * 1024)));
+    TRY_D(cudaDeviceSynchronize());
+#undef ALLOC
+#undef TRY_D
+    *out = det;
+    return PIFPAF_OK;
+}
+
+int pifpaf_cifdet_decode_device(pifpaf_cifdet_t* det, const float* field_dev, int32_t batch, int32_t h, int32_t w,
+                                int32_t stride, const pifpaf_cifdet_params_t* params, void* stream_v) {
+    PIFPAF_CHECK_ARG(det != nullptr, "cifdet handle is null");
+    PIFPAF_CHECK_ARG(field_dev != nullptr && params != nullptr, "null argument");
+    PIFPAF_CHECK_ARG(batch >= 1 && batch <= det->max_batch, "batch exceeds max_batch given at create()");
+    PIFPAF_CHECK_ARG(h >= 1 && w >= 1 && h <= det->max_h && w <= det->max_w, "field shape exceeds max_h/max_w");
+    PIFPAF_CHECK_ARG(stride >= 1 && stride <= det->max_stride, "stride exceeds max_stride");
+    const pifpaf_cifdet_params_t& p = *params;
+    PIFPAF_CHECK_ARG(p.occ_reduction >= 1.0 && p.cifhr_neighbors != 0, "bad occupancy reduction / neighbors");
+    PIFPAF_CHECK_ARG(p.max_detections_before_nms >= 1 && p.max_detections_before_nms <= det->max_det,
+                     "max_detections_before_nms exceeds the max_detections given at create()");
+    PIFPAF_CUDA_TRY(cudaSetDevice(det->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
+    Dims d;
+    d.B = batch; d.F = det->F; d.C = 0; d.K = det->F;
+    d.h = h; d.w = w; d.hw = h * w; d.cif_stride = stride; d.caf_stride = stride;
+    d.H = (h - 1) * stride + 1; d.W = (w - 1) * stride + 1;
+    d.Wp = (d.W + TILE - 1) / TILE * TILE;
+    d.Ho = (int)((double)d.H / p.occ_reduction) + 1; d.Wo = (int)((double)d.W / p.occ_reduction) + 1;
+    d.tiles_x = d.Wp / TILE; d.tiles_y = (d.H + TILE - 1) / TILE;
+    d.max_ann = det->max_det;
+    det->last = d; det->has_last = true;
+    if (det->epoch > 254) {                                    // one occupancy tag per decode
+        PIFPAF_CUDA_TRY(cudaMemsetAsync(det->d_occ, 0, det->occ_bytes, st));
+        det->epoch = 1;
+    }
+    const unsigned char tag = (unsigned char)det->epoch++;
+    if (++det->hr_epoch == 0) {
+        PIFPAF_CUDA_TRY(cudaMemsetAsync(det->d_tile_epoch, 0, sizeof(unsigned) * det->tile_epoch_elems, st));
+        det->hr_epoch = 1;
+    }
+    GrowParams gp{};
+    gp.occ_reduction = p.occ_reduction; gp.occ_min_scale_reduced = p.occ_min_scale / p.occ_reduction;
+    // cifDetHr.accumulate(field, stride, 0.0, 1.0)   (src/cifdet.cpp:31)
+    const float min_scale_f = (float)(0.0 / (double)stride);
+    PIFPAF_CUDA_TRY(cudaMemsetAsync(det->d_work_count, 0, sizeof(int), st));
+    k_cif_compact<<<dim3(d.F, d.B), NT, 0, st>>>(field_dev, d, 1, p.cifhr_threshold, (long long)p.cifhr_neighbors,
+                                                 min_scale_f, 1.0, det->d_cells, det->d_boxes, det->d_cell_counts,
+                                                 det->d_tile_epoch, det->hr_epoch, det->d_worklist, det->d_work_count);
+    PIFPAF_LAUNCH_CHECK();
+    k_cifhr_tiles<<<det->n_sm * 8, NT, 0, st>>>(d, p.cifhr_revision, det->d_cells, det->d_boxes, det->d_cell_counts,
+                                                det->d_worklist, det->d_work_count, det->d_cifhr);
+    PIFPAF_LAUNCH_CHECK();
+    k_seed_candidates<<<dim3(d.F, d.B), NT, 0, st>>>(field_dev, d, det->d_cifhr, det->d_tile_epoch, det->hr_epoch,
+                                                     p.cifhr_revision, p.seed_threshold, 0, 0, 1,
+                                                     det->d_seg_v, det->d_seg_xys, det->d_seg_counts);
+    PIFPAF_LAUNCH_CHECK();
+    const size_t ss = sizeof(int) * (((size_t)d.F + 1 + 3) / 4 * 4 + 256 + 256 + 8) + 2 * 32 * 256 + 16;
+    k_seed_sort<<<d.B, SORT_NT, ss, st>>>(d, det->d_seg_counts, det->d_seg_v, det->d_seg_xys, det->d_keys_a,
+                                          det->d_vals_a, det->d_keys_b, det->d_vals_b, det->d_seed_f,
+                                          det->d_seed_vxyw, det->d_seed_h, det->d_n_seeds);
+    PIFPAF_LAUNCH_CHECK();
+    const int max_det = (int)p.max_detections_before_nms;
+    k_det_select<<<d.B, 32, 0, st>>>(d, gp, max_det, det->d_seed_f, det->d_seed_vxyw, det->d_seed_h, det->d_n_seeds,
+                                     det->d_occ, tag, det->d_records, det->d_counts);
+    PIFPAF_LAUNCH_CHECK();
+    if (p.nms) {
+        k_det_nms<<<d.B, DET_NMS_NT, det_nms_smem(max_det), st>>>(max_det, (float)p.iou_threshold, p.nms_by_category,
+                                                                  (float)p.suppression, (float)p.instance_threshold,
+                                                                  det->d_records, det->d_counts);
+        PIFPAF_LAUNCH_CHECK();
+    }
+    det->last.max_ann = max_det;
+    return PIFPAF_OK;
+}
+
+int pifpaf_cifdet_fetch(pifpaf_cifdet_t* det, int32_t* counts, float* records, int32_t cap, void* stream_v) {
+    PIFPAF_CHECK_ARG(det != nullptr && det->has_last, "no decode to fetch");
+    PIFPAF_CHECK_ARG(counts != nullptr, "counts is null");
+    PIFPAF_CUDA_TRY(cudaSetDevice(det->device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
+    const int B = det->last.B, max_det = det->last.max_ann;
+    PIFPAF_CUDA_TRY(cudaMemcpyAsync(det->h_counts, det->d_counts, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    PIFPAF_CUDA_TRY(cudaMemcpyAsync(det->h_records, det->d_records, sizeof(float) * (size_t)B * max_det * DET_REC,
+                                    cudaMemcpyDeviceToHost, st));
+    PIFPAF_CUDA_TRY(cudaStreamSynchronize(st));
+    bool overflow = false;
+    for (int b = 0; b < B; b++) {
+        counts[b] = det->h_counts[b];
+        if (records == nullptr) continue;
+        int n = det->h_counts[b];
+        if (n > cap) { overflow = true; n = cap; }
+        std::memcpy(records + (size_t)b * cap * DET_REC, det->h_records + (size_t)b * max_det * DET_REC,
+                    sizeof(float) * (size_t)n * DET_REC);
+    }
+    if (overflow) { pifpaf::set_error("detection capacity exceeded (cap=%d)", cap); return PIFPAF_E_OVERFLOW; }
+    return PIFPAF_OK;
+}
+
+int pifpaf_cifdet_call(pifpaf_cifdet_t* det, const float* field, int32_t stride, int32_t h, int32_t w,
+                       const pifpaf_cifdet_params_t* params, float* records, int32_t cap, int32_t* n_out) {
+    PIFPAF_CHECK_ARG(det != nullptr && field != nullptr && n_out != nullptr, "null argument");
+    PIFPAF_CHECK_ARG(h >= 1 && w >= 1 && h <= det->max_h && w <= det->max_w, "field shape exceeds max_h/max_w");
+    PIFPAF_CUDA_TRY(cudaSetDevice(det->device));
+    cudaStream_t st = det->own_stream;
+    PIFPAF_CUDA_TRY(cudaMemcpyAsync(det->d_in_field, field, sizeof(float) * (size_t)det->F * 6 * h * w,
+                                    cudaMemcpyHostToDevice, st));
+    int rc = pifpaf_cifdet_decode_device(det, det->d_in_field, 1, h, w, stride, params, st);
+    if (rc != PIFPAF_OK) return rc;
+    int32_t count = 0;
+    rc = pifpaf_cifdet_fetch(det, &count, records, cap, st);
+    *n_out = count;
+    return rc;
 }
 
 }  // extern "C"

@@ -330,6 +330,129 @@ class CifCaf(metaclass=_Statics):
         self._tap_hw = h * w
 
 
+class CifDetSeeds(metaclass=_Statics):
+    """static of csrc/src/cif_seeds.cpp:12 (module.cpp:96-97)"""
+    STATICS = {'threshold': 0.2}
+
+
+class CifDet(metaclass=_Statics):
+    """Drop-in for torch.classes.openpifpaf_decoder.CifDet (csrc/include/openpifpaf/decoder/cifdet.hpp:33-47,
+    csrc/src/cifdet.cpp:24-80): ``call(cifdet_field [F,6,h,w], stride) -> (categories [N] int64 (1-based),
+    scores [N] float32, boxes [N,4] float32 (x1, y1, x2, y2))`` -- before NMS, like the reference class; the statics
+    CifHr.{neighbors,threshold}, CifDetSeeds.threshold and max_detections_before_nms go by value into every call.
+    Beyond the reference: ``decode_batch`` on device-resident field batches, optionally with the NMS / score filter
+    of the reference's Python wrapper (decoder/cifdet.py:55-64) done on the GPU."""
+    STATICS = {'max_detections_before_nms': 120}
+    #: capacity of the native handle for max_detections_before_nms
+    max_detections = 1024
+
+    def __init__(self, n_categories=None, *, device=0):
+        self.n_categories = None if n_categories is None else int(n_categories)
+        self.device = int(device)
+        self._handle = None
+        self._caps = None
+
+    def __getstate__(self):
+        return (self.n_categories, self.device)
+
+    def __setstate__(self, state):
+        self.__init__(state[0], device=state[1])
+
+    def __del__(self):
+        self._free()
+
+    def _free(self):
+        h, self._handle = getattr(self, '_handle', None), None
+        if h is not None:
+            try:
+                _lib.lib().pifpaf_cifdet_destroy(h)
+            except Exception:   # interpreter shutdown
+                pass
+
+    def _ensure(self, n_categories, batch, h, w, stride):
+        if self.n_categories is None:
+            self.n_categories = int(n_categories)
+        if int(n_categories) != self.n_categories:
+            raise RuntimeError('field count does not match the number of categories of this decoder')
+        need = (batch, h, w, stride, max(self.max_detections, self._max_detections_before_nms))
+        if self._caps is not None and all(c >= n for c, n in zip(self._caps, need)):
+            return self._handle
+        if self._caps is not None:
+            need = tuple(max(c, n) for c, n in zip(self._caps, need))
+        self._free()
+        handle = ctypes.c_void_p()
+        _lib.check(_lib.lib().pifpaf_cifdet_create(ctypes.byref(handle), self.device, self.n_categories, *need))
+        self._handle, self._caps = handle, need
+        return handle
+
+    @classmethod
+    def params(cls, **overrides):
+        p = _lib.CifDetParams()
+        _lib.check(_lib.lib().pifpaf_cifdet_default_params(ctypes.byref(p)))
+        p.cifhr_neighbors, p.cifhr_threshold = CifHr._neighbors, CifHr._threshold
+        p.seed_threshold = CifDetSeeds._threshold
+        p.max_detections_before_nms = cls._max_detections_before_nms
+        for k, v in overrides.items():
+            if not hasattr(p, k):
+                raise AttributeError(f'unknown CifDet parameter {k}')
+            setattr(p, k, v)
+        return p
+
+    @staticmethod
+    def _unpack(rec, n, filtered):
+        rec = rec[:n]
+        if filtered:
+            rec = rec[rec[:, 7] > 0.5]
+            scores = rec[:, 6]
+        else:
+            scores = rec[:, 1]
+        return (torch.from_numpy(rec[:, 0].astype(np.int64)), torch.from_numpy(scores.copy()),
+                torch.from_numpy(rec[:, 2:6].copy()))
+
+    def call(self, cifdet_field, cifdet_stride):
+        """csrc/src/cifdet.cpp:24-80"""
+        field = _as_f32_cpu(cifdet_field, 'cifdet_field')
+        if field.dim() != 4 or field.shape[1] < 6:
+            raise RuntimeError('expected cifdet_field [F,6,h,w]')
+        if field.is_cuda:
+            return self.decode_batch(field[:, :6].unsqueeze(0), int(cifdet_stride))[0]
+        F, _, h, w = (int(v) for v in field.shape)
+        handle = self._ensure(F, 1, h, w, int(cifdet_stride))
+        p = self.params()
+        cap = int(p.max_detections_before_nms)
+        rec = np.empty((cap, 8), dtype=np.float32)
+        n = ctypes.c_int32(0)
+        fc = field[:, :6].contiguous()
+        _lib.check(_lib.lib().pifpaf_cifdet_call(handle, fc.data_ptr(), int(cifdet_stride), h, w, ctypes.byref(p),
+                                                 rec.ctypes.data, cap, ctypes.byref(n)))
+        return self._unpack(rec, n.value, False)
+
+    def decode_batch(self, field_batch, stride, *, nms=False, iou_threshold=0.5, nms_by_category=True,
+                     suppression=0.1, instance_threshold=0.15, stream=None):
+        """field_batch [B,F,6,h,w] CUDA float32.  nms=False: per image the raw (categories, scores, boxes) of
+        CifDet::call; nms=True: the filtered detections of decoder/cifdet.py:55-64 (scores after suppression)."""
+        if not field_batch.is_cuda or field_batch.dtype != torch.float32:
+            raise RuntimeError('decode_batch expects a CUDA float32 tensor (use call() for host fields)')
+        field_batch = field_batch.contiguous()
+        B, F, ncomp, h, w = (int(v) for v in field_batch.shape)
+        if ncomp != 6:
+            raise RuntimeError('expected cifdet fields [B,F,6,h,w]')
+        if field_batch.device.index != self.device:
+            raise RuntimeError('fields live on a different CUDA device than the decoder')
+        handle = self._ensure(F, B, h, w, int(stride))
+        p = self.params(nms=int(bool(nms)), iou_threshold=float(iou_threshold), nms_by_category=int(bool(nms_by_category)),
+                        suppression=float(suppression), instance_threshold=float(instance_threshold))
+        st = stream if stream is not None else torch.cuda.current_stream(field_batch.device)
+        _lib.check(_lib.lib().pifpaf_cifdet_decode_device(handle, field_batch.data_ptr(), B, h, w, int(stride),
+                                                          ctypes.byref(p), ctypes.c_void_p(st.cuda_stream)))
+        cap = int(p.max_detections_before_nms)
+        counts = np.zeros((B,), dtype=np.int32)
+        rec = np.empty((B, cap, 8), dtype=np.float32)
+        _lib.check(_lib.lib().pifpaf_cifdet_fetch(handle, counts.ctypes.data, rec.ctypes.data, cap,
+                                                  ctypes.c_void_p(st.cuda_stream)))
+        return [self._unpack(rec[b], int(counts[b]), bool(nms)) for b in range(B)]
+
+
 def grow_connection_blend(caf, x, y, s, filter_sigmas=1.0, only_max=False):
     """torch.ops.openpifpaf_decoder.grow_connection_blend (csrc/src/cifcaf.cpp:105-113): returns [x, y, s, v]."""
     caf = _as_f32_cpu(caf, 'caf').contiguous()

@@ -401,9 +401,12 @@ def default_layout():
 
 
 def default_fuse_dw():
-    """Fuse depthwise 5x5 (stride 1) with the 1x1 conv that follows it into one kernel (k_dw_gemm); PIFPAF_FUSE_DW=0
-    keeps them as two launches."""
-    return os.environ.get('PIFPAF_FUSE_DW', '1') != '0'
+    """Fuse depthwise 5x5 (stride 1) with the 1x1 conv that follows it into one kernel (k_dw_gemm)?  Off by default:
+    the fused kernel is bit-identical to the two-kernel schedule but measured SLOWER on B200 (round 2: 0.91 ms against
+    0.42 + 0.22 ms per stage-2 block, 0.58 against 0.27 + 0.14 ms per stage-3 block -- one CTA per SM leaves only 8
+    depthwise warps per SM where the stand-alone depthwise kernel runs 16, and the depthwise FMA loop is issue bound;
+    profiles/r2_history.md).  PIFPAF_FUSE_DW=1 turns it on."""
+    return os.environ.get('PIFPAF_FUSE_DW', '0') == '1'
 
 
 def build_ops(plan, in_h, in_w, layout=None, fuse_dw=None):

@@ -180,7 +180,84 @@ def _build_class():
             self.last_nn_time = self.last_decoder_time = time.perf_counter() - start
             return [self._annotations(a.numpy(), i.numpy()) for a, i in results]
 
-    return openpifpaf, CifCafB200
+    class CifCafDenseB200(Decoder):
+        """decoder/cifcaf.py:17-78 (CifCafDense): the CAF and the dense CAF (caf25) heads concatenated behind one
+        CifCaf decode over the concatenated skeleton.  (The dense head's decoder_confidence_scales set by the
+        reference's constructor are not read by its C++ decoder, csrc/src/cifcaf.cpp:299-301 -- nor here.)"""
+
+        def __init__(self, cif_meta, caf_meta, dense_caf_meta):
+            super().__init__()
+            self.cif_meta, self.caf_meta, self.dense_caf_meta = cif_meta, caf_meta, dense_caf_meta
+            self.priority += 1.0 + (cif_meta.n_fields + caf_meta.n_fields + dense_caf_meta.n_fields) / 1000.0
+            dense_caf_meta.decoder_confidence_scales = [
+                openpifpaf.decoder.cifcaf.CifCafDense.dense_coupling for _ in dense_caf_meta.skeleton]
+            concatenated = headmeta.Caf.concatenate([caf_meta, dense_caf_meta])
+            self.cifcaf = CifCafB200([cif_meta], [concatenated])
+
+        @classmethod
+        def factory(cls, head_metas):
+            if len(head_metas) < 3 or not openpifpaf.decoder.cifcaf.CifCafDense.dense_coupling:
+                return []
+            return [
+                CifCafDenseB200(cif_meta, caf_meta, dense_meta)
+                for cif_meta, caf_meta, dense_meta in zip(head_metas, head_metas[1:], head_metas[2:])
+                if (isinstance(cif_meta, headmeta.Cif) and isinstance(caf_meta, headmeta.Caf)
+                    and isinstance(dense_meta, headmeta.Caf))
+            ]
+
+        def __call__(self, fields, initial_annotations=None):
+            caf = torch.cat([fields[self.caf_meta.head_index], fields[self.dense_caf_meta.head_index]], dim=0)
+            cifcaf_fields = [None] * (max(self.cif_meta.head_index, self.caf_meta.head_index) + 1)
+            cifcaf_fields[self.cif_meta.head_index] = fields[self.cif_meta.head_index]
+            cifcaf_fields[self.caf_meta.head_index] = caf
+            return self.cifcaf(cifcaf_fields, initial_annotations=initial_annotations)
+
+    class CifDetB200(Decoder):
+        """decoder/cifdet.py:15-96 with the C++ CifDet call AND the torchvision NMS / score filter on the GPU
+        (libpifpaf_b200 pifpaf_cifdet_*).  Class attributes are read from the reference's CifDet at call time, so
+        decoder.factory.configure (decoder/factory.py:68,78) keeps configuring one source of truth."""
+
+        def __init__(self, head_metas):
+            super().__init__()
+            self.metas = head_metas
+            self.priority = -1.0 + 0.5                      # decoder/cifdet.py:29 is -1.0: outrank it, stay below poses
+            self.priority += sum(m.n_fields for m in head_metas) / 1000.0
+            self.native = b200_decoder.CifDet(head_metas[0].n_fields)
+
+        @classmethod
+        def factory(cls, head_metas):
+            return [CifDetB200([meta]) for meta in head_metas if isinstance(meta, headmeta.CifDet)]
+
+        @staticmethod
+        def sync_statics():
+            utl = torch.classes.openpifpaf_decoder_utils
+            b200_decoder.CifHr.set_neighbors(utl.CifHr.get_neighbors())
+            b200_decoder.CifHr.set_threshold(utl.CifHr.get_threshold())
+            b200_decoder.CifDetSeeds.set_threshold(utl.CifDetSeeds.get_threshold())
+            b200_decoder.CifDet.set_max_detections_before_nms(
+                torch.classes.openpifpaf_decoder.CifDet.get_max_detections_before_nms())
+
+        def __call__(self, fields):
+            from openpifpaf.annotation import AnnotationDet
+            ref = openpifpaf.decoder.CifDet
+            self.sync_statics()
+            field = fields[self.metas[0].head_index]
+            if not field.is_cuda:
+                field = field.cuda(self.native.device)
+            cats, scores, boxes = self.native.decode_batch(
+                field[:, :6].unsqueeze(0), self.metas[0].stride, nms=True, iou_threshold=ref.iou_threshold,
+                nms_by_category=ref.nms_by_category, suppression=ref.suppression,
+                instance_threshold=ref.instance_threshold)[0]
+            boxes_np = boxes.numpy()
+            boxes_np[:, 2:] -= boxes_np[:, :2]              # xyxy -> xywh (decoder/cifdet.py:86-87)
+            out = []
+            for category, score, box in zip(cats, scores, boxes_np):
+                ann = AnnotationDet(self.metas[0].categories)
+                ann.set(int(category), float(score), box)
+                out.append(ann)
+            return out
+
+    return openpifpaf, CifCafB200, CifCafDenseB200, CifDetB200
 
 
 _CLASS = None
@@ -194,10 +271,12 @@ def decoder_class():
 
 
 def register():
-    openpifpaf, cls = _build_class()
+    openpifpaf, cls, dense_cls, det_cls = _build_class()
     global _CLASS
     _CLASS = cls
     openpifpaf.DECODERS.add(cls)
+    openpifpaf.DECODERS.add(dense_cls)
+    openpifpaf.DECODERS.add(det_cls)
 
     # Predictor calls Multi.batch (predictor.py:131); let it delegate to the GPU-resident batch path when the
     # selected decoder provides one.

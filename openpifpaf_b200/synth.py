@@ -103,14 +103,15 @@ def _poisson(rng, lam):
 
 
 def make_fields(workload='cocokp', h=41, w=41, n_people=None, seed=0,
-                n_distractors=0, people_lambda=4.0):
+                n_distractors=0, people_lambda=4.0, skeleton=None):
     """One image worth of fields.
 
     Returns dict(cif [F,5,h,w] f32, caf [C,8,h,w] f32, skeleton [C,2] int64 0-based,
     n_keypoints, n_planted, keypoints [n_planted,K,2] in field units).
-    n_people=None draws Poisson(people_lambda)+1 (COCO-like)."""
+    n_people=None draws Poisson(people_lambda)+1 (COCO-like).  skeleton: optional 1-based connection list replacing the
+    workload's own (e.g. the sparse + dense COCO connections of CifCafDense)."""
     K, _, template_fn, (smin, smax), joint_scale = WORKLOADS[workload]
-    skeleton1 = np.asarray(skeleton_for(workload), dtype=np.int64)
+    skeleton1 = np.asarray(skeleton_for(workload) if skeleton is None else skeleton, dtype=np.int64)
     C = skeleton1.shape[0]
     rng = np.random.Generator(np.random.PCG64(seed))
     template = template_fn()
@@ -222,6 +223,64 @@ def make_batch(workload='cocokp', batch=8, h=41, w=41, n_people=None, seed=0, n_
         'skeleton': items[0]['skeleton'], 'n_keypoints': items[0]['n_keypoints'],
         'n_planted': [it['n_planted'] for it in items],
     }
+
+
+def make_det_fields(n_categories=80, h=41, w=41, n_objects=6, seed=0, n_distractors=4):
+    """One image worth of CifDet fields ("planted boxes"): [F,6,h,w] f32 -- intensity(unused), confidence, x, y
+    (cell index added, like the eval head), w, h in field units (headmeta.py:117-134; csrc/src/cif_hr.cpp:124-150
+    reads components 1..5).  Per planted object of category f, every cell within ~2.5 cells of its centre votes for
+    the centre with a bump-shaped confidence; a few cells carry a NEGATIVE width (skipped by `w < min_scale`), and
+    near-duplicate objects of the same category test the occupancy suppression.  Distractors are weak blobs (some
+    between the CifHr threshold 0.3 and the seed threshold 0.2).
+    Returns dict(field, n_planted, boxes [n,5] (category 1-based, cx, cy, w, h))."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    F = n_categories
+    field = np.zeros((F, 6, h, w), dtype=np.float64)
+    ii, jj = np.meshgrid(np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64))
+    field[:, 1] = rng.random((F, h, w)) * 0.05
+    field[:, 2] = ii
+    field[:, 3] = jj
+    field[:, 4] = 1.0
+    field[:, 5] = 1.0
+    planted = []
+
+    def plant(f, x, y, bw, bh, peak, radius2=6.5):
+        for j in range(max(int(y) - 3, 0), min(int(y) + 4, h - 1) + 1):
+            for i in range(max(int(x) - 3, 0), min(int(x) + 4, w - 1) + 1):
+                d2 = (i - x) * (i - x) + (j - y) * (j - y)
+                if d2 > radius2:
+                    continue
+                g = (1.0 - d2 / 20.0)
+                conf = peak * g * g - 0.01 * rng.random()
+                if conf <= field[f, 1, j, i]:
+                    continue
+                field[f, 1, j, i] = conf
+                field[f, 2, j, i] = x + 0.002 * (i - x)
+                field[f, 3, j, i] = y + 0.002 * (j - y)
+                field[f, 4, j, i] = bw * (1.0 + 0.01 * (rng.random() - 0.5))
+                field[f, 5, j, i] = bh * (1.0 + 0.01 * (rng.random() - 0.5))
+
+    for n in range(n_objects):
+        f = int(rng.random() * F) % F
+        bw, bh = 1.5 + rng.random() * 0.3 * w, 1.5 + rng.random() * 0.3 * h
+        x = 1.0 + rng.random() * (w - 3.0)
+        y = 1.0 + rng.random() * (h - 3.0)
+        plant(f, x, y, bw, bh, 0.95)
+        planted.append([f + 1, x, y, bw, bh])
+        if n % 3 == 2:        # a near duplicate of the same category, half a cell away: suppressed by the occupancy
+            plant(f, x + 0.5, y + 0.25, bw * 1.1, bh * 0.9, 0.7, radius2=2.5)
+    for _ in range(n_distractors):
+        f = int(rng.random() * F) % F
+        x, y = rng.random() * (w - 1), rng.random() * (h - 1)
+        plant(f, x, y, 1.0 + 3.0 * rng.random(), 1.0 + 3.0 * rng.random(), 0.22 + 0.3 * rng.random(), radius2=2.5)
+    # a few cells with a negative width / height (never contribute to the hi-res map, still become seeds)
+    for _ in range(3):
+        f = int(rng.random() * F) % F
+        i, j = int(rng.random() * w) % w, int(rng.random() * h) % h
+        field[f, 1, j, i] = 0.6 + 0.2 * rng.random()
+        field[f, 4, j, i] = -0.5
+    return {'field': field.astype(np.float32), 'n_planted': n_objects,
+            'boxes': np.asarray(planted, dtype=np.float64).reshape(n_objects, 5)}
 
 
 def fields_digest(cif, caf):

@@ -57,6 +57,7 @@ def lib():
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.oracle_cifcaf_call.restype = ctypes.c_int64
         _lib.oracle_cifseeds.restype = ctypes.c_int64
+        _lib.oracle_cifdet_call.restype = ctypes.c_int64
     return _lib
 
 
@@ -134,6 +135,39 @@ def decode(cif, cif_stride, caf, caf_stride, skeleton, n_keypoints=None, params=
         'n_pre_nms': int(t['n_pre_nms'].value),
     }
     return out[:n].copy(), ids[:n].copy(), taps_out
+
+
+def decode_det(field, stride, params=None, max_detections_before_nms=120, taps=False):
+    """Oracle equivalent of torch.classes.openpifpaf_decoder.CifDet().call(field, stride) on a FRESH instance
+    (csrc/src/cifdet.cpp:24-80).  field [F,6,h,w] float32.  params.seed_threshold plays CifDetSeeds::threshold.
+    Returns (categories [N] i64, scores [N] f32, boxes [N,4] f32 (x1,y1,x2,y2)[, taps dict])."""
+    field = np.ascontiguousarray(field, dtype=np.float32)
+    F, ncomp, h, w = field.shape
+    assert ncomp == 6
+    p = params if params is not None else default_params()
+    cap = F * h * w + 1
+    cats = np.zeros((cap,), dtype=np.int64)
+    scores = np.zeros((cap,), dtype=np.float32)
+    boxes = np.zeros((cap, 4), dtype=np.float32)
+    H, W = (h - 1) * stride + 1, (w - 1) * stride + 1
+    t = {}
+    if taps:
+        t['cifhr'] = np.zeros((F, H, W), dtype=np.float32)
+        t['seeds_f'] = np.zeros((F * h * w,), dtype=np.int64)
+        t['seeds_vxywh'] = np.zeros((F * h * w, 5), dtype=np.float32)
+        t['n_seeds'] = ctypes.c_int64(0)
+    i64, f32 = ctypes.c_int64, ctypes.c_float
+    n = int(lib().oracle_cifdet_call(
+        _ptr(field, f32), i64(F), i64(h), i64(w), i64(stride), ctypes.byref(p), i64(max_detections_before_nms),
+        _ptr(cats, i64), _ptr(scores, f32), _ptr(boxes, f32), i64(cap),
+        _ptr(t.get('cifhr'), f32), _ptr(t.get('seeds_f'), i64), _ptr(t.get('seeds_vxywh'), f32), i64(F * h * w),
+        ctypes.byref(t['n_seeds']) if taps else None))
+    out = (cats[:n].copy(), scores[:n].copy(), boxes[:n].copy())
+    if not taps:
+        return out
+    ns = int(t['n_seeds'].value)
+    return out + ({'cifhr': t['cifhr'], 'seeds_f': t['seeds_f'][:ns].copy(),
+                   'seeds_vxywh': t['seeds_vxywh'][:ns].copy()},)
 
 
 def grow_connection_blend(caf, x, y, s, filter_sigmas=1.0, only_max=False):
@@ -223,3 +257,13 @@ def ref_decode(cif, cif_stride, caf, caf_stride, skeleton, n_keypoints=None,
          'seeds_f': sf.numpy().copy(), 'seeds_vxys': sv.numpy().copy(),
          'fwd': [x.clone().numpy() for x in fwd], 'bwd': [x.clone().numpy() for x in bwd]}
     return ann.numpy().copy(), ids.numpy().copy(), t
+
+
+def ref_decode_det(field, stride):
+    """Run the unmodified reference CifDet (csrc/src/cifdet.cpp) on a FRESH instance.  (CifDetHr is not exported
+    as a TorchScript class, module.cpp:76-102, so there are no stage taps on this side.)"""
+    import torch
+    dec = load_ref()
+    f_t = torch.from_numpy(np.ascontiguousarray(field, dtype=np.float32))
+    cats, scores, boxes = dec.CifDet().call(f_t, stride)
+    return cats.numpy().copy(), scores.numpy().copy(), boxes.numpy().copy().reshape(-1, 4)

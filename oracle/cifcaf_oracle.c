@@ -169,7 +169,7 @@ static float cifhr_value(const float* acc, int64_t F, int64_t H, int64_t W, doub
 
 /* ------------------------------------------------------------------ CifSeeds */
 
-typedef struct { int64_t f; float v, x, y, s; int64_t order; } seed_t;
+typedef struct { int64_t f; float v, x, y, s; int64_t order; float h; } seed_t;   /* s doubles as DetSeed::w, h = DetSeed::h */
 
 /* libstdc++ std::sort (bits/stl_algo.h: __introsort_loop + __final_insertion_sort,
  * _S_threshold = 16) restated for comp(a,b) = a.v > b.v, so that exact float ties
@@ -798,4 +798,99 @@ int64_t oracle_cifcaf_call(const float* cif, int64_t F, int64_t cif_h, int64_t c
     free(seeds_f); free(seeds_vxys); free(acc);
     free(anns);
     return keep;
+}
+
+
+/* ------------------------------------------------------------------ CifDet */
+
+/* src/cif_hr.cpp:124-150 (CifDetHr::accumulate).  field is [F][6][h][w]: conf at 1, x,y at 2,3, w,h at 4,5
+ * (headmeta.py:117-134: n_confidences 1, n_vectors 2, vector_offsets [True, False]). */
+void oracle_cifdethr_accumulate(const float* field, int64_t F, int64_t h, int64_t w, int64_t stride,
+                                double min_scale, double factor, const oracle_params_t* p, float* acc) {
+    int64_t H = (h - 1) * stride + 1, W = (w - 1) * stride + 1;
+    float min_scale_f = (float)(min_scale / (double)stride);
+    int64_t hw = h * w;
+    for (int64_t f = 0; f < F; f++) {
+        const float* cf = field + f * 6 * hw;
+        for (int64_t j = 0; j < h; j++) {
+            for (int64_t i = 0; i < w; i++) {
+                float v = cf[1 * hw + j * w + i];
+                if ((double)v < p->cifhr_threshold) continue;
+                float bw = cf[4 * hw + j * w + i];
+                float bh = cf[5 * hw + j * w + i];
+                if (bw < min_scale_f || bh < min_scale_f) continue;
+                float x = cf[2 * hw + j * w + i] * (float)stride;
+                float y = cf[3 * hw + j * w + i] * (float)stride;
+                float sigma = fmaxf(1.0f, (float)(0.1 * (double)fminf(bw, bh) * (double)stride));
+                float vn = (float)((double)(v / (float)p->cifhr_neighbors) * factor);
+                cifhr_add_gauss(acc, H, W, p->cifhr_revision, f, vn, x, y, sigma, 1.0f);
+            }
+        }
+    }
+}
+
+/* src/cifdet.cpp:24-80 on a FRESH instance (revision p->cifhr_revision), with CifDetSeeds::fill/get
+ * (src/cif_seeds.cpp:69-90, 117-139).  p->seed_threshold plays CifDetSeeds::threshold.
+ * Outputs: categories [cap] (f + 1), scores [cap], boxes [cap][4] (x1, y1, x2, y2); returns N <= max_detections.
+ * Optional taps: tap_cifhr [F][H][W]; tap_seeds_f / tap_seeds_vxywh [.][5] (cap tap_seeds_cap), *tap_n_seeds. */
+int64_t oracle_cifdet_call(const float* field, int64_t F, int64_t h, int64_t w, int64_t stride,
+                           const oracle_params_t* p, int64_t max_detections_before_nms,
+                           int64_t* out_categories, float* out_scores, float* out_boxes, int64_t cap,
+                           float* tap_cifhr, int64_t* tap_seeds_f, float* tap_seeds_vxywh, int64_t tap_seeds_cap,
+                           int64_t* tap_n_seeds) {
+    int64_t H = (h - 1) * stride + 1, W = (w - 1) * stride + 1, hw = h * w;
+    float* acc = (float*)calloc((size_t)(F * H * W), sizeof(float));
+    oracle_cifdethr_accumulate(field, F, h, w, stride, 0.0, 1.0, p, acc);      /* cifdet.cpp:31 */
+    if (tap_cifhr) memcpy(tap_cifhr, acc, sizeof(float) * (size_t)(F * H * W));
+
+    seed_t* seeds = (seed_t*)malloc(sizeof(seed_t) * (size_t)(F * hw + 1));
+    int64_t n = 0;
+    for (int64_t f = 0; f < F; f++) {                                          /* cif_seeds.cpp:69-90 */
+        const float* cf = field + f * 6 * hw;
+        for (int64_t j = 0; j < h; j++) {
+            for (int64_t i = 0; i < w; i++) {
+                float c = cf[1 * hw + j * w + i];
+                if ((double)c < p->seed_threshold) continue;
+                float x = cf[2 * hw + j * w + i] * (float)stride;
+                float y = cf[3 * hw + j * w + i] * (float)stride;
+                float v = (float)(0.9 * (double)cifhr_value(acc, F, H, W, p->cifhr_revision, f, x, y, -1.0f)
+                                  + 0.1 * (double)c);
+                if ((double)v < p->seed_threshold) continue;
+                seeds[n].f = f; seeds[n].v = v; seeds[n].x = x; seeds[n].y = y;
+                seeds[n].s = cf[4 * hw + j * w + i] * (float)stride;
+                seeds[n].h = cf[5 * hw + j * w + i] * (float)stride;
+                seeds[n].order = n;
+                n++;
+            }
+        }
+    }
+    if (p->seed_sort_stable) qsort(seeds, (size_t)n, sizeof(seed_t), seed_cmp);
+    else seed_std_sort(seeds, n);                                              /* cif_seeds.cpp:117-121 */
+    if (tap_n_seeds) *tap_n_seeds = n;
+    if (tap_seeds_f) for (int64_t k = 0; k < n && k < tap_seeds_cap; k++) {
+        tap_seeds_f[k] = seeds[k].f;
+        tap_seeds_vxywh[5 * k + 0] = seeds[k].v; tap_seeds_vxywh[5 * k + 1] = seeds[k].x;
+        tap_seeds_vxywh[5 * k + 2] = seeds[k].y; tap_seeds_vxywh[5 * k + 3] = seeds[k].s;
+        tap_seeds_vxywh[5 * k + 4] = seeds[k].h;
+    }
+
+    occupancy_t occ;
+    occupancy_reset(&occ, F, H, W, p);                                         /* cifdet.cpp:43 */
+    int64_t n_det = 0;
+    for (int64_t si = 0; si < n; si++) {                                       /* cifdet.cpp:50-66 */
+        const int64_t f = seeds[si].f;
+        const float c = seeds[si].v, x = seeds[si].x, y = seeds[si].y, bw = seeds[si].s, bh = seeds[si].h;
+        if (occupancy_get(&occ, f, x, y)) continue;
+        occupancy_set(&occ, f, x, y, 0.1 * (double)fminf(bw, bh));
+        if (n_det < cap) {
+            out_categories[n_det] = f + 1;
+            out_scores[n_det] = c;
+            out_boxes[4 * n_det + 0] = x - 0.5f * bw; out_boxes[4 * n_det + 1] = y - 0.5f * bh;
+            out_boxes[4 * n_det + 2] = x + 0.5f * bw; out_boxes[4 * n_det + 3] = y + 0.5f * bh;
+        }
+        n_det++;
+        if (n_det >= max_detections_before_nms) break;
+    }
+    free(occ.occ); free(seeds); free(acc);
+    return n_det;
 }

@@ -36,6 +36,15 @@ CASES = [
 ]
 
 
+DET_CASES = [
+    # name, n_categories, h, w, n_objects, seed, n_distractors, stride
+    ('det11_3cat_1', 3, 11, 11, 1, 2, 2, 16),
+    ('det41_80cat_6', 80, 41, 41, 6, 0, 4, 16),
+    ('det21x33_80cat_3', 80, 21, 33, 3, 1, 4, 16),
+    ('det51_80cat_150', 80, 51, 51, 150, 4, 10, 8),         # hits max_detections_before_nms = 120
+]
+
+
 def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
@@ -68,6 +77,14 @@ def main():
         np.savez_compressed(path, **data)
         print(name, 'N =', len(ann), 'seeds =', len(taps['seeds_f']), os.path.getsize(path), 'bytes')
     oc.ref_configure()
+    # CifDet (csrc/src/cifdet.cpp): raw output of a FRESH torch.classes.openpifpaf_decoder.CifDet instance
+    for name, n_cat, h, w, n_obj, seed, n_dis, stride in DET_CASES:
+        f = synth.make_det_fields(n_cat, h, w, n_obj, seed, n_dis)
+        cats, scores, boxes = oc.ref_decode_det(f['field'], stride)
+        path = os.path.join(out_dir, f'cifdet_{name}.npz')
+        np.savez_compressed(path, n_categories=n_cat, h=h, w=w, n_objects=n_obj, seed=seed, n_distractors=n_dis,
+                            stride=stride, field_sha256=sha(f['field']), categories=cats, scores=scores, boxes=boxes)
+        print(name, 'N =', len(cats), os.path.getsize(path), 'bytes')
 
 
 if __name__ == '__main__':

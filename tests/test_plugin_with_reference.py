@@ -56,6 +56,27 @@ def test_plugin_registers_and_is_selected(tmp_path):
         assert (p.force_complete, p.keypoint_threshold, p.keypoint_threshold_rel, p.seed_threshold,
                 p.nms_instance_threshold, p.nms_keypoint_threshold) == (1, 0.0, 0.0, 0.1, 0.0, 0.0), \\
             (p.force_complete, p.keypoint_threshold, p.seed_threshold)
+        # CifDet heads select the GPU detection decoder (decoder/cifdet.py:40-47)
+        det = openpifpaf.headmeta.CifDet('cifdet', 'cocodet', categories=['a', 'b', 'c'])
+        det.head_index, det.base_stride = 0, 16
+        args = parser.parse_args([])
+        openpifpaf.decoder.configure(args)
+        multi = openpifpaf.decoder.factory([det])
+        assert type(multi.decoders[0]).__name__ == 'CifDetB200', type(multi.decoders[0]).__name__
+        assert multi.decoders[0].native.n_categories == 3
+        # --dense-connections: CifCafDense semantics (decoder/cifcaf.py:17-78), concatenated skeleton
+        from openpifpaf.plugins.coco.constants import DENSER_COCO_PERSON_CONNECTIONS
+        caf25 = openpifpaf.headmeta.Caf('caf25', 'cocokp', keypoints=COCO_KEYPOINTS, sigmas=COCO_PERSON_SIGMAS,
+                                        skeleton=DENSER_COCO_PERSON_CONNECTIONS, sparse_skeleton=COCO_PERSON_SKELETON,
+                                        only_in_field_of_view=True)
+        caf25.head_index, caf25.base_stride = 2, 16
+        args = parser.parse_args(['--dense-connections'])
+        openpifpaf.decoder.configure(args)
+        multi = openpifpaf.decoder.factory([cif, caf, caf25])
+        top = multi.decoders[0]
+        assert type(top).__name__ == 'CifCafDenseB200', type(top).__name__
+        assert tuple(top.cifcaf.native.skeleton.shape) == (19 + len(DENSER_COCO_PERSON_CONNECTIONS), 2)
+        openpifpaf.decoder.configure(parser.parse_args([]))
         print('PLUGIN_OK')
     ''')
     env = dict(os.environ, PYTHONPATH=f'{stage}:{ROOT}')
