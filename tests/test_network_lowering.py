@@ -189,12 +189,13 @@ def test_k30_wholebody_lowering_reproduces_oracle_net():
     assert head['kind'] == 'heads' and head['w'].shape == (133 * 5 + 160 * 8, 2048)
 
 
-def test_random_plan_has_reference_architecture():
+@pytest.mark.parametrize('fuse', [False, True])
+def test_random_plan_has_reference_architecture(fuse):
     plan = network.random_plan('shufflenetv2k16')
     assert [len(s) for s in plan['stages']] == [4, 8, 4]
     assert plan['conv5'][0].shape[:2] == (1392, 1392)
     assert [h['w'].shape[0] for h in plan['heads']] == [85, 152]
-    tensors, ops, _ = network.build_ops(plan, 641, 641)
+    tensors, ops, _ = network.build_ops(plan, 641, 641, fuse_dw=fuse)
     gmac = 0.0
     for o in ops:
         hh, ww, _ = tensors[o['out']] if 'out' in o else tensors[o['in']]
@@ -209,7 +210,8 @@ def test_random_plan_has_reference_architecture():
         elif o['kind'] == 'input_conv':
             gmac += hh * ww * o['w'].size / 1e9
     assert abs(gmac - 36.58) < 0.2, gmac       # 36.58 GMAC / image @641
-    assert sum(o['kind'] == 'dw_conv1x1' for o in ops) == 3 + 7        # stride-1 blocks of stages 2 and 3 (N <= 512)
+    # fused schedule: the stride-1 blocks of stages 2 and 3 (N <= 512)
+    assert sum(o['kind'] == 'dw_conv1x1' for o in ops) == ((3 + 7) if fuse else 0)
 
 
 @pytest.mark.parametrize('fuse', [True, False])
