@@ -217,7 +217,27 @@ def forward_profile(net, images, pk):
     ms_op, kind, flops, nbytes = net.forward_timed(images)
     sel = kind == 1
     gemm_ms = float(ms_op[sel].sum())
+    # every tcgen05 GEMM launch against ITS OWN bound: the slower of (algorithmic bytes / measured HBM peak) and
+    # (algorithmic FLOPs / measured bf16 peak).  Stage-4 / conv5 launches (K, N >= 696) are tensor bound, the rest
+    # HBM bound; `frac` below = sum of the bound times / sum of the measured times.
+    t_hbm = nbytes[sel] / (pk['hbm_gbs'] * 1e9) * 1e3
+    t_ten = flops[sel] / (pk['bf16_tflops'] * 1e12) * 1e3
+    is_hbm = t_hbm >= t_ten
+    ms_g = ms_op[sel]
+
+    def cls(mask, bound_ms, unit_scale, work, unit, peak):
+        if not mask.any():
+            return None
+        t = float(ms_g[mask].sum())
+        return {'launches': int(mask.sum()), 'ms': round(t, 3), 'achieved': round(float(work[mask].sum()) / (t * 1e-3) / unit_scale, 1),
+                'peak': peak, 'unit': unit, 'frac': round(float(bound_ms[mask].sum()) / t, 4)}
+    per_bound = {
+        'hbm_bound': cls(is_hbm, t_hbm, 1e9, nbytes[sel], 'GB/s', pk['hbm_gbs']),
+        'tensor_bound': cls(~is_hbm, t_ten, 1e12, flops[sel], 'TFLOP/s', pk['bf16_tflops']),
+        'frac_of_own_bound': round(float(np.maximum(t_hbm, t_ten).sum()) / gemm_ms, 4),
+    }
     return ms_op, kind, flops, nbytes, {
+        'per_bound': per_bound,
         'forward_ms': round(float(ms_op.sum()), 3),
         'by_kind_ms': {'input_conv': round(float(ms_op[kind == 0].sum()), 3), 'gemm_tc': round(gemm_ms, 3),
                        'dwconv': round(float(ms_op[kind == 2].sum()), 3),
@@ -397,6 +417,7 @@ def run_b200(args):
             'forward_tflops': prof['forward_tflops'],
             'forward_tensor_frac_of_measured_bf16': round(prof['forward_tflops'] / pk['bf16_tflops'], 4),
             'forward_hbm_frac': round(prof['forward_gbs'] / pk['hbm_gbs'], 4),
+            'per_bound': prof['per_bound'],
         }
         # ---- decoder-only on the planted fields
         pred.decode_fields_override = None

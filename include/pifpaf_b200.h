@@ -293,6 +293,14 @@ int pifpaf_net_dw_conv1x1_scatter(pifpaf_net_t* net, int32_t in_tensor, int32_t 
 int pifpaf_net_heads(pifpaf_net_t* net, int32_t in_tensor, int32_t k_cols, int32_t n_heads,
                      const int32_t* n_fields, const int32_t* n_comp, const int32_t* comp_ops,
                      const float* weight, const float* bias);
+/* The same with `upsample_stride` > 1 heads (heads.py:307-343: the conv emits n_fields*n_comp*up*up channels,
+ * torch.nn.PixelShuffle(up) and the crop [ (up-1)/2, size - ceil((up-1)/2) ) follow): the epilogue writes conv
+ * channel c*up*up + dy*up + dx of cell (y, x) to output channel c at (y*up + dy - low, x*up + dx - low); index
+ * fields are added in the up-sampled grid.  weight [sum n_fields*n_comp*up*up][k_cols].  Outputs
+ * [B][n_fields][n_comp][h*up - low - high][w*up - low - high]. */
+int pifpaf_net_heads_upsampled(pifpaf_net_t* net, int32_t in_tensor, int32_t k_cols, int32_t n_heads,
+                               const int32_t* n_fields, const int32_t* n_comp, const int32_t* comp_ops,
+                               int32_t upsample_stride, const float* weight, const float* bias);
 int pifpaf_net_head_output(pifpaf_net_t* net, int32_t head, float** dev_ptr,
                            int32_t* n_fields, int32_t* n_comp, int32_t* h, int32_t* w);
 

@@ -21,6 +21,7 @@
 // has no fused multiply-adds and parity needs the same roundings.
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -49,6 +50,7 @@ struct GrowParams {
     int reverse_match, greedy;
     double occ_reduction, occ_min_scale_reduced;
     double nms_suppression, nms_instance_threshold, nms_keypoint_threshold;
+    float defer_radius;      // k_grow: a seed within defer_radius * scale of a seed picked in the same round waits
 };
 
 // ---------------------------------------------------------------------------
@@ -946,7 +948,8 @@ __global__ void __launch_bounds__(32 * GROW_MAX_WORKERS) k_grow(Dims d, Graph gr
     __shared__ int s_sel[GROW_MAX_WORKERS];       // seed index (or initial-annotation index) per worker
     __shared__ int s_slot[GROW_MAX_WORKERS];      // output slot, or -1 if dropped
     __shared__ int s_wc[GROW_MAX_WORKERS];
-    __shared__ int s_nsel, s_ptr, s_nann, s_over;
+    __shared__ float s_px[GROW_MAX_WORKERS], s_py[GROW_MAX_WORKERS], s_pr[GROW_MAX_WORKERS];   // picks: x, y, scale
+    __shared__ int s_nsel, s_ptr, s_nann, s_over, s_scan_end, s_stop;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = blockDim.x >> 5;
     GrowShared g;
@@ -1011,70 +1014,129 @@ __global__ void __launch_bounds__(32 * GROW_MAX_WORKERS) k_grow(Dims d, Graph gr
     }
 
     // ---- seeds
+    // Round structure with DEFERRAL.  The seeds of one person crowd the top of the sorted list (every joint casts
+    // a dozen high seeds), so "the next W uncovered seeds" would mostly be W seeds of the same one or two people,
+    // all but the first dropped at commit time.  A seed close to a seed already picked in this round is therefore
+    // DEFERRED: not grown now, in the expectation that the picked neighbour's annotation will cover it.  The commit
+    // walk stays exact: seeds are resolved strictly in order; the first deferred seed that turns out NOT to be
+    // covered by the annotations committed before it stops the walk (s_ptr = that seed; later picks of this round
+    // are thrown away and re-examined in the next round, which picks that seed first).  The heuristic only decides
+    // how much speculative work is wasted, never the result.
+    const float defer_k = gp.defer_radius;
     while (!s_over) {
-        // 1. the next W seeds (index >= s_ptr) the occupancy map does not cover
-        if (tid == 0) s_nsel = 0;
+        // 1. selection: scan from s_ptr in chunks of blockDim seeds, in order
+        if (tid == 0) { s_nsel = 0; s_scan_end = s_ptr; }
         __syncthreads();
         int ptr = s_ptr;
         while (ptr < ns) {
             const int idx = ptr + tid;
-            bool flag = false;
+            bool avail = false;
+            float4 sd = make_float4(0.f, 0.f, 0.f, 0.f);
             if (idx < ns) {
-                const float4 s = sv[idx];
-                flag = !occ_get(occ, sf[idx], (double)s.y, (double)s.z);
+                sd = sv[idx];
+                avail = !occ_get(occ, sf[idx], (double)sd.y, (double)sd.z);
             }
-            const unsigned m = __ballot_sync(0xffffffffu, flag);
-            if (lane == 0) s_wc[warp] = __popc(m);
+            int n_known = s_nsel;                 // picks of earlier chunks of this round
+            if (avail && defer_k > 0.f)
+                for (int k = 0; k < n_known && avail; k++) {
+                    const float r = defer_k * fmaxf(s_pr[k], sd.w);
+                    if (fabsf(sd.y - s_px[k]) <= r && fabsf(sd.z - s_py[k]) <= r) avail = false;
+                }
+            for (;;) {
+                // first still-available seed of the chunk
+                const unsigned m = __ballot_sync(0xffffffffu, avail);
+                if (lane == 0) s_wc[warp] = m ? (warp * 32 + __ffs(m) - 1) : INT_MAX;
+                __syncthreads();
+                int first = INT_MAX;
+                for (int w2 = 0; w2 < W; w2++) first = min(first, s_wc[w2]);
+                if (first == INT_MAX) { __syncthreads(); break; }
+                if (tid == first) {
+                    const int k = s_nsel;
+                    s_sel[k] = idx; s_px[k] = sd.y; s_py[k] = sd.z; s_pr[k] = sd.w;
+                    s_nsel = k + 1;
+                    avail = false;
+                }
+                __syncthreads();
+                const int k = s_nsel - 1;
+                if (avail && defer_k > 0.f) {
+                    const float r = defer_k * fmaxf(s_pr[k], sd.w);
+                    if (fabsf(sd.y - s_px[k]) <= r && fabsf(sd.z - s_py[k]) <= r) avail = false;
+                }
+                if (k + 1 == W) break;            // uniform
+            }
             __syncthreads();
-            int before = s_nsel, total = 0;
-            for (int w2 = 0; w2 < W; w2++) { if (w2 < warp) before += s_wc[w2]; total += s_wc[w2]; }
-            const int pos = before + __popc(m & ((1u << lane) - 1u));
-            if (flag && pos < W) s_sel[pos] = idx;
-            __syncthreads();
-            if (tid == 0) s_nsel = min(W, s_nsel + total);
-            __syncthreads();
-            if (s_nsel == W) break;
+            if (s_nsel == W) { if (tid == 0) s_scan_end = s_sel[W - 1] + 1; break; }
             ptr += blockDim.x;
+            if (tid == 0) s_scan_end = min(ptr, ns);
         }
+        __syncthreads();
         const int n_sel = s_nsel;
-        if (n_sel == 0) break;
-        // 2. grow, one warp per selected seed
+        const int scan_end = s_scan_end;
+        if (n_sel == 0) break;                    // every remaining seed is covered by the map
+        // 2. grow, one warp per picked seed
         if (warp < n_sel) {
             const int si = s_sel[warp];
-            const float4 s = sv[si];
+            const float4 sd = sv[si];
             const int f = sf[si];
             for (int k = lane; k < d.K; k += 32) {
                 WJoint j; j.v = 0.0; j.x = 0.f; j.y = 0.f; j.s = 0.f; j.pad = 0;
-                if (k == f) { j.v = (double)s.x; j.x = s.y; j.y = s.z; j.s = s.w; }
+                if (k == f) { j.v = (double)sd.x; j.x = sd.y; j.y = sd.z; j.s = sd.w; }
                 w.joints[k] = j;
             }
             warp_grow(g, w, true, 1.0, false, lane);
         }
+        if (tid == 0) s_stop = INT_MAX;
         __syncthreads();
-        // 3. commit decisions in seed order (thread 0; W <= 16 seeds x earlier kept annotations)
+        // 3a. keep / drop of the picks among themselves, in seed order (picks are in ascending seed order)
         if (tid == 0) {
-            int n_keep = 0;
             for (int i = 0; i < n_sel; i++) {
                 const int si = s_sel[i];
-                const float4 s = sv[si];
+                const float4 sd = sv[si];
                 const int f = sf[si];
                 bool covered = false;
                 for (int a = 0; a < i && !covered; a++) {
                     if (s_slot[a] < 0) continue;
-                    if (f < d.F && f < d.K) covered = occ_joint_covers(occ, joints_of(a)[f], (double)s.y, (double)s.z);
+                    if (f < d.F && f < d.K) covered = occ_joint_covers(occ, joints_of(a)[f], (double)sd.y, (double)sd.z);
                 }
-                if (covered) { s_slot[i] = -1; continue; }
+                s_slot[i] = covered ? -1 : 0;
+            }
+        }
+        __syncthreads();
+        // 3b. the first deferred seed that no earlier kept pick covers stops the walk
+        for (int idx = s_ptr + tid; idx < scan_end; idx += blockDim.x) {
+            bool is_pick = false;
+            for (int k = 0; k < n_sel; k++) is_pick |= (s_sel[k] == idx);
+            if (is_pick) continue;
+            const float4 sd = sv[idx];
+            const int f = sf[idx];
+            if (occ_get(occ, f, (double)sd.y, (double)sd.z)) continue;        // covered by the map: resolved
+            bool covered = false;
+            if (f < d.F && f < d.K)
+                for (int a = 0; a < n_sel && s_sel[a] < idx && !covered; a++) {
+                    if (s_slot[a] < 0) continue;
+                    covered = occ_joint_covers(occ, joints_of(a)[f], (double)sd.y, (double)sd.z);
+                }
+            if (!covered) atomicMin(&s_stop, idx);
+        }
+        __syncthreads();
+        // 3c. output slots of the kept picks before the stop
+        if (tid == 0) {
+            const int stop = s_stop;
+            int n_keep = 0;
+            for (int i = 0; i < n_sel; i++) {
+                if (s_slot[i] < 0) continue;
+                if (s_sel[i] > stop) { s_slot[i] = -1; continue; }
                 if (s_nann + n_keep >= d.max_ann) { s_over = 1; s_slot[i] = -1; continue; }
                 s_slot[i] = s_nann + n_keep;
                 n_keep++;
             }
             s_nann += n_keep;
-            s_ptr = s_sel[n_sel - 1] + 1;
+            s_ptr = min(stop, scan_end);
         }
         __syncthreads();
         if (warp < n_sel && s_slot[warp] >= 0) commit_mine(s_slot[warp], -1);
         __syncthreads();          // occupancy marks visible to the next selection
-        if (n_sel < W) break;     // the seed list is exhausted
+        if (s_ptr >= ns) break;
     }
     if (tid == 0) {
         n_anns[b] = s_nann;
@@ -1301,6 +1363,7 @@ struct pifpaf_decoder {
     int* d_in_init_count = nullptr; int in_init_cap = 0;
     // pinned staging
     cudaStream_t own_stream = nullptr;
+    float defer_radius = 6.0f;        // PIFPAF_GROW_DEFER (a performance heuristic of k_grow, never changes results)
     GrowLayout grow{};                // warps (annotations in flight) per image and shared-memory plan of k_grow
     unsigned epoch = 1;               // occupancy tags: epoch (seed loop), epoch+1 (NMS)
     Dims last{};
@@ -1489,6 +1552,7 @@ int pifpaf_decoder_create(pifpaf_decoder_t** out, int32_t device, int32_t n_keyp
     TRY_D(cudaStreamCreateWithFlags(&dec->own_stream, cudaStreamNonBlocking));
 
     dec->grow = plan_grow(K, C);
+    if (const char* e = std::getenv("PIFPAF_GROW_DEFER")) dec->defer_radius = (float)std::atof(e);
     TRY_D(cudaFuncSetAttribute(k_grow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec->grow.smem));
     TRY_D(cudaFuncSetAttribute(k_force_complete, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec->grow.smem));
     const size_t ns = (sizeof(double) + 2 * sizeof(int)) * A + 16;
@@ -1537,6 +1601,7 @@ int pifpaf_decoder_decode_device(pifpaf_decoder_t* dec, const float* cif_dev, co
     gp.occ_reduction = p.occ_reduction; gp.occ_min_scale_reduced = p.occ_min_scale / p.occ_reduction;
     gp.nms_suppression = p.nms_suppression; gp.nms_instance_threshold = p.nms_instance_threshold;
     gp.nms_keypoint_threshold = p.nms_keypoint_threshold;
+    gp.defer_radius = dec->defer_radius;
     Graph gr{dec->d_skeleton, dec->d_adj_start, dec->d_adj_edge, dec->d_edge_lookup, dec->d_pair_id};
 
     // CifHr (src/cifcaf.cpp:140-142: accumulate(cif, stride, min_scale 0.0, factor 1.0)).  A new epoch

@@ -155,7 +155,9 @@ enum { MODE_PLAIN = 0, MODE_SHUFFLE = 1, MODE_HEADS = 2, MODE_SCATTER = 3 };
 struct DestGroup { __nv_bfloat16* base; int ld; int pad; };
 static_assert(sizeof(DestGroup) == 16, "DestGroup is copied to shared memory as 16-byte entries");
 
-struct HeadCol { int head; int plane; int op; int pad; };   // per GEMM output column (heads mode)
+// per GEMM output column (heads mode): plane = field * n_comp + comp; sub = (dy << 8) | dx is the PixelShuffle
+// position of this conv channel inside the up x up block of its cell (heads.py:333-343), 0 without upsampling
+struct HeadCol { int head; int plane; int op; int sub; };
 
 struct GemmArgs {
     int M, N, K;                 // rows, real output channels, k extent (columns of the A view)
@@ -174,7 +176,8 @@ struct GemmArgs {
     // heads
     const HeadCol* head_cols;    // [n_blocks * block_n]
     float* head_base[4]; int head_planes[4];
-    int hw, w;                   // pixels per image, field width
+    int hw, w;                   // pixels per image, field width (of the conv output)
+    int up, up_low, out_h, out_w;   // PixelShuffle factor, low crop, head output size (== h, w when up == 1)
     // implicit-GEMM convolution (conv_k > 0): one M tile = a PH x PW patch of output pixels of one image;
     // K blocks run over taps x 64-channel blocks; A comes from a 4-D tensor map {C, W, H, B}
     int conv_k, conv_stride, conv_pad, conv_cblocks;
@@ -262,17 +265,22 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, int m, int n0,
     if (g.mode == MODE_HEADS) {
         const int b = m / g.hw, pix = m - b * g.hw;
         const int y = pix / g.w, x = pix - y * g.w;
+        const int out_hw = g.out_h * g.out_w;
 #pragma unroll
         for (int j = 0; j < CHUNK; j++) {
             const int n = n0 + j;
             if (n >= g.N) break;
             const HeadCol hc = g.head_cols[n];
+            // PixelShuffle(up) + crop [low, size - high) (heads.py:333-343): conv channel c*up*up + dy*up + dx of
+            // cell (y, x) is output channel c at (y*up + dy - low, x*up + dx - low)
+            const int oy = y * g.up + (hc.sub >> 8) - g.up_low, ox = x * g.up + (hc.sub & 255) - g.up_low;
+            if (oy < 0 || oy >= g.out_h || ox < 0 || ox >= g.out_w) continue;
             float v = acc[j] + bv[j];
             if (hc.op == 1) v = sigmoid_f(v);
-            else if (hc.op == 2) v += (float)x;
-            else if (hc.op == 3) v += (float)y;
+            else if (hc.op == 2) v += (float)ox;
+            else if (hc.op == 3) v += (float)oy;
             else if (hc.op == 4) v = softplus_f(v);
-            g.head_base[hc.head][((size_t)b * g.head_planes[hc.head] + hc.plane) * g.hw + pix] = v;
+            g.head_base[hc.head][((size_t)b * g.head_planes[hc.head] + hc.plane) * out_hw + oy * g.out_w + ox] = v;
         }
         return;
     }
@@ -973,7 +981,10 @@ k_dw_gemm(const __grid_constant__ CUtensorMap tmap_win, const __grid_constant__ 
     unsigned char* win = b_st + (size_t)f.bs * b_bytes;
     float* bias_s = reinterpret_cast<float*>(win + (size_t)f.ws * T::BYTES);
     DestGroup* dest_s = reinterpret_cast<DestGroup*>(bias_s + f.n_pad);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(dest_s + f.n_pad / CHUNK);
+    // depthwise weights [25][C] + bias [C], staged once per CTA: a per-K-block reload from global memory put the
+    // depthwise warps on the long scoreboard (ncu round 2: 1.4 - 2.8 warps per issue, the L1 is carved down to a few KB)
+    float* dww_s = reinterpret_cast<float*>(dest_s + f.n_pad / CHUNK);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(dww_s + 26 * (size_t)f.C);
     uint64_t* win_full = bars;                 uint64_t* win_empty = win_full + f.ws;
     uint64_t* a_full = win_empty + f.ws;       uint64_t* a_empty = a_full + f.as;
     uint64_t* b_full = a_empty + f.as;         uint64_t* b_empty = b_full + f.bs;
@@ -988,6 +999,8 @@ k_dw_gemm(const __grid_constant__ CUtensorMap tmap_win, const __grid_constant__ 
     for (int i = threadIdx.x; i < f.n_pad; i += FD_THREADS) bias_s[i] = g.bias[i];
     if (g.mode == MODE_SCATTER)
         for (int i = threadIdx.x; i < f.n_pad / CHUNK; i += FD_THREADS) dest_s[i] = g.dest[i];
+    for (int i = threadIdx.x; i < 25 * f.C; i += FD_THREADS) dww_s[i] = f.dw_weight[i];
+    for (int i = threadIdx.x; i < f.C; i += FD_THREADS) dww_s[25 * f.C + i] = f.dw_bias[i];
     if (warp == 1) {
         if (lane == 0) {
             for (int i = 0; i < f.ws; i++) { mbar_init(&win_full[i], 1); mbar_init(&win_empty[i], FD_DW_WARPS); }
@@ -1077,11 +1090,11 @@ k_dw_gemm(const __grid_constant__ CUtensorMap tmap_win, const __grid_constant__ 
                 if (inside) {
 #pragma unroll
                     for (int tp = 0; tp < 25; tp++) {
-                        const float2 wv = cok ? __ldg(reinterpret_cast<const float2*>(f.dw_weight + (size_t)tp * f.C + c0))
+                        const float2 wv = cok ? *reinterpret_cast<const float2*>(dww_s + (size_t)tp * f.C + c0)
                                               : make_float2(0.f, 0.f);
                         wgt[tp][0] = wv.x; wgt[tp][1] = wv.y;
                     }
-                    if (cok) { const float2 bv = __ldg(reinterpret_cast<const float2*>(f.dw_bias + c0)); bias0 = bv.x; bias1 = bv.y; }
+                    if (cok) { const float2 bv = *reinterpret_cast<const float2*>(dww_s + 25 * (size_t)f.C + c0); bias0 = bv.x; bias1 = bv.y; }
                 }
                 float acc[4][4][2];
                 mbar_wait(&win_full[wi], wph);
@@ -1190,9 +1203,9 @@ k_dw_gemm(const __grid_constant__ CUtensorMap tmap_win, const __grid_constant__ 
     }
 }
 
-size_t fused_smem_bytes(int ws, int as, int bs, int n_pad) {
+size_t fused_smem_bytes(int ws, int as, int bs, int n_pad, int c_dw) {
     return 1024 + (size_t)as * BM * BK * 2 + (size_t)bs * n_pad * BK * 2 + (size_t)ws * DwTile<1, PH, PW, 4, 1>::BYTES +
-           (size_t)n_pad * 5 + (size_t)(2 * (ws + as + bs) + 4) * 8 + 64;
+           (size_t)n_pad * 5 + (size_t)c_dw * 26 * 4 + (size_t)(2 * (ws + as + bs) + 4) * 8 + 64;
 }
 
 // ------------------------------------------------------------------ input conv: f32 NCHW [B,3,H,W] -> bf16 NHWC
@@ -1970,15 +1983,17 @@ int pifpaf_net_dw_conv1x1_scatter(pifpaf_net_t* net, int32_t in_tensor, int32_t 
     g.tiles_x = (g.Wo + PW - 1) / PW; g.tiles_y = (g.Ho + PH - 1) / PH;
     op.a_tensor = in_tensor; op.rows_per_image = g.Ho * g.Wo; op.tiles_per_image = g.tiles_x * g.tiles_y;
     // ring depths: as deep as the shared memory allows, windows first (their TMA has the longest latency)
-    const int cand[][3] = {{3, 3, 2}, {3, 2, 2}, {2, 2, 2}, {2, 2, 1}, {1, 1, 1}};
+    // (an A stage is written only after the depthwise warps hold their results in registers, so one A stage costs
+    // little; a single B stage would expose the weight TMA latency in every K block)
+    const int cand[][3] = {{3, 3, 2}, {3, 2, 2}, {2, 2, 2}, {2, 1, 2}, {2, 2, 1}, {1, 1, 1}};
     bool fits = false;
     for (const auto& c : cand) {
-        if (fused_smem_bytes(c[0], c[1], c[2], f.n_pad) <= GEMM_SMEM_BUDGET) {
+        if (fused_smem_bytes(c[0], c[1], c[2], f.n_pad, C) <= GEMM_SMEM_BUDGET) {
             f.ws = c[0]; f.as = c[1]; f.bs = c[2]; fits = true; break;
         }
     }
     PIFPAF_CHECK_ARG(fits, "fused depthwise -> 1x1 op does not fit in shared memory");
-    op.smem = fused_smem_bytes(f.ws, f.as, f.bs, f.n_pad);
+    op.smem = fused_smem_bytes(f.ws, f.as, f.bs, f.n_pad, C);
     op.n_real = n_real;
     op.flops_per_image = 2.0 * (double)op.rows_per_image * ((double)nnz + 25.0 * channels);
     op.bytes_per_image = (double)op.rows_per_image * (channels + n_real) * 2.0;     // dw input once + 1x1 output once
@@ -1996,27 +2011,42 @@ int pifpaf_net_dw_conv1x1_scatter(pifpaf_net_t* net, int32_t in_tensor, int32_t 
 int pifpaf_net_heads(pifpaf_net_t* net, int32_t in_tensor, int32_t k_cols, int32_t n_heads,
                      const int32_t* n_fields, const int32_t* n_comp, const int32_t* comp_ops,
                      const float* weight, const float* bias) {
+    return pifpaf_net_heads_upsampled(net, in_tensor, k_cols, n_heads, n_fields, n_comp, comp_ops, 1, weight, bias);
+}
+
+int pifpaf_net_heads_upsampled(pifpaf_net_t* net, int32_t in_tensor, int32_t k_cols, int32_t n_heads,
+                               const int32_t* n_fields, const int32_t* n_comp, const int32_t* comp_ops,
+                               int32_t upsample_stride, const float* weight, const float* bias) {
     PIFPAF_CHECK_ARG(net != nullptr && weight != nullptr && n_fields && n_comp && comp_ops, "null argument");
     PIFPAF_CHECK_ARG(n_heads >= 1 && n_heads <= 4, "1..4 heads supported");
+    PIFPAF_CHECK_ARG(upsample_stride >= 1 && upsample_stride <= 8, "upsample_stride must be in [1, 8]");
     PIFPAF_CHECK_ARG(in_tensor >= 0 && in_tensor < (int)net->tensors.size(), "bad tensor id");
     PIFPAF_CUDA_TRY(cudaSetDevice(net->device));
     const Tensor& tin = net->tensors[in_tensor];
+    const int up = upsample_stride, up2 = up * up;
+    // heads.py:336-343: low_cut = (up - 1) / 2, high_cut = ceil((up - 1) / 2)
+    const int low = (up - 1) / 2, high = up / 2;
+    const int out_h = tin.h * up - low - high, out_w = tin.w * up - low - high;
+    PIFPAF_CHECK_ARG(out_h >= 1 && out_w >= 1, "feature map too small for this upsample_stride");
     int n_total = 0;
-    for (int i = 0; i < n_heads; i++) n_total += n_fields[i] * n_comp[i];
+    for (int i = 0; i < n_heads; i++) n_total += n_fields[i] * n_comp[i] * up2;
     Op op; op.kind = OP_GEMM;
     int rc = emit_gemm(net, op, in_tensor, 0, k_cols, n_total, weight, bias);
     if (rc != PIFPAF_OK) return rc;
     GemmArgs& g = op.g;
     g.mode = MODE_HEADS; g.relu = 0;
-    op.bytes_per_image += (double)op.rows_per_image * op.n_real * 4.0;
+    op.bytes_per_image += (double)out_h * out_w * (op.n_real / up2) * 4.0;
     std::vector<HeadCol> cols((size_t)g.block_n * g.n_blocks, HeadCol{0, 0, 0, 0});
     int col = 0, op_off = 0;
     for (int i = 0; i < n_heads; i++) {
         for (int f = 0; f < n_fields[i]; f++)
-            for (int c = 0; c < n_comp[i]; c++) cols[col++] = HeadCol{i, f * n_comp[i] + c, comp_ops[op_off + c], 0};
+            for (int c = 0; c < n_comp[i]; c++)
+                for (int dy = 0; dy < up; dy++)
+                    for (int dx = 0; dx < up; dx++)
+                        cols[col++] = HeadCol{i, f * n_comp[i] + c, comp_ops[op_off + c], (dy << 8) | dx};
         op_off += n_comp[i];
         net->head_fields[i] = n_fields[i]; net->head_comp[i] = n_comp[i];
-        net->head_elems[i] = (size_t)net->max_batch * n_fields[i] * n_comp[i] * tin.h * tin.w;
+        net->head_elems[i] = (size_t)net->max_batch * n_fields[i] * n_comp[i] * out_h * out_w;
         rc = net_alloc(net, &net->head_out[0][i], net->head_elems[i], true);
         if (rc != PIFPAF_OK) return rc;
         g.head_base[i] = net->head_out[0][i];
@@ -2026,7 +2056,8 @@ int pifpaf_net_heads(pifpaf_net_t* net, int32_t in_tensor, int32_t k_cols, int32
     rc = net_upload(net, &d_cols, cols); if (rc != PIFPAF_OK) return rc;
     g.head_cols = d_cols;
     g.hw = tin.h * tin.w; g.w = tin.w;
-    net->n_heads = n_heads; net->head_h = tin.h; net->head_w = tin.w;
+    g.up = up; g.up_low = low; g.out_h = out_h; g.out_w = out_w;
+    net->n_heads = n_heads; net->head_h = out_h; net->head_w = out_w;
     net->ops.push_back(op);
     return PIFPAF_OK;
 }

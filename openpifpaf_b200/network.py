@@ -74,15 +74,18 @@ def _heads_plan(shell, base):
     heads = []
     for hn in shell.head_nets:
         m = hn.meta
-        if getattr(m, 'upsample_stride', 1) != 1:
-            raise RuntimeError('upsample_stride > 1 heads are not supported')
+        up = int(getattr(m, 'upsample_stride', 1))
         ncomp = 1 + m.n_confidences + m.n_vectors * 2 + m.n_scales
         heads.append({
-            'w': hn.conv.weight.detach().float().cpu().numpy().reshape(m.n_fields * ncomp, -1),
+            # upsample_stride > 1 (heads.py:307-343): the conv has n_fields * n_comp * up^2 channels, PixelShuffle(up)
+            # and the crop run in the GEMM epilogue (pifpaf_net_heads_upsampled)
+            'w': hn.conv.weight.detach().float().cpu().numpy().reshape(m.n_fields * ncomp * up * up, -1),
             'b': hn.conv.bias.detach().float().cpu().numpy(),
-            'n_fields': int(m.n_fields), 'n_comp': int(ncomp),
+            'n_fields': int(m.n_fields), 'n_comp': int(ncomp), 'upsample': up,
             'ops': head_ops(m.n_confidences, m.n_vectors, m.n_scales, tuple(m.vector_offsets)),
-            'stride': int(base.stride)})
+            'stride': int(base.stride) // up})
+    if len({hd['upsample'] for hd in heads}) > 1:
+        raise RuntimeError('heads with different upsample_stride values are not supported')
     return heads
 
 
@@ -587,17 +590,12 @@ def build_ops(plan, in_h, in_w, layout=None, fuse_dw=None):
     c5 = w5.shape[0]
     t5 = tensor(h, w, pad16(c5))
     conv1x1(cur, 0, lay.cols(), lay.width, (w5, b5), True, t5)
-    heads = plan['heads']
-    ops.append({'kind': 'heads', 'in': t5, 'k_cols': c5,
-                'n_fields': [hd['n_fields'] for hd in heads], 'n_comp': [hd['n_comp'] for hd in heads],
-                'ops': [o for hd in heads for o in hd['ops']],
-                'w': _f32(np.concatenate([_f32(hd['w']) for hd in heads], axis=0)),
-                'b': _f32(np.concatenate([_f32(hd['b']) for hd in heads], axis=0))})
+    ops.append(_heads_op(plan['heads'], t5, c5))
     return tensors, ops, {'block_outputs': block_outputs, 'feature': (t5, _Layout(c5, split=False))}
 
 
 def _heads_op(heads, t_in, k_cols):
-    return {'kind': 'heads', 'in': t_in, 'k_cols': k_cols,
+    return {'kind': 'heads', 'in': t_in, 'k_cols': k_cols, 'upsample': int(heads[0].get('upsample', 1)),
             'n_fields': [hd['n_fields'] for hd in heads], 'n_comp': [hd['n_comp'] for hd in heads],
             'ops': [o for hd in heads for o in hd['ops']],
             'w': _f32(np.concatenate([_f32(hd['w']) for hd in heads], axis=0)),
@@ -738,7 +736,8 @@ class CompiledNet:
                 nf = (ctypes.c_int32 * n)(*o['n_fields'])
                 nc = (ctypes.c_int32 * n)(*o['n_comp'])
                 ops_c = (ctypes.c_int32 * len(o['ops']))(*o['ops'])
-                _lib.check(L.pifpaf_net_heads(H, o['in'], o['k_cols'], n, nf, nc, ops_c, _ptr(o['w']), _ptr(o['b'])))
+                _lib.check(L.pifpaf_net_heads_upsampled(H, o['in'], o['k_cols'], n, nf, nc, ops_c, int(o.get('upsample', 1)),
+                                                        _ptr(o['w']), _ptr(o['b'])))
             else:
                 raise RuntimeError(o['kind'])
 

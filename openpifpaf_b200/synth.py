@@ -225,7 +225,7 @@ def make_batch(workload='cocokp', batch=8, h=41, w=41, n_people=None, seed=0, n_
     }
 
 
-def make_det_fields(n_categories=80, h=41, w=41, n_objects=6, seed=0, n_distractors=4):
+def make_det_fields(n_categories=80, h=41, w=41, n_objects=6, seed=0, n_distractors=4, n_overlapping=0):
     """One image worth of CifDet fields ("planted boxes"): [F,6,h,w] f32 -- intensity(unused), confidence, x, y
     (cell index added, like the eval head), w, h in field units (headmeta.py:117-134; csrc/src/cif_hr.cpp:124-150
     reads components 1..5).  Per planted object of category f, every cell within ~2.5 cells of its centre votes for
@@ -273,8 +273,18 @@ def make_det_fields(n_categories=80, h=41, w=41, n_objects=6, seed=0, n_distract
         f = int(rng.random() * F) % F
         x, y = rng.random() * (w - 1), rng.random() * (h - 1)
         plant(f, x, y, 1.0 + 3.0 * rng.random(), 1.0 + 3.0 * rng.random(), 0.22 + 0.3 * rng.random(), radius2=2.5)
+    # pairs of large same-category boxes 1.5 cells apart: far enough to escape each other's occupancy mark, close
+    # enough for IoU ~ 0.6 -- work for the NMS of decoder/cifdet.py:55-64 (drawn after everything above, so the
+    # fields of n_overlapping == 0 are unchanged)
+    for _ in range(n_overlapping):
+        f = int(rng.random() * F) % F
+        bw, bh = 8.0 + 2.0 * rng.random(), 8.0 + 2.0 * rng.random()
+        x = 2.0 + rng.random() * (w - 6.0)
+        y = 2.0 + rng.random() * (h - 5.0)
+        plant(f, x, y, bw, bh, 0.9)
+        plant(f, x + 1.5, y + 0.5, bw * 1.03, bh * 0.97, 0.75, radius2=2.5)
     # a few cells with a negative width / height (never contribute to the hi-res map, still become seeds)
-    for _ in range(3):
+    for _ in range(3 if n_overlapping == 0 else 0):
         f = int(rng.random() * F) % F
         i, j = int(rng.random() * w) % w, int(rng.random() * h) % h
         field[f, 1, j, i] = 0.6 + 0.2 * rng.random()

@@ -68,7 +68,7 @@ def test_cifdet_statics_like_reference():
 def test_cifdet_gpu_nms_equals_torchvision(by_category):
     """decoder/cifdet.py:55-64 on the GPU == torchvision on the host, on the same raw detections"""
     torchvision = pytest.importorskip('torchvision')
-    fields = [synth.make_det_fields(6, 31, 31, n, 400 + n, n_distractors=8)['field'] for n in (12, 60)]
+    fields = [synth.make_det_fields(6, 31, 31, n, 400 + n, n_distractors=8, n_overlapping=5)['field'] for n in (12, 60)]
     d = decoder.CifDet()
     dev = torch.from_numpy(np.stack(fields)).cuda()
     raw = d.decode_batch(dev, 16)

@@ -232,3 +232,50 @@ def test_raw_uint8_images_equal_normalised_float_images():
         assert torch.equal(af, au) and torch.equal(idf, idu)
     with pytest.raises(RuntimeError):
         net.forward_uint8(raw[:, :10].cuda())
+
+
+@pytest.mark.parametrize('up', [2, 3])
+def test_upsampled_heads_pixelshuffle_in_the_epilogue(up):
+    """upsample_stride > 1 heads (heads.py:307-343).  The heads GEMM writes PixelShuffle(up) +
+    crop + the CompositeField4 eval ops straight from its epilogue; checked against plain torch ops (conv as a matmul
+    on the same bf16-rounded operands, torch.nn.PixelShuffle, the reference's crop, sigmoid / index add / softplus)."""
+    rng = np.random.default_rng(up)
+    c_in, h, w, B = 136, 9, 13, 3
+    heads_spec = ((5, 1, 1, 1), (4, 1, 2, 2))         # a CIF-like and a CAF-like head
+    heads = []
+    for nf, nconf, nvec, nsc in heads_spec:
+        ncomp = 1 + nconf + 2 * nvec + nsc
+        heads.append({'w': (rng.standard_normal((nf * ncomp * up * up, c_in)) / np.sqrt(c_in)).astype(np.float32),
+                      'b': (rng.standard_normal(nf * ncomp * up * up) * 0.3).astype(np.float32),
+                      'n_fields': nf, 'n_comp': ncomp, 'upsample': up,
+                      'ops': network.head_ops(nconf, nvec, nsc, (True,) * nvec), 'stride': 16 // up})
+    plan = {'kind': 'heads_only', 'c_in': c_in, 'heads': heads}
+    net = network.CompiledNet(plan, h, w, B)
+    feat = rng.standard_normal((B, h, w, c_in)).astype(np.float32)
+    got = [t.clone().cpu() for t in net.forward_features(feat)]
+
+    def bf16(a):
+        return torch.from_numpy(a).to(torch.bfloat16).to(torch.float64)
+    x = bf16(feat).permute(0, 3, 1, 2)                                   # [B, C, h, w]
+    low, high = (up - 1) // 2, int(np.ceil((up - 1) / 2.0))
+    for hd, g in zip(heads, got):
+        y = torch.einsum('bchw,nc->bnhw', x, bf16(hd['w'])) + torch.from_numpy(hd['b']).double().view(1, -1, 1, 1)
+        y = torch.nn.PixelShuffle(up)(y)
+        y = y[:, :, low:y.shape[2] - high, low:y.shape[3] - high]
+        H2, W2 = y.shape[2], y.shape[3]
+        assert (H2, W2) == (h * up - low - high, w * up - low - high)
+        y = y.reshape(B, hd['n_fields'], hd['n_comp'], H2, W2).clone()
+        xs = torch.arange(W2, dtype=torch.float64).view(1, 1, 1, W2)
+        ys = torch.arange(H2, dtype=torch.float64).view(1, 1, H2, 1)
+        for c, op in enumerate(hd['ops']):
+            if op == network.OP_SIGMOID:
+                y[:, :, c] = torch.sigmoid(y[:, :, c])
+            elif op == network.OP_ADD_X:
+                y[:, :, c] += xs
+            elif op == network.OP_ADD_Y:
+                y[:, :, c] += ys
+            elif op == network.OP_SOFTPLUS:
+                y[:, :, c] = torch.nn.functional.softplus(y[:, :, c])
+        assert tuple(g.shape) == tuple(y.shape)
+        assert float((g.double() - y).abs().max()) < 2e-4
+    net.close()
