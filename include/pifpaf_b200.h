@@ -211,6 +211,27 @@ int pifpaf_cifdet_call(pifpaf_cifdet_t* det, const float* field, int32_t stride,
 
 
 /* ------------------------------------------------------------------------ */
+/* Image preprocessing on the GPU.  Replaces, on the inference path of the reference's Predictor
+ * (predictor.py:85-102), transforms.RescaleAbsolute(fast=True) -> PIL.Image.resize(BILINEAR)
+ * (transforms/scale.py:154-176,56-59) and the image part of transforms.CenterPad / CenterPadTight
+ * (transforms/pad.py:15-110).  Raw uint8 HWC images, resized bit-identically to Pillow's ImagingResample
+ * (horizontal pass into an 8-bit intermediate, then vertical; 22-bit fixed-point coefficients) straight into a
+ * window of a padded canvas [H][W][3] that pifpaf_net_forward_u8 consumes.
+ *   xbounds [dst_w][2] / xkk [dst_w][xksize], ybounds [dst_h][2] / ykk [dst_h][yksize]: device int32 tables of
+ *   Pillow's precompute_coeffs + normalize_coeffs_8bpc (built by the host mirror, openpifpaf_b200/preprocess.py);
+ *   a direction whose size does not change needs none.  tmp: device scratch of src_h * dst_w * 3 bytes.
+ *   dst points at the window's first pixel inside the canvas, dst_pitch_bytes = canvas row pitch. */
+int pifpaf_image_resize_bilinear_u8(const uint8_t* src_dev, int32_t src_h, int32_t src_w,
+                                    uint8_t* dst_dev, int64_t dst_pitch_bytes, int32_t dst_h, int32_t dst_w,
+                                    const int32_t* xbounds_dev, const int32_t* xkk_dev, int32_t xksize,
+                                    const int32_t* ybounds_dev, const int32_t* ykk_dev, int32_t yksize,
+                                    uint8_t* tmp_dev, void* stream);
+/* constant RGB fill of a canvas of n_pixels pixels: the pad colour (CenterPad draws a random grey per image,
+ * transforms/pad.py:52-54; CenterPadTight uses (124, 116, 104), transforms/pad.py:100-101) */
+int pifpaf_image_fill_rgb(uint8_t* dst_dev, int64_t n_pixels, int32_t r, int32_t g, int32_t b, void* stream);
+
+
+/* ------------------------------------------------------------------------ */
 /* Network forward: backbone + CompositeField4 heads (network/nets.py:35-48,
  * network/basenetworks.py:186-355, network/heads.py:272-378), as a list of fused
  * ops over NHWC bf16 activation tensors.  The host mirror of the reference

@@ -70,6 +70,9 @@ SYMBOLS = {
     'pifpaf_cifdet_decode_device': (ctypes.c_int, [VP, VP, c_i32, c_i32, c_i32, c_i32, P(CifDetParams), VP]),
     'pifpaf_cifdet_fetch': (ctypes.c_int, [VP, VP, VP, c_i32, VP]),
     'pifpaf_cifdet_call': (ctypes.c_int, [VP, VP, c_i32, c_i32, c_i32, P(CifDetParams), VP, c_i32, P(c_i32)]),
+    'pifpaf_image_resize_bilinear_u8': (ctypes.c_int, [VP, c_i32, c_i32, VP, c_i64, c_i32, c_i32, VP, VP, c_i32,
+                                                        VP, VP, c_i32, VP, VP]),
+    'pifpaf_image_fill_rgb': (ctypes.c_int, [VP, c_i64, c_i32, c_i32, c_i32, VP]),
     'pifpaf_net_create': (ctypes.c_int, [P(VP), c_i32, c_i32]),
     'pifpaf_net_destroy': (None, [VP]),
     'pifpaf_net_tensor': (ctypes.c_int, [VP, c_i32, c_i32, c_i32, P(c_i32)]),

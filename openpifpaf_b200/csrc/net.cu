@@ -20,7 +20,9 @@
 #include <cuda_bf16.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -120,6 +122,15 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t* v) {
                  :
                  : "memory");
 }
+
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream is still draining; everything up to pdl_wait() (barrier init, TMEM
+// allocation, descriptor prefetch, staging of constant weights / biases) overlaps the predecessor's tail.
+// pdl_wait() returns once the predecessor has completed and its writes are visible -- it must precede every access
+// to activations (reads AND writes: the predecessor may still be reading what this kernel overwrites).  Both are
+// no-ops in a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ------------------------------------------------------------------ descriptors
 constexpr int BM = 128;          // UMMA M (cta_group::1): TMEM lane == tile row
@@ -412,6 +423,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // (after the TMEM allocation: a dependent CTA that becomes co-resident must not take the columns first)
+    pdl_launch_dependents();
+    pdl_wait();
 
     // tile schedule: streaming mode walks (m_blk, n_blk) tiles round-robin over the CTAs; weights-resident mode
     // pins one n block per CTA (gridDim.x is a multiple of n_blocks) and walks M tiles only
@@ -742,7 +756,25 @@ __device__ __forceinline__ void dw_advance(DwPos& p, const DwPos& d, int B, int 
     p.c += d.c + carry;
 }
 
-template <int S, int TH, int TW, int BW, int NSTAGE>
+// channel-block-FASTEST item order (CBF): item = (image, tile row, tile column, channel block) with the channel block
+// as the fastest digit, so the 128-byte channel blocks of one pixel (352 / 704-byte pixels: most blocks straddle a
+// 64-byte DRAM atom) and the halos of neighbouring tiles are fetched by CTAs running at the same time and meet in L2.
+__device__ __forceinline__ DwPos dw_decompose_cf(int w, int cblks, int tiles_y, int tiles_x) {
+    DwPos p;
+    p.c = w % cblks; int r = w / cblks;
+    p.x = r % tiles_x; r /= tiles_x;
+    p.y = r % tiles_y; p.b = r / tiles_y;
+    return p;
+}
+
+__device__ __forceinline__ void dw_advance_cf(DwPos& p, const DwPos& d, int cblks, int tiles_y, int tiles_x) {
+    p.c += d.c; int carry = p.c >= cblks; p.c -= carry ? cblks : 0;
+    p.x += d.x + carry; carry = p.x >= tiles_x; p.x -= carry ? tiles_x : 0;
+    p.y += d.y + carry; carry = p.y >= tiles_y; p.y -= carry ? tiles_y : 0;
+    p.b += d.b + carry;
+}
+
+template <int S, int TH, int TW, int BW, int NSTAGE, bool CBF = false>
 __global__ void __launch_bounds__(DwTile<S, TH, TW, BW, NSTAGE>::THREADS, 2)
 k_dwconv5_tma(const __grid_constant__ CUtensorMap tmap_in, DwArgs a) {
     using T = DwTile<S, TH, TW, BW, NSTAGE>;
@@ -758,6 +790,18 @@ k_dwconv5_tma(const __grid_constant__ CUtensorMap tmap_in, DwArgs a) {
     const int per_c = a.B * tiles_y * tiles_x;
     const int total = per_c * cblks;
     const int C = a.C8 * 8;
+    // CBF: the channel block changes with (almost) every item, so the weights [25][C] + bias [C] are staged in
+    // shared memory once per CTA and re-read from there (26 LDS.64 per item)
+    const float* s_w = reinterpret_cast<const float*>(dsm + (size_t)NSTAGE * T::BYTES);
+    if (CBF) {
+        float* sw = reinterpret_cast<float*>(dsm + (size_t)NSTAGE * T::BYTES);
+        for (int i = tid; i < 25 * C; i += T::THREADS) sw[i] = a.weight[i];
+        for (int i = tid; i < C; i += T::THREADS) sw[25 * C + i] = a.bias[i];
+    }
+    auto decompose = [&](int w) { return CBF ? dw_decompose_cf(w, cblks, tiles_y, tiles_x) : dw_decompose(w, per_c, tiles_y, tiles_x); };
+    auto advance = [&](DwPos& p, const DwPos& d) {
+        if (CBF) dw_advance_cf(p, d, cblks, tiles_y, tiles_x); else dw_advance(p, d, a.B, tiles_y, tiles_x);
+    };
 
     auto issue = [&](const DwPos& p, int buf) {
         mbar_expect_tx(&full[buf], (uint32_t)T::BYTES);
@@ -765,6 +809,8 @@ k_dwconv5_tma(const __grid_constant__ CUtensorMap tmap_in, DwArgs a) {
                     p.y * TH * S - a.pad, p.b);
     };
 
+    pdl_launch_dependents();
+    pdl_wait();
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < NSTAGE; s++) { mbar_init(&full[s], 1); done[s] = 0; }
@@ -773,15 +819,15 @@ k_dwconv5_tma(const __grid_constant__ CUtensorMap tmap_in, DwArgs a) {
 #pragma unroll
         for (int s = 0; s < NSTAGE; s++) {
             const int w0 = blockIdx.x + s * gridDim.x;
-            if (w0 < total) issue(dw_decompose(w0, per_c, tiles_y, tiles_x), s);
+            if (w0 < total) issue(decompose(w0), s);
         }
     }
     __syncthreads();
 
     const int by = warp / (TW / BW), bx = warp % (TW / BW);     // 4 x BW output block of this warp inside the tile
-    const DwPos step = dw_decompose(gridDim.x, per_c, tiles_y, tiles_x);
-    const DwPos step_ring = dw_decompose(NSTAGE * gridDim.x, per_c, tiles_y, tiles_x);
-    DwPos pos = dw_decompose(blockIdx.x, per_c, tiles_y, tiles_x);
+    const DwPos step = decompose(gridDim.x);
+    const DwPos step_ring = decompose(NSTAGE * gridDim.x);
+    DwPos pos = decompose(blockIdx.x);
     const size_t out_row = (size_t)a.Wout * a.ld_out;           // elements per output image row
     int buf = 0; uint32_t phase = 0;
     int w_cblk = -1;
@@ -794,11 +840,14 @@ k_dwconv5_tma(const __grid_constant__ CUtensorMap tmap_in, DwArgs a) {
             const bool cok = c0 < C;
 #pragma unroll
             for (int tp = 0; tp < 25; tp++) {
-                const float2 wv = cok ? __ldg(reinterpret_cast<const float2*>(a.weight + (size_t)tp * C + c0))
-                                      : make_float2(0.f, 0.f);
+                const float2 wv = !cok ? make_float2(0.f, 0.f)
+                                  : CBF ? *reinterpret_cast<const float2*>(s_w + (size_t)tp * C + c0)
+                                        : __ldg(reinterpret_cast<const float2*>(a.weight + (size_t)tp * C + c0));
                 wgt[tp][0] = wv.x; wgt[tp][1] = wv.y;
             }
-            const float2 bv = cok ? __ldg(reinterpret_cast<const float2*>(a.bias + c0)) : make_float2(0.f, 0.f);
+            const float2 bv = !cok ? make_float2(0.f, 0.f)
+                              : CBF ? *reinterpret_cast<const float2*>(s_w + 25 * (size_t)C + c0)
+                                    : __ldg(reinterpret_cast<const float2*>(a.bias + c0));
             bias0 = bv.x; bias1 = bv.y;
         }
         const int oy0 = pos.y * TH + by * 4, ox0 = pos.x * TW + bx * BW;
@@ -875,12 +924,12 @@ k_dwconv5_tma(const __grid_constant__ CUtensorMap tmap_in, DwArgs a) {
                 done[buf] = 0;
                 if (w + NSTAGE * (int)gridDim.x < total) {
                     DwPos pn = pos;
-                    dw_advance(pn, step_ring, a.B, tiles_y, tiles_x);
+                    advance(pn, step_ring);
                     issue(pn, buf);
                 }
             }
         }
-        dw_advance(pos, step, a.B, tiles_y, tiles_x);
+        advance(pos, step);
         if (++buf == NSTAGE) { buf = 0; phase ^= 1; }
     }
 }
@@ -1016,6 +1065,9 @@ k_dw_gemm(const __grid_constant__ CUtensorMap tmap_win, const __grid_constant__ 
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // (after the TMEM allocation: a dependent CTA that becomes co-resident must not take the columns first)
+    pdl_launch_dependents();
+    pdl_wait();
     const int per_img = g.tiles_x * g.tiles_y;
     const int nkb = g.num_k_blocks;
 
@@ -1239,6 +1291,8 @@ __global__ void __launch_bounds__(256) k_input_conv(InConvArgs a) {
 #pragma unroll
             for (int c = 0; c < 3; c++) s_lut[c * 256 + i] = __fdiv_rn(__fsub_rn(x, a.mean[c]), a.stdev[c]);
         }
+    pdl_launch_dependents();
+    pdl_wait();
     __syncthreads();
     const long long total = (long long)a.B * a.Hout * a.Wout;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -1424,6 +1478,18 @@ int make_tmap_dw(CUtensorMap* map, const void* base, uint64_t c, uint64_t w, uin
     return PIFPAF_OK;
 }
 
+// launch with (or without) the programmatic-stream-serialization attribute
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 struct Tensor { int h, w, c; __nv_bfloat16* data; };
 
 enum OpKind { OP_INPUT_CONV, OP_GEMM, OP_DW, OP_FUSED };
@@ -1465,6 +1531,8 @@ struct pifpaf_net {
     size_t head_elems[4] = {0, 0, 0, 0};
     bool setup_synced = false;           // build-time memsets / uploads (legacy stream) ordered before the first forward
     int sm_limit = 0;                    // > 0: persistent grids use at most this many SMs
+    bool pdl = true;                     // programmatic dependent launch between the ops of a forward (PIFPAF_PDL=0: off)
+    bool dw_cbf = false;                 // stride-2 depthwise: channel-block-fastest item order (PIFPAF_DW_CBF=1; measured neutral)
     int head_fields[4] = {0, 0, 0, 0}, head_comp[4] = {0, 0, 0, 0}, head_h = 0, head_w = 0;
     int in_h = 0, in_w = 0;
 };
@@ -1626,11 +1694,15 @@ int pifpaf_net_create(pifpaf_net_t** out, int32_t device, int32_t max_batch) {
     }
     pifpaf_net* net = new pifpaf_net();
     net->device = device; net->max_batch = max_batch; net->n_sm = prop.multiProcessorCount;
+    if (const char* e = std::getenv("PIFPAF_DW_CBF")) net->dw_cbf = std::atoi(e) != 0;
+    if (const char* e = std::getenv("PIFPAF_PDL")) net->pdl = std::atoi(e) != 0;
     PIFPAF_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     PIFPAF_CUDA_TRY(cudaFuncSetAttribute(k_dwconv5_tma<1, DW1_TH, DW1_TW, 4, 3>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, DwS1::SMEM));
     PIFPAF_CUDA_TRY(cudaFuncSetAttribute(k_dwconv5_tma<2, DW2_TH, DW2_TW, 4, 2>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, DwS2::SMEM));
+    PIFPAF_CUDA_TRY(cudaFuncSetAttribute(k_dwconv5_tma<2, DW2_TH, DW2_TW, 4, 2, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     PIFPAF_CUDA_TRY(cudaFuncSetAttribute(k_dw_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     *out = net;
     return PIFPAF_OK;
@@ -2090,8 +2162,12 @@ static int net_forward_impl(pifpaf_net_t* net, const float* images_dev, int32_t 
     if (net->head_buffers == 2) net->head_cur ^= 1;
     const int n_sm = net->sm_limit > 0 ? std::min(net->sm_limit, net->n_sm) : net->n_sm;
     int op_index = 0;
+    // PDL between consecutive ops (not in the per-op timing pass: the events would sit between the launches; not for
+    // the first op: its predecessor in the stream is a copy or another forward's decode, not one of these kernels)
+    const bool pdl_on = net->pdl && events == nullptr && gemm_impl == 0;
     for (Op& op : net->ops) {
         if (events) PIFPAF_CUDA_TRY(cudaEventRecord(events[op_index], st));
+        const bool pdl = pdl_on && op_index > 0;
         op_index++;
         if (op.kind == OP_INPUT_CONV) {
             InConvArgs a = op.ic;
@@ -2117,7 +2193,7 @@ static int net_forward_impl(pifpaf_net_t* net, const float* images_dev, int32_t 
             g.M = batch * op.rows_per_image;
             g.m_blocks = batch * op.tiles_per_image;
             const int grid = std::min(g.m_blocks, n_sm);
-            k_dw_gemm<1><<<grid, FD_THREADS, op.smem, st>>>(op.tmap_dw, op.tmap_b, g, op.fu);
+            PIFPAF_CUDA_TRY(launch_k(pdl, k_dw_gemm<1>, dim3(grid), dim3(FD_THREADS), op.smem, st, op.tmap_dw, op.tmap_b, g, op.fu));
             PIFPAF_LAUNCH_CHECK();
         } else if (op.kind == OP_DW) {
             DwArgs a = op.dw;
@@ -2129,12 +2205,20 @@ static int net_forward_impl(pifpaf_net_t* net, const float* images_dev, int32_t 
                     const long long total = (long long)batch * ((a.Hout + DW1_TH - 1) / DW1_TH) *
                                             ((a.Wout + DW1_TW - 1) / DW1_TW) * cblks;
                     const int grid = (int)std::min<long long>(total, (long long)n_sm * 2);
-                    k_dwconv5_tma<1, DW1_TH, DW1_TW, 4, 3><<<grid, DwS1::THREADS, DwS1::SMEM, st>>>(op.tmap_dw, a);
+                    PIFPAF_CUDA_TRY(launch_k(pdl, k_dwconv5_tma<1, DW1_TH, DW1_TW, 4, 3, false>, dim3(grid), dim3(DwS1::THREADS),
+                                             (size_t)DwS1::SMEM, st, op.tmap_dw, a));
                 } else {
                     const long long total = (long long)batch * ((a.Hout + DW2_TH - 1) / DW2_TH) *
                                             ((a.Wout + DW2_TW - 1) / DW2_TW) * cblks;
                     const int grid = (int)std::min<long long>(total, (long long)n_sm);
-                    k_dwconv5_tma<2, DW2_TH, DW2_TW, 4, 2><<<grid, DwS2::THREADS, DwS2::SMEM, st>>>(op.tmap_dw, a);
+                    // channel-block-fastest order with the weights staged in shared memory while they fit
+                    const size_t smem_cf = (size_t)DwS2::SMEM + (size_t)26 * a.C8 * 8 * sizeof(float);
+                    if (net->dw_cbf && cblks > 1 && smem_cf <= 226 * 1024)
+                        PIFPAF_CUDA_TRY(launch_k(pdl, k_dwconv5_tma<2, DW2_TH, DW2_TW, 4, 2, true>, dim3(grid), dim3(DwS2::THREADS),
+                                                 smem_cf, st, op.tmap_dw, a));
+                    else
+                        PIFPAF_CUDA_TRY(launch_k(pdl, k_dwconv5_tma<2, DW2_TH, DW2_TW, 4, 2, false>, dim3(grid), dim3(DwS2::THREADS),
+                                                 (size_t)DwS2::SMEM, st, op.tmap_dw, a));
                 }
             } else if (a.kernel == 5 && (a.stride == 1 || a.stride == 2)) {
                 const long long total = (long long)batch * ((a.Hout + DW_OY - 1) / DW_OY) * DW_OY *
@@ -2162,8 +2246,8 @@ static int net_forward_impl(pifpaf_net_t* net, const float* images_dev, int32_t 
                 const int tiles = g.m_blocks * g.n_blocks;
                 int grid = std::min(tiles, n_sm);
                 if (g.b_resident) grid = std::max(1, std::min(n_sm / g.n_blocks, g.m_blocks)) * g.n_blocks;
-                k_gemm_tc<<<grid, GEMM_THREADS, op.smem, st>>>(op.tmap_a, op.tmap_b,
-                                                                g.src_tma ? op.tmap_src : op.tmap_a, g);
+                PIFPAF_CUDA_TRY(launch_k(pdl, k_gemm_tc, dim3(grid), dim3(GEMM_THREADS), op.smem, st, op.tmap_a, op.tmap_b,
+                                         g.src_tma ? op.tmap_src : op.tmap_a, g));
             }
             PIFPAF_LAUNCH_CHECK();
         }

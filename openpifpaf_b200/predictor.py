@@ -17,6 +17,7 @@ import torch
 
 from . import decoder as _decoder
 from . import network as _network
+from . import preprocess as _preprocess
 
 
 class Predictor:
@@ -134,6 +135,33 @@ class Predictor:
             self.join()
         self.last_nn_time = self.last_decoder_time = time.perf_counter() - t0
         return result
+
+    def raw_images(self, images, *, json_data=False, fill=None, score_weights=None):
+        """The reference's Predictor.numpy_images / images (predictor.py:155-196) for a list of RAW uint8 [h, w, 3]
+        images with everything after the JPEG decode on the GPU: RescaleAbsolute(long edge = the compiled input size)
+        + CenterPad (`preprocess.GpuPreprocess`, bit-identical to the reference's Pillow path), ToTensor + Normalize in
+        the stem, forward, decode; then `Annotation.inverse_transform` (and `json_data`) for all annotations of an
+        image at once.  Returns per image (data [N, K, 3] (x, y, v) in original-image pixels, joint_scales [N, K], meta)
+        or, with json_data, (list of dicts, meta)."""
+        if self.net.in_h != self.net.in_w:
+            raise RuntimeError('raw_images needs a net compiled for a square input (CenterPad(long_edge))')
+        if getattr(self, '_gpu_preprocess', None) is None:
+            self._gpu_preprocess = _preprocess.GpuPreprocess(self.net.in_w, batched=True, device=self.device.index)
+        out = []
+        for i in range(0, len(images), self.net.max_batch):
+            chunk = images[i:i + self.net.max_batch]
+            with torch.cuda.stream(self.stream):
+                canvas, metas = self._gpu_preprocess(chunk, fill=fill, stream=self.stream)
+                self.batch_device(canvas)
+                result = self.decoder.fetch(stream=self.result_stream())
+                self.join()
+            for (ann, _), meta in zip(result, metas):
+                data, scales = _preprocess.inverse_transform_batch(ann.numpy(), meta)
+                if json_data:
+                    out.append((_preprocess.json_data_batch(data, scales, score_weights=score_weights), meta))
+                else:
+                    out.append((data, scales, meta))
+        return out
 
     def batches(self, host_batches):
         """Pipelined variant of `batch` over an iterable of host image batches (what Predictor.dataloader /

@@ -99,6 +99,7 @@ def _match(a, b):
 @pytest.mark.parametrize('base,workload,size,batch,n_people', [
     ('shufflenetv2k16', 'cocokp', 641, 4, None),          # BASELINE C0/C2 network at size, Poisson(4)+1 people
     ('resnet50', 'cocokp', 321, 2, 3),                    # C4 family
+    ('resnet50', 'cocokp', 801, 2, 4),                    # BASELINE C4 at size (801 px, 51 x 51 cells)
     ('shufflenetv2k30', 'wholebody', 641, 2, 2),          # C3 at size: 133 keypoints / 160 connections
 ])
 def test_bf16_network_decodes_like_fp32(base, workload, size, batch, n_people):

@@ -58,6 +58,7 @@ SCRIPT = textwrap.dedent('''
                 up2 = head.upsample_stride ** 2
                 conv.bias.view(head.meta.n_fields, head.n_components, up2)[:, 1] += -1.0
     calibrate(predictor.model, predictor.device)
+    ref_cpu = openpifpaf.decoder.CifCaf([cif_meta], [caf_meta])      # the reference's CPU decoder: the checker
 
     def compare(got, want, what):
         assert len(got) == len(want), (what, len(got), len(want))
