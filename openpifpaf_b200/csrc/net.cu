@@ -994,24 +994,16 @@ __global__ void __launch_bounds__(256) k_dwconv(DwArgs a) {
 // InvertedResidualK branch2 tail (basenetworks.py:219-226: dw5x5, BN, 1x1, BN, ReLU) as ONE kernel: the depthwise
 // output never visits HBM.  Per CTA (persistent over 8 x 16 output-pixel patches == 128-row M tiles), per 64-channel
 // K block:
-//   warp 0      TMA producer: the patch's input window (12 x 20 pixels x 64 channels, zero fill == conv padding) into
-//               a window ring, and the K block of the 1x1 weights [n_pad x 64] into a B ring
-//   warps 8-23  depthwise, two groups of 8 warps that take alternate K blocks (group = running K-block index & 1):
-//               inside a group one warp = a 4 x 4 block of output pixels, one lane = a channel pair (the
-//               register-blocked FMA loop of k_dwconv5_tma); results go as bf16 straight into a 128B-swizzled K-major
-//               A stage (row = pixel of the patch, the layout TMA would have produced), fence.proxy.async + mbarrier
-//   warp 1      tcgen05.mma issuer: D[128 x n_pad] += A-stage x B-stage^T in TMEM; tcgen05.commit frees the stages
-//   warps 4-7   epilogue: TMEM -> registers -> bias + ReLU -> bf16 -> scatter stores
-// The kernel is bound by the FMA issue rate of the depthwise warps (the tensor pipe idles most of the time), so it
-// runs as many of them as the stand-alone depthwise kernel has per SM (16) -- the first version had 8 and lost to
-// the two-kernel schedule.  768 threads leave 80 registers per thread at launch; setmaxnreg hands the registers
-// of the control and epilogue warpgroups to the four depthwise warpgroups (24 / 72 / 104 per thread).
+//   warp 0     TMA producer: the patch's input window (12 x 20 pixels x 64 channels, zero fill == conv padding) into
+//              a window ring, and the K block of the 1x1 weights [n_pad x 64] into a B ring
+//   warps 2-9  depthwise: one warp = a 4 x 4 block of output pixels, one lane = a channel pair (the register-blocked
+//              FMA loop of k_dwconv5_tma); results go as bf16 straight into a 128B-swizzled K-major A stage
+//              (row = pixel of the patch, the layout TMA would have produced), fence.proxy.async + mbarrier arrive
+//   warp 1     tcgen05.mma issuer: D[128 x n_pad] += A-stage x B-stage^T in TMEM; tcgen05.commit frees the stages
+//   warps 10-13 epilogue: TMEM -> registers -> bias + ReLU -> bf16 -> scatter / plain stores (epilogue_chunk)
 // n_pad <= 512 TMEM columns; n_pad > 256 runs as two UMMA halves; two accumulator stages when 2 * n_pad <= 512.
-constexpr int FD_DW_WARPS = 16, FD_DW_GROUP = 8, FD_EPI_WARPS = 4;
-constexpr int FD_DW_WARP0 = 8, FD_EPI_WARP0 = 4;
-constexpr int FD_THREADS = 32 * (FD_DW_WARP0 + FD_DW_WARPS);           // 768
-constexpr int FD_REGS_CTRL = 24, FD_REGS_EPI = 72, FD_REGS_DW = 96;
-static_assert(128 * FD_REGS_CTRL + 128 * FD_REGS_EPI + 512 * FD_REGS_DW <= FD_THREADS * 80, "setmaxnreg can only redistribute what the CTA got at launch (80 registers per thread)");
+constexpr int FD_DW_WARPS = 8, FD_EPI_WARPS = 4;
+constexpr int FD_THREADS = 32 * (2 + FD_DW_WARPS + FD_EPI_WARPS);     // 448
 
 struct FusedArgs {
     const float* dw_weight;      // [25][C] f32, tap-major
@@ -1021,21 +1013,16 @@ struct FusedArgs {
     int ws, as, bs;              // ring depths: windows, A stages, B stages
     int n_pad, n_halves, half_n; // n_pad = n_halves * half_n, half_n <= 256, multiple of 16
     int acc_stages;
-    int w_smem;                  // depthwise weights staged in shared memory (else read through L1/L2 per K block)
 };
 
 __device__ __forceinline__ void fence_proxy_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-template <int R> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
-template <int R> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 
 template <int S>
 __global__ void __launch_bounds__(FD_THREADS, 1)
 k_dw_gemm(const __grid_constant__ CUtensorMap tmap_win, const __grid_constant__ CUtensorMap tmap_b, GemmArgs g, FusedArgs f) {
     using T = DwTile<S, PH, PW, 4, 1>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // align with pointer arithmetic on the array itself: the compiler keeps the shared address space (LDS / STS for
-    // the window reads and A-stage writes of the depthwise warps instead of generic loads)
-    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int a_bytes = BM * BK * 2;                     // 16 KB
     const int b_bytes = f.n_pad * BK * 2;                // multiple of 1024 (n_pad % 16 == 0)
     unsigned char* a_st = smem;
@@ -1043,9 +1030,10 @@ k_dw_gemm(const __grid_constant__ CUtensorMap tmap_win, const __grid_constant__ 
     unsigned char* win = b_st + (size_t)f.bs * b_bytes;
     float* bias_s = reinterpret_cast<float*>(win + (size_t)f.ws * T::BYTES);
     DestGroup* dest_s = reinterpret_cast<DestGroup*>(bias_s + f.n_pad);
-    // depthwise weights [25][C] + bias [C], staged once per CTA (every K block of every tile re-reads them)
+    // depthwise weights [25][C] + bias [C], staged once per CTA: a per-K-block reload from global memory put the
+    // depthwise warps on the long scoreboard (ncu round 2: 1.4 - 2.8 warps per issue, the L1 is carved down to a few KB)
     float* dww_s = reinterpret_cast<float*>(dest_s + f.n_pad / CHUNK);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(dww_s + (f.w_smem ? 26 * (size_t)f.C : 0));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(dww_s + 26 * (size_t)f.C);
     uint64_t* win_full = bars;                 uint64_t* win_empty = win_full + f.ws;
     uint64_t* a_full = win_empty + f.ws;       uint64_t* a_empty = a_full + f.as;
     uint64_t* b_full = a_empty + f.as;         uint64_t* b_empty = b_full + f.bs;
@@ -1058,15 +1046,14 @@ k_dw_gemm(const __grid_constant__ CUtensorMap tmap_win, const __grid_constant__ 
 
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_win); tma_prefetch_desc(&tmap_b); }
     for (int i = threadIdx.x; i < f.n_pad; i += FD_THREADS) bias_s[i] = g.bias[i];
-    for (int i = threadIdx.x; i < f.n_pad / CHUNK; i += FD_THREADS) dest_s[i] = g.dest[i];
-    if (f.w_smem) {
-        for (int i = threadIdx.x; i < 25 * f.C; i += FD_THREADS) dww_s[i] = f.dw_weight[i];
-        for (int i = threadIdx.x; i < f.C; i += FD_THREADS) dww_s[25 * f.C + i] = f.dw_bias[i];
-    }
+    if (g.mode == MODE_SCATTER)
+        for (int i = threadIdx.x; i < f.n_pad / CHUNK; i += FD_THREADS) dest_s[i] = g.dest[i];
+    for (int i = threadIdx.x; i < 25 * f.C; i += FD_THREADS) dww_s[i] = f.dw_weight[i];
+    for (int i = threadIdx.x; i < f.C; i += FD_THREADS) dww_s[25 * f.C + i] = f.dw_bias[i];
     if (warp == 1) {
         if (lane == 0) {
-            for (int i = 0; i < f.ws; i++) { mbar_init(&win_full[i], 1); mbar_init(&win_empty[i], FD_DW_GROUP); }
-            for (int i = 0; i < f.as; i++) { mbar_init(&a_full[i], FD_DW_GROUP); mbar_init(&a_empty[i], 1); }
+            for (int i = 0; i < f.ws; i++) { mbar_init(&win_full[i], 1); mbar_init(&win_empty[i], FD_DW_WARPS); }
+            for (int i = 0; i < f.as; i++) { mbar_init(&a_full[i], FD_DW_WARPS); mbar_init(&a_empty[i], 1); }
             for (int i = 0; i < f.bs; i++) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
             for (int i = 0; i < 2; i++) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], FD_EPI_WARPS); }
             fence_barrier_init();
@@ -1084,10 +1071,9 @@ k_dw_gemm(const __grid_constant__ CUtensorMap tmap_win, const __grid_constant__ 
     const int per_img = g.tiles_x * g.tiles_y;
     const int nkb = g.num_k_blocks;
 
-    if (warp < FD_EPI_WARP0) {
-        // ===== control warpgroup: warp 0 TMA producer, warp 1 MMA issuer, warps 2-3 idle =====
-        setmaxnreg_dec<FD_REGS_CTRL>();
-        if (warp == 0 && lane == 0) {
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
             int wi = 0; uint32_t wph = 0; int bi = 0; uint32_t bph = 0;
             for (int tile = blockIdx.x; tile < g.m_blocks; tile += gridDim.x) {
                 const int img = tile / per_img, t = tile - img * per_img;
@@ -1105,7 +1091,10 @@ k_dw_gemm(const __grid_constant__ CUtensorMap tmap_win, const __grid_constant__ 
                     if (++bi == f.bs) { bi = 0; bph ^= 1; }
                 }
             }
-        } else if (warp == 1 && lane == 0) {
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
             const uint32_t idesc = make_instr_desc(BM, f.half_n);
             int ai = 0; uint32_t aph = 0; int bi = 0; uint32_t bph = 0; int acc = 0; uint32_t acc_ph = 0;
             for (int tile = blockIdx.x; tile < g.m_blocks; tile += gridDim.x) {
@@ -1135,92 +1124,39 @@ k_dw_gemm(const __grid_constant__ CUtensorMap tmap_win, const __grid_constant__ 
                 if (++acc == f.acc_stages) { acc = 0; acc_ph ^= 1; }
             }
         }
-    } else if (warp < FD_DW_WARP0) {
-        // ===== epilogue warpgroup: TMEM lane quadrant = warp % 4 =====
-        setmaxnreg_dec<FD_REGS_EPI>();
-        const int q = warp & 3;
-        const int n_chunks = f.n_pad / CHUNK;
-        int acc = 0; uint32_t acc_ph = 0;
+    } else if (warp < 2 + FD_DW_WARPS) {
+        // ===== depthwise warps =====
+        const int dwi = warp - 2;
+        const int by = dwi / (PW / 4), bx = dwi % (PW / 4);        // 4 x 4 output block of this warp inside the patch
+        int wi = 0; uint32_t wph = 0; int ai = 0; uint32_t aph = 0;
         for (int tile = blockIdx.x; tile < g.m_blocks; tile += gridDim.x) {
-            mbar_wait(&tmem_full[acc], acc_ph);
-            tcgen05_fence_after();
-            const int m = tile_row_to_m(g, tile, q * 32 + lane);
-            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (uint32_t)(acc * f.n_pad);
-            uint32_t va[CHUNK], vb[CHUNK];
-            // scatter epilogue (the only mode of this kernel): bias + ReLU -> bf16 -> one 256-bit store per chunk
-            auto process = [&](int ci, const uint32_t* v) {
-                const int n0 = ci * CHUNK;
-                if (m < 0 || n0 >= g.N) return;
-                const float4* bp = reinterpret_cast<const float4*>(bias_s + n0);
-                uint32_t w[CHUNK / 2];
-#pragma unroll
-                for (int j4 = 0; j4 < CHUNK / 4; j4++) {
-                    const float4 b4 = bp[j4];
-                    float a0 = __uint_as_float(v[4 * j4]) + b4.x, a1 = __uint_as_float(v[4 * j4 + 1]) + b4.y;
-                    float a2 = __uint_as_float(v[4 * j4 + 2]) + b4.z, a3 = __uint_as_float(v[4 * j4 + 3]) + b4.w;
-                    if (g.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); a2 = fmaxf(a2, 0.f); a3 = fmaxf(a3, 0.f); }
-                    w[2 * j4] = pack_bf16(a0, a1); w[2 * j4 + 1] = pack_bf16(a2, a3);
-                }
-                const DestGroup d = dest_s[n0 >> 4];
-                st_global_256(d.base + (size_t)m * d.ld, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
-            };
-            tmem_ld16_async(t_row, va);
-            for (int ci = 0; ci < n_chunks; ci += 2) {
-                tmem_ld_wait(va);
-                if (ci + 1 < n_chunks) tmem_ld16_async(t_row + (uint32_t)((ci + 1) * CHUNK), vb);
-                process(ci, va);
-                if (ci + 1 < n_chunks) {
-                    tmem_ld_wait(vb);
-                    if (ci + 2 < n_chunks) tmem_ld16_async(t_row + (uint32_t)((ci + 2) * CHUNK), va);
-                    process(ci + 1, vb);
-                }
-            }
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-            if (++acc == f.acc_stages) { acc = 0; acc_ph ^= 1; }
-        }
-    } else {
-        // ===== depthwise warpgroups: two groups of 8 warps take alternate K blocks (running index gk over all tiles);
-        // inside a group warp = a 4 x 4 block of output pixels of the patch, lane = channel pair =====
-        setmaxnreg_inc<FD_REGS_DW>();
-        const int dwi = warp - FD_DW_WARP0;
-        const int group = dwi >> 3, wig = dwi & 7;
-        const int by = wig / (PW / 4), bx = wig % (PW / 4);
-        const float* wsrc = f.w_smem ? dww_s : f.dw_weight;
-        const float* bsrc = f.w_smem ? dww_s + 25 * (size_t)f.C : f.dw_bias;
-        int gk = 0;                                                  // K blocks seen so far (both groups count all)
-        // ring positions of this group's K blocks (gk = group, group + 2, ...): advance by two slots per block
-        int wi = group % f.ws, ai = group % f.as;
-        uint32_t wph = 0, aph = 0;
-        for (int tile = blockIdx.x; tile < g.m_blocks; tile += gridDim.x) {
-            const int t = tile % per_img;
+            const int img = tile / per_img, t = tile - img * per_img;
             const int oy0 = (t / g.tiles_x) * PH + by * 4, ox0 = (t % g.tiles_x) * PW + bx * 4;
             const bool inside = oy0 < g.Ho && ox0 < g.Wo;            // blocks past the image edge: rows nobody stores
-            for (int kb = 0; kb < nkb; kb++, gk++) {
-                if ((gk & 1) != group) continue;
+            (void)img;
+            for (int kb = 0; kb < nkb; kb++) {
                 const int c0 = kb * 64 + lane * 2;
                 const bool cok = c0 < f.C;
                 float wgt[25][2];
-                float acc[4][4][2];
+                float bias0 = 0.f, bias1 = 0.f;
                 if (inside) {
-                    float bias0 = 0.f, bias1 = 0.f;
 #pragma unroll
                     for (int tp = 0; tp < 25; tp++) {
-                        const float2 wv = cok ? *reinterpret_cast<const float2*>(wsrc + (size_t)tp * f.C + c0)
+                        const float2 wv = cok ? *reinterpret_cast<const float2*>(dww_s + (size_t)tp * f.C + c0)
                                               : make_float2(0.f, 0.f);
                         wgt[tp][0] = wv.x; wgt[tp][1] = wv.y;
                     }
-                    if (cok) { const float2 bv = *reinterpret_cast<const float2*>(bsrc + c0); bias0 = bv.x; bias1 = bv.y; }
-#pragma unroll
-                    for (int i = 0; i < 4; i++)
-#pragma unroll
-                        for (int j = 0; j < 4; j++) { acc[i][j][0] = bias0; acc[i][j][1] = bias1; }
+                    if (cok) { const float2 bv = *reinterpret_cast<const float2*>(dww_s + 25 * (size_t)f.C + c0); bias0 = bv.x; bias1 = bv.y; }
                 }
+                float acc[4][4][2];
                 mbar_wait(&win_full[wi], wph);
                 if (inside) {
                     const unsigned char* tile_p = win + (size_t)wi * T::BYTES + lane * 4 +
                                                   ((by * 4 * S) * T::IW + bx * 4 * S) * 128;
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) { acc[i][j][0] = bias0; acc[i][j][1] = bias1; }
 #pragma unroll
                     for (int ry = 0; ry < T::WIN_Y; ry++) {
                         float v2[T::WIN_X][2];
@@ -1256,6 +1192,7 @@ k_dw_gemm(const __grid_constant__ CUtensorMap tmap_win, const __grid_constant__ 
                 // the window slot is free as soon as its values sit in registers
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&win_empty[wi]);
+                if (++wi == f.ws) { wi = 0; wph ^= 1; }
                 // A stage: row = pixel of the patch, 16-byte chunk index XOR (row & 7) (SWIZZLE_128B, K-major)
                 mbar_wait(&a_empty[ai], aph ^ 1);
                 if (inside) {
@@ -1272,9 +1209,42 @@ k_dw_gemm(const __grid_constant__ CUtensorMap tmap_win, const __grid_constant__ 
                 fence_proxy_async_shared();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_full[ai]);
-                wi += 2; if (wi >= f.ws) { wi -= f.ws; wph ^= 1u; }
-                ai += 2; if (ai >= f.as) { ai -= f.as; aph ^= 1u; }
+                if (++ai == f.as) { ai = 0; aph ^= 1; }
             }
+        }
+    } else {
+        // ===== epilogue warps: TMEM lane quadrant = warp % 4 =====
+        const int q = warp & 3;
+        const int n_chunks = f.n_pad / CHUNK;
+        int acc = 0; uint32_t acc_ph = 0;
+        for (int tile = blockIdx.x; tile < g.m_blocks; tile += gridDim.x) {
+            mbar_wait(&tmem_full[acc], acc_ph);
+            tcgen05_fence_after();
+            const int m = tile_row_to_m(g, tile, q * 32 + lane);
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (uint32_t)(acc * f.n_pad);
+            uint32_t va[CHUNK], vb[CHUNK];
+            auto process = [&](int ci, const uint32_t* v) {
+                float accf[CHUNK];
+#pragma unroll
+                for (int j = 0; j < CHUNK; j++) accf[j] = __uint_as_float(v[j]);
+                const int n0 = ci * CHUNK;
+                if (n0 < ((g.N + 7) & ~7)) epilogue_chunk(g, m, n0, accf, bias_s + n0, nullptr, dest_s);
+            };
+            tmem_ld16_async(t_row, va);
+            for (int ci = 0; ci < n_chunks; ci += 2) {
+                tmem_ld_wait(va);
+                if (ci + 1 < n_chunks) tmem_ld16_async(t_row + (uint32_t)((ci + 1) * CHUNK), vb);
+                process(ci, va);
+                if (ci + 1 < n_chunks) {
+                    tmem_ld_wait(vb);
+                    if (ci + 2 < n_chunks) tmem_ld16_async(t_row + (uint32_t)((ci + 2) * CHUNK), va);
+                    process(ci + 1, vb);
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == f.acc_stages) { acc = 0; acc_ph ^= 1; }
         }
     }
     tcgen05_fence_before();
@@ -1285,9 +1255,9 @@ k_dw_gemm(const __grid_constant__ CUtensorMap tmap_win, const __grid_constant__ 
     }
 }
 
-size_t fused_smem_bytes(int ws, int as, int bs, int n_pad, int c_dw_staged) {
+size_t fused_smem_bytes(int ws, int as, int bs, int n_pad, int c_dw) {
     return 1024 + (size_t)as * BM * BK * 2 + (size_t)bs * n_pad * BK * 2 + (size_t)ws * DwTile<1, PH, PW, 4, 1>::BYTES +
-           (size_t)n_pad * 5 + (size_t)c_dw_staged * 26 * 4 + (size_t)(2 * (ws + as + bs) + 4) * 8 + 64;
+           (size_t)n_pad * 5 + (size_t)c_dw * 26 * 4 + (size_t)(2 * (ws + as + bs) + 4) * 8 + 64;
 }
 
 // ------------------------------------------------------------------ input conv: f32 NCHW [B,3,H,W] -> bf16 NHWC
@@ -2087,20 +2057,17 @@ int pifpaf_net_dw_conv1x1_scatter(pifpaf_net_t* net, int32_t in_tensor, int32_t 
     // ring depths: as deep as the shared memory allows, windows first (their TMA has the longest latency)
     // (an A stage is written only after the depthwise warps hold their results in registers, so one A stage costs
     // little; a single B stage would expose the weight TMA latency in every K block)
-    // The two depthwise groups work on consecutive K blocks at the same time: at least two windows and two A stages.
-    // The depthwise weights are staged in shared memory only if that costs no ring stage.
-    const int cand[][3] = {{4, 4, 2}, {4, 3, 2}, {3, 3, 2}, {3, 2, 2}, {2, 2, 2}, {2, 2, 1}};
+    // (an A stage is written only after the depthwise warps hold their results in registers, so one A stage costs
+    // little; a single B stage would expose the weight TMA latency in every K block)
+    const int cand[][3] = {{3, 3, 2}, {3, 2, 2}, {2, 2, 2}, {2, 1, 2}, {2, 2, 1}, {1, 1, 1}};
     bool fits = false;
     for (const auto& c : cand) {
-        for (int wsm = 1; wsm >= 0 && !fits; wsm--) {
-            if (fused_smem_bytes(c[0], c[1], c[2], f.n_pad, wsm ? C : 0) <= GEMM_SMEM_BUDGET) {
-                f.ws = c[0]; f.as = c[1]; f.bs = c[2]; f.w_smem = wsm; fits = true;
-            }
+        if (fused_smem_bytes(c[0], c[1], c[2], f.n_pad, C) <= GEMM_SMEM_BUDGET) {
+            f.ws = c[0]; f.as = c[1]; f.bs = c[2]; fits = true; break;
         }
-        if (fits) break;
     }
     PIFPAF_CHECK_ARG(fits, "fused depthwise -> 1x1 op does not fit in shared memory");
-    op.smem = fused_smem_bytes(f.ws, f.as, f.bs, f.n_pad, f.w_smem ? C : 0);
+    op.smem = fused_smem_bytes(f.ws, f.as, f.bs, f.n_pad, C);
     op.n_real = n_real;
     op.flops_per_image = 2.0 * (double)op.rows_per_image * ((double)nnz + 25.0 * channels);
     op.bytes_per_image = (double)op.rows_per_image * (channels + n_real) * 2.0;     // dw input once + 1x1 output once
