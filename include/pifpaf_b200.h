@@ -156,7 +156,9 @@ int pifpaf_decoder_debug_set_epochs(pifpaf_decoder_t* dec, uint32_t occupancy_ep
 
 /* Work counters of the last decode, summed over its batch (synchronises; bench.py's decoder roofline):
  * stats[0] hi-res CifHr pixels written (the map is tile-sparse), [1] seeds (CifSeeds.get), [2] CAF list entries
- * (forward + backward, CafScored.get; of the force-complete refill if that ran), [3] annotations before NMS. */
+ * (forward + backward, CafScored.get; of the force-complete refill if that ran), [3] annotations before NMS;
+ * with n_stats >= 10 also the seed loop's diagnostics: [4] rounds, [5] seeds grown speculatively, [6..9] SM clocks
+ * spent in setup / seed selection / growing / committing (one CTA per image, summed). */
 int pifpaf_decoder_last_stats(pifpaf_decoder_t* dec, int64_t* stats, int32_t n_stats);
 
 /* Free op grow_connection_blend (csrc/src/cifcaf.cpp:32-113, module.cpp:60):

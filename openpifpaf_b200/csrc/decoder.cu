@@ -900,24 +900,33 @@ __device__ void grow_shared_init(GrowShared& g, unsigned char* smem, const Graph
     for (int i = threadIdx.x; i <= K; i += blockDim.x) s_adj_start[i] = gr.adj_start[i];
     __syncthreads();
     for (int i = threadIdx.x; i < s_adj_start[K]; i += blockDim.x) s_adj_edge[i] = gr.adj_edge[i];
+    // list offsets in the staging area: counts fetched in parallel (s_loff doubles as scratch), then one thread runs
+    // the greedy first-fit prefix over shared memory (a serial walk over global memory cost 20 us per image with 38
+    // lists and 210 us with the 320 lists of the wholebody skeleton, measured round 2)
+    for (int li = threadIdx.x; li < 2 * C; li += blockDim.x) s_loff[li] = list_counts[li];
+    __syncthreads();
     if (threadIdx.x == 0) {
         int run = 0;
         for (int li = 0; li < 2 * C; li++) {
-            const int n = list_counts[li];
+            const int n = s_loff[li];
             if (run + n <= list_cap) { s_loff[li] = run; run += n; }
             else s_loff[li] = -1;
         }
     }
     __syncthreads();
-    for (int li = 0; li < 2 * C; li++) {
-        const int off = s_loff[li];
-        if (off < 0) continue;
-        const int n = list_counts[li];
-        const float* L = lists + ((size_t)li * 7) * d.hw;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            s_cxy[off + i] = L[i];
-            s_cxy[list_cap + off + i] = L[d.hw + i];
-            s_cxy[2 * list_cap + off + i] = L[2 * (size_t)d.hw + i];
+    // one warp per list (lists are short: a few dozen entries)
+    {
+        const int warp_i = threadIdx.x >> 5, lane_i = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+        for (int li = warp_i; li < 2 * C; li += n_warps) {
+            const int off = s_loff[li];
+            if (off < 0) continue;
+            const int n = list_counts[li];
+            const float* L = lists + ((size_t)li * 7) * d.hw;
+            for (int i = lane_i; i < n; i += 32) {
+                s_cxy[off + i] = L[i];
+                s_cxy[list_cap + off + i] = L[d.hw + i];
+                s_cxy[2 * list_cap + off + i] = L[2 * (size_t)d.hw + i];
+            }
         }
     }
     g.skeleton = s_skel; g.adj_start = s_adj_start; g.adj_edge = s_adj_edge; g.edge_lookup = s_lookup; g.pair_id = s_pair;
@@ -943,22 +952,29 @@ __global__ void __launch_bounds__(32 * GROW_MAX_WORKERS) k_grow(Dims d, Graph gr
                                              const float* __restrict__ init_ann, const long long* __restrict__ init_ids,
                                              const int* __restrict__ init_counts, int init_cap,
                                              Joint* __restrict__ anns, long long* __restrict__ ann_ids,
-                                             int* __restrict__ n_anns, int* __restrict__ flags) {
+                                             int* __restrict__ n_anns, int* __restrict__ flags,
+                                             long long* __restrict__ dbg) {
+    // dbg (diagnostics, may be null): per image 6 values -- rounds, picks, clocks in init / select / grow / commit
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_sel[GROW_MAX_WORKERS];       // seed index (or initial-annotation index) per worker
     __shared__ int s_slot[GROW_MAX_WORKERS];      // output slot, or -1 if dropped
     __shared__ int s_wc[GROW_MAX_WORKERS];
     __shared__ float s_px[GROW_MAX_WORKERS], s_py[GROW_MAX_WORKERS], s_pr[GROW_MAX_WORKERS];   // picks: x, y, scale
+    __shared__ unsigned char s_cov[GROW_MAX_WORKERS][GROW_MAX_WORKERS];   // annotation a covers the seed of pick i
     __shared__ int s_nsel, s_ptr, s_nann, s_over, s_scan_end, s_stop;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int W = blockDim.x >> 5;
     GrowShared g;
     unsigned char* workers_base; int* ctl;
+    long long t_mark = clock64(), t_init = 0, t_sel = 0, t_grow = 0, t_commit = 0;
+    int n_rounds = 0, n_picks = 0;
+    auto lap = [&](long long& acc) { const long long now = clock64(); acc += now - t_mark; t_mark = now; };
     grow_shared_init(g, smem, gr, d, list_cap, lists + ((size_t)b * d.C * 2 * 7) * d.hw,
                      list_counts + (size_t)b * d.C * 2, gp, &workers_base, &ctl);
     (void)ctl;
     Worker w;
     worker_init(w, workers_base + (size_t)warp * worker_bytes(d.K, d.C), d.K, d.C);
+    lap(t_init);
     // every warp can read every worker's joints at commit time
     auto joints_of = [&](int wk) { return reinterpret_cast<const WJoint*>(workers_base + (size_t)wk * worker_bytes(d.K, d.C)); };
 
@@ -1072,7 +1088,9 @@ __global__ void __launch_bounds__(32 * GROW_MAX_WORKERS) k_grow(Dims d, Graph gr
         __syncthreads();
         const int n_sel = s_nsel;
         const int scan_end = s_scan_end;
+        lap(t_sel);
         if (n_sel == 0) break;                    // every remaining seed is covered by the map
+        n_rounds++; n_picks += n_sel;
         // 2. grow, one warp per picked seed
         if (warp < n_sel) {
             const int si = s_sel[warp];
@@ -1087,17 +1105,25 @@ __global__ void __launch_bounds__(32 * GROW_MAX_WORKERS) k_grow(Dims d, Graph gr
         }
         if (tid == 0) s_stop = INT_MAX;
         __syncthreads();
-        // 3a. keep / drop of the picks among themselves, in seed order (picks are in ascending seed order)
-        if (tid == 0) {
-            for (int i = 0; i < n_sel; i++) {
+        lap(t_grow);
+        // 3a. keep / drop of the picks among themselves, in seed order (picks are in ascending seed order): the
+        // "annotation a would cover seed i" matrix in parallel, then the order-dependent walk over it
+        if (tid < GROW_MAX_WORKERS * GROW_MAX_WORKERS) {
+            const int i = tid / GROW_MAX_WORKERS, a = tid % GROW_MAX_WORKERS;
+            bool c = false;
+            if (a < i && i < n_sel) {
                 const int si = s_sel[i];
                 const float4 sd = sv[si];
                 const int f = sf[si];
+                if (f < d.F && f < d.K) c = occ_joint_covers(occ, joints_of(a)[f], (double)sd.y, (double)sd.z);
+            }
+            s_cov[i][a] = c ? 1 : 0;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int i = 0; i < n_sel; i++) {
                 bool covered = false;
-                for (int a = 0; a < i && !covered; a++) {
-                    if (s_slot[a] < 0) continue;
-                    if (f < d.F && f < d.K) covered = occ_joint_covers(occ, joints_of(a)[f], (double)sd.y, (double)sd.z);
-                }
+                for (int a = 0; a < i && !covered; a++) covered = s_slot[a] >= 0 && s_cov[i][a];
                 s_slot[i] = covered ? -1 : 0;
             }
         }
@@ -1136,7 +1162,12 @@ __global__ void __launch_bounds__(32 * GROW_MAX_WORKERS) k_grow(Dims d, Graph gr
         __syncthreads();
         if (warp < n_sel && s_slot[warp] >= 0) commit_mine(s_slot[warp], -1);
         __syncthreads();          // occupancy marks visible to the next selection
+        lap(t_commit);
         if (s_ptr >= ns) break;
+    }
+    if (dbg != nullptr && tid == 0) {
+        long long* o = dbg + (size_t)b * 6;
+        o[0] = n_rounds; o[1] = n_picks; o[2] = t_init; o[3] = t_sel; o[4] = t_grow; o[5] = t_commit;
     }
     if (tid == 0) {
         n_anns[b] = s_nann;
@@ -1349,6 +1380,7 @@ struct pifpaf_decoder {
     float* d_lists = nullptr; int* d_list_counts = nullptr;
     unsigned char* d_occ = nullptr; size_t occ_bytes = 0;
     Joint* d_anns = nullptr; long long* d_ann_ids = nullptr; int* d_n_anns = nullptr; int* d_flags = nullptr;
+    long long* d_grow_dbg = nullptr;      // k_grow diagnostics (rounds, picks, clocks per phase), [B][6]
     float4* d_out_ann = nullptr; long long* d_out_ids = nullptr; int* d_out_counts = nullptr;
     // packed results, double buffered (device + pinned host + event) so that a fetch can overlap the next decode
     unsigned char* d_result[2] = {nullptr, nullptr};
@@ -1423,7 +1455,7 @@ void pifpaf_decoder_destroy(pifpaf_decoder_t* dec) {
         dec->d_work_count, dec->d_seg_v, dec->d_seg_xys,
         dec->d_seg_counts, dec->d_keys_a, dec->d_vals_a, dec->d_keys_b, dec->d_vals_b, dec->d_seed_f,
         dec->d_seed_vxys, dec->d_n_seeds, dec->d_lists, dec->d_list_counts, dec->d_occ, dec->d_anns,
-        dec->d_ann_ids, dec->d_n_anns, dec->d_flags, dec->d_out_ann, dec->d_out_ids, dec->d_out_counts,
+        dec->d_ann_ids, dec->d_n_anns, dec->d_flags, dec->d_grow_dbg, dec->d_out_ann, dec->d_out_ids, dec->d_out_counts,
         dec->d_result[0], dec->d_result[1], dec->d_in_cif, dec->d_in_caf, dec->d_in_init,
         dec->d_in_init_ids, dec->d_in_init_count};
     for (void* p : dev_ptrs) if (p) cudaFree(p);
@@ -1537,6 +1569,7 @@ int pifpaf_decoder_create(pifpaf_decoder_t** out, int32_t device, int32_t n_keyp
     TRY_D(cudaMemset(dec->d_occ, 0, dec->occ_bytes));
     const size_t A = max_annotations;
     ALLOC(dec->d_anns, B * A * K); ALLOC(dec->d_ann_ids, B * A); ALLOC(dec->d_n_anns, B); ALLOC(dec->d_flags, B);
+    ALLOC(dec->d_grow_dbg, B * 6);
     ALLOC(dec->d_out_ann, B * A * K); ALLOC(dec->d_out_ids, B * A); ALLOC(dec->d_out_counts, B);
     dec->result_bytes = result_header_bytes((int)B) + B * A * (K + 1) * sizeof(float4);
     // one async D2H copies the header and this much payload; the (rare) rest is fetched on demand
@@ -1645,7 +1678,7 @@ int pifpaf_decoder_decode_device(pifpaf_decoder_t* dec, const float* cif_dev, co
     k_grow<<<d.B, grow_threads, gs, st>>>(d, gr, gp, dec->grow.list_cap, dec->d_seed_f, dec->d_seed_vxys, dec->d_n_seeds, dec->d_lists,
                                 dec->d_list_counts, dec->d_occ, tag_seed, init_ann_dev,
                                 reinterpret_cast<const long long*>(init_ids_dev), init_counts_dev, init_cap,
-                                dec->d_anns, dec->d_ann_ids, dec->d_n_anns, dec->d_flags);
+                                dec->d_anns, dec->d_ann_ids, dec->d_n_anns, dec->d_flags, dec->d_grow_dbg);
     PIFPAF_LAUNCH_CHECK();
     if (p.force_complete && d.C > 0) {
         // src/cifcaf.cpp:414-426: CafScored(cifhr, rev, force_complete_caf_th, 0.1); score_th_ >= 0 ? it : default
@@ -1868,6 +1901,11 @@ int pifpaf_decoder_last_stats(pifpaf_decoder_t* dec, int64_t* stats, int32_t n_s
     for (size_t i = 0; i < (size_t)d.B * d.C * 2; i++) nl += lists[i];
     stats[0] = (int64_t)tiles * TILE * TILE;   // hi-res CifHr pixels written (sparse map)
     stats[1] = ns; stats[2] = nl; stats[3] = na;
+    if (n_stats >= 10) {       // k_grow diagnostics, summed over the batch: rounds, picks, clocks in init/select/grow/commit
+        std::vector<long long> dbg((size_t)d.B * 6);
+        PIFPAF_CUDA_TRY(cudaMemcpy(dbg.data(), dec->d_grow_dbg, sizeof(long long) * dbg.size(), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < 6; k++) { long long t = 0; for (int b = 0; b < d.B; b++) t += dbg[(size_t)b * 6 + k]; stats[4 + k] = t; }
+    }
     return PIFPAF_OK;
 }
 

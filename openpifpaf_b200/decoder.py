@@ -285,10 +285,11 @@ class CifCaf(metaclass=_Statics):
     def last_stats(self):
         """Work counters of the last decode over its batch (synchronises): hi-res pixels written, seeds, CAF list
         entries, annotations before NMS."""
-        out = (ctypes.c_int64 * 4)()
-        _lib.check(_lib.lib().pifpaf_decoder_last_stats(self._handle, out, 4))
+        out = (ctypes.c_int64 * 10)()
+        _lib.check(_lib.lib().pifpaf_decoder_last_stats(self._handle, out, 10))
         return {'cifhr_pixels_written': int(out[0]), 'seeds': int(out[1]), 'caf_entries': int(out[2]),
-                'annotations_before_nms': int(out[3])}
+                'annotations_before_nms': int(out[3]), 'grow_rounds': int(out[4]), 'grow_seeds_grown': int(out[5]),
+                'grow_clocks': {'setup': int(out[6]), 'select': int(out[7]), 'grow': int(out[8]), 'commit': int(out[9])}}
 
     def get_cifhr(self, image=0):
         """csrc/src/module.cpp:36-38: (accumulated [F,H,W] float32, revision)."""

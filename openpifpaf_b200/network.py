@@ -397,6 +397,15 @@ def _plan_stage_bins(bf, n_blocks):
     return producers, bins, final
 
 
+def _branch_pitch(bf):
+    """Physical channel count of the branch-internal tensors (1x1 -> depthwise -> 1x1).  The depthwise kernels fetch
+    one 64-channel block (128 bytes) per pixel and CTA; with a pitch that is a multiple of 64 channels every block is
+    one aligned 128-byte line instead of straddling two 64-byte DRAM atoms.  PIFPAF_BRANCH_PAD selects the multiple
+    (16: the round-1 layout)."""
+    mult = int(os.environ.get('PIFPAF_BRANCH_PAD', '16'))
+    return (bf + mult - 1) // mult * mult
+
+
 def default_layout():
     """'bins' (no pass-through copies, see _plan_stage_bins) or 'shuffle' (every block writes the interleaved
     2*bf-channel tensor through the fused cat+shuffle epilogue); PIFPAF_LAYOUT overrides."""
@@ -508,7 +517,7 @@ def build_ops(plan, in_h, in_w, layout=None, fuse_dw=None):
     for blocks in plan['stages'] if layout == 'bins' else []:
         # ---- 'bins' layout: every channel is written once, into the buffer of the block that consumes it
         bf = blocks[0]['b2_pw2'][0].shape[0]
-        hp = pad16(bf)
+        hp = _branch_pitch(bf)
         e0 = blocks[0]
         kk, st, pd = e0['kernel'], e0['stride'], e0['pad']
         ho, wo = (h + 2 * pd - kk) // st + 1, (w + 2 * pd - kk) // st + 1

@@ -25,6 +25,11 @@ def run(workload, B, n_people, reps=20, label=''):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
+    st = d.last_stats()
+    ck = st['grow_clocks']
+    print(f'   k_grow per image: rounds {st["grow_rounds"] / B:.2f}, seeds grown {st["grow_seeds_grown"] / B:.1f}, '
+          f'annotations {st["annotations_before_nms"] / B:.1f}; kclocks setup {ck["setup"] / B / 1e3:.0f} select {ck["select"] / B / 1e3:.0f} '
+          f'grow {ck["grow"] / B / 1e3:.0f} commit {ck["commit"] / B / 1e3:.0f}', flush=True)
     print(f'{label or workload} B={B} people={n_people}: {ms:.3f} ms/batch = {ms / B:.4f} ms/img, '
           f'{n_ann} annotations (planted {sum(batch["n_planted"])})', flush=True)
 
