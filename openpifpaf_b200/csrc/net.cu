@@ -98,6 +98,25 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// the same, executed by a converged warp: descriptors as (lo, hi) words, one elected lane issues
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(smem_u32(bar)) : "memory");
+}
 // mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -942,6 +961,242 @@ constexpr int DW1_TH = 8, DW1_TW = 16, DW2_TH = 8, DW2_TW = 16;
 using DwS1 = DwTile<1, DW1_TH, DW1_TW, 4, 3>;
 using DwS2 = DwTile<2, DW2_TH, DW2_TW, 4, 2>;
 
+// ------------------------------------------------------------------ depthwise 5x5 on the tensor cores
+// k_dwconv5_tma is bound by FMA issue (25 FFMA per output value, ncu: issue active 77 %), at 40 % of what HBM allows.
+// The same sums as block-diagonal tcgen05 MMAs: for one tap (dy, dx) and one group of 16 channels
+//     D[pixel][c] += A[pixel][c'] * B[c'][c],   A = the input window shifted by the tap, B = diag(w[tap][c])
+// is ONE UMMA of M = 128 pixels, N = 16, K = 16 (8 tensor-pipe cycles at the N-proportional rate): 100 MMAs per
+// 128-pixel x 64-channel item = 800 cycles, against >= 1600 cycles of FFMA for the same item.  Nothing is gathered:
+// the window lies in shared memory exactly as TMA wrote it (SWIZZLE_128B, one 128-byte row per pixel = 64 channels),
+// which IS the canonical K-major A layout with "row" = window pixel.  An output tile is 16 rows x 8 pixels, so the
+// 8 rows of a core-matrix group are 8 horizontally consecutive window pixels and the group stride (SBO) is one
+// window row; a tap only moves the descriptor start address by (dy * IW + dx) pixels = that many 128-byte rows and
+// a channel group by 32 bytes inside the swizzle atom (the XOR pattern is a function of the shared-memory address).
+// The depthwise weights are rounded to bf16 (as every 1x1 weight is); bias and accumulation stay f32.
+// Stride 2: the window is loaded as two column-phase planes (TMA elementStrides {1,2,1,1}), so that the pixels of
+// one group are again consecutive 128-byte rows; the group stride is two plane rows.
+constexpr int DT_TH = 16, DT_TW = 8;
+constexpr int DT_EPI_WARPS = 8;
+constexpr int DT_THREADS = 64 + 32 * DT_EPI_WARPS;
+constexpr int DT_B_TAP = 16 * 128;                 // one tap: 16 rows (n) x 64 k slots, diagonal of each 16x16 group
+constexpr int DT_B_BYTES = 25 * DT_B_TAP;
+
+template <int S>
+struct DwTc {
+    static constexpr int IH = (DT_TH - 1) * S + 5;
+    static constexpr int NEED_W = (DT_TW - 1) * S + 5;                 // 12 / 19 input columns
+    static constexpr int PLANES = S;
+    static constexpr int PWID = S == 1 ? 12 : 10;                      // plane width in pixels
+    static constexpr int PLANE_BYTES = ((IH * PWID * 128 + 1023) / 1024) * 1024;
+    static constexpr int STAGE_BYTES = PLANES * PLANE_BYTES;
+    static constexpr int STAGES = S == 1 ? 4 : 2;
+    // stride 2 fills the 227 KB: no slack for aligning the base (the kernel traps if it is not 1024-byte aligned)
+    static constexpr int SMEM = STAGES * STAGE_BYTES + DT_B_BYTES + 64 * 4 + 128 + (S == 1 ? 1024 : 0);
+};
+
+struct DwTcArgs {
+    int pwid;            // plane width actually used (test switch: 12 or 16 for stride 1)
+    int base_off_mode;   // test switch: 1 = put (start >> 7) & 7 into the descriptor's base-offset field
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes, int base_off_mode) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3fffu);
+    d |= static_cast<uint64_t>(1u) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fffu) << 32;
+    d |= static_cast<uint64_t>(1u) << 46;
+    if (base_off_mode) d |= static_cast<uint64_t>((smem_addr >> 7) & 7u) << 49;
+    d |= static_cast<uint64_t>(2u) << 61;
+    return d;
+}
+
+template <int S>
+__global__ void __launch_bounds__(DT_THREADS, 1)
+k_dwconv5_tc(const __grid_constant__ CUtensorMap tmap_in, DwArgs a, DwTcArgs x) {
+    using T = DwTc<S>;
+    extern __shared__ __align__(1024) unsigned char dt_raw[];
+    unsigned char* smem = dt_raw + ((1024u - (smem_u32(dt_raw) & 1023u)) & 1023u);
+    if (S == 2 && smem != dt_raw) __trap();
+    const int plane_bytes = S == 1 ? ((T::IH * x.pwid * 128 + 1023) / 1024) * 1024 : T::PLANE_BYTES;
+    const int stage_bytes = T::PLANES * plane_bytes;
+    unsigned char* b_s = smem + (size_t)T::STAGES * stage_bytes;        // 1024-aligned: stage_bytes % 1024 == 0
+    float* bias_s = reinterpret_cast<float*>(b_s + DT_B_BYTES);         // [64]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + 64);      // [STAGES]
+    uint64_t* empty_bar = full_bar + T::STAGES;                         // [STAGES]
+    uint64_t* tmem_full = empty_bar + T::STAGES;                        // [2]
+    uint64_t* tmem_empty = tmem_full + 2;                               // [2]
+    uint64_t* b_ready = tmem_empty + 2;                                 // [1]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_ready + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles_x = (a.Wout + DT_TW - 1) / DT_TW, tiles_y = (a.Hout + DT_TH - 1) / DT_TH;
+    const int cblks = (a.C8 + 7) / 8;
+    const int per_c = a.B * tiles_y * tiles_x;
+    const int total = per_c * cblks;
+    const int C = a.C8 * 8;
+    constexpr uint32_t TMEM_COLS = 128;                                 // two accumulator stages of 64 columns
+
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_in);
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < T::STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+            for (int i = 0; i < 2; i++) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], DT_EPI_WARPS); }
+            mbar_init(b_ready, DT_EPI_WARPS);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_ptr, TMEM_COLS);
+    }
+    // the off-diagonal zeros of B are written once; a channel-block change rewrites the diagonals only
+    for (int i = tid; i < DT_B_BYTES / 16; i += DT_THREADS) reinterpret_cast<uint4*>(b_s)[i] = make_uint4(0, 0, 0, 0);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    pdl_launch_dependents();
+    pdl_wait();
+
+    const DwPos step = dw_decompose(gridDim.x, per_c, tiles_y, tiles_x);
+    DwPos pos = dw_decompose(blockIdx.x, per_c, tiles_y, tiles_x);
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int w = blockIdx.x; w < total; w += gridDim.x) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                unsigned char* dst = smem + (size_t)stage * stage_bytes;
+                const int x0 = pos.x * DT_TW * S - a.pad, y0 = pos.y * DT_TH * S - a.pad;
+                mbar_expect_tx(&full_bar[stage], (uint32_t)(T::PLANES * T::IH * x.pwid * 128));
+#pragma unroll
+                for (int p = 0; p < T::PLANES; p++)
+                    tma_load_4d(dst + (size_t)p * plane_bytes, &tmap_in, &full_bar[stage], pos.c * 64, x0 + p, y0, pos.b);
+                dw_advance(pos, step, a.B, tiles_y, tiles_x);
+                if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: the whole warp runs the loop converged (descriptor arithmetic on the uniform datapath),
+        // one elected lane issues =====
+        {
+            const uint32_t idesc = make_instr_desc(BM, 16);
+            const uint32_t sbo = (uint32_t)(S * x.pwid * 128);              // one output row down = S plane rows
+            const uint32_t a_hi = (uint32_t)(make_smem_desc_sbo(0, sbo, 0) >> 32);
+            const uint32_t b_hi = (uint32_t)(make_smem_desc(0) >> 32);
+            const uint32_t b_lo0 = (smem_u32(b_s) >> 4) | (1u << 16);
+            const uint32_t tmem_b = __shfl_sync(0xffffffffu, tmem_base, 0);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            int cur_c = -1; uint32_t b_phase = 0;
+            for (int w = blockIdx.x; w < total; w += gridDim.x) {
+                if (pos.c != cur_c) {                                        // weights of a new channel block
+                    cur_c = pos.c;
+                    mbar_wait(b_ready, b_phase); b_phase ^= 1;
+                }
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                mbar_wait(&full_bar[stage], phase);
+                __syncwarp();
+                tcgen05_fence_after();
+                const uint32_t sa = smem_u32(smem) + (uint32_t)(stage * stage_bytes);
+                const uint32_t a_lo0 = (sa >> 4) | (1u << 16);
+                const uint32_t d_tmem = tmem_b + (uint32_t)(acc * 64);
+#pragma unroll 1
+                for (int dy = 0; dy < 5; dy++) {
+                    const uint32_t a_row = a_lo0 + (uint32_t)(dy * x.pwid * 8);
+                    const uint32_t b_row = b_lo0 + (uint32_t)(dy * 5 * (DT_B_TAP >> 4));
+#pragma unroll
+                    for (int dx = 0; dx < 5; dx++) {
+                        const uint32_t a_tap = a_row + (uint32_t)((dx % S) * (plane_bytes >> 4)) + (uint32_t)((dx / S) * 8);
+                        const uint32_t b_tap = b_row + (uint32_t)(dx * (DT_B_TAP >> 4));
+#pragma unroll
+                        for (int gq = 0; gq < 4; gq++) {
+                            uint32_t ahi = a_hi;
+                            if (x.base_off_mode) ahi |= (((a_tap + gq * 2) >> 3) & 7u) << 17;
+                            umma_bf16_elect(d_tmem + (uint32_t)(gq * 16), a_tap + gq * 2, ahi, b_tap + gq * 2, b_hi, idesc,
+                                            (dy | dx) != 0 ? 1u : 0u);
+                        }
+                    }
+                }
+                umma_commit_elect(&empty_bar[stage]);
+                umma_commit_elect(&tmem_full[acc]);
+                dw_advance(pos, step, a.B, tiles_y, tiles_x);
+                if (++stage == T::STAGES) { stage = 0; phase ^= 1; }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue warps: TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4 =====
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int etid = tid - 64;
+        const int row = q * 32 + lane;                      // tile row == TMEM lane: output pixel (row / 8, row % 8)
+        const int ry = row / DT_TW, rx = row % DT_TW;
+        int acc = 0; uint32_t acc_phase = 0;
+        int cur_c = -1;
+        for (int w = blockIdx.x; w < total; w += gridDim.x) {
+            if (pos.c != cur_c) {
+                // every MMA that read the old diagonals has retired: this warp has passed tmem_full of all earlier
+                // items, and the issuer does not start this item before b_ready
+                cur_c = pos.c;
+                for (int i = etid; i < 25 * 64; i += 32 * DT_EPI_WARPS) {
+                    const int tap = i >> 6, c = i & 63, gq = c >> 4, n = c & 15;
+                    const int cg = pos.c * 64 + c;
+                    const float wv = cg < C ? a.weight[(size_t)tap * C + cg] : 0.f;
+                    const int chunk = 2 * gq + (n >> 3);
+                    *reinterpret_cast<__nv_bfloat16*>(b_s + tap * DT_B_TAP + n * 128 + ((chunk ^ (n & 7)) << 4) + (n & 7) * 2) =
+                        __float2bfloat16_rn(wv);
+                }
+                // bias_s is read by the epilogue warps only: order the rewrite behind their reads of the old values
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * DT_EPI_WARPS) : "memory");
+                if (etid < 64) bias_s[etid] = pos.c * 64 + etid < C ? a.bias[pos.c * 64 + etid] : 0.f;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * DT_EPI_WARPS) : "memory");
+                if (lane == 0) mbar_arrive(b_ready);
+            }
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tcgen05_fence_after();
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (uint32_t)(acc * 64 + half * 32);
+            uint32_t va[CHUNK], vb[CHUNK];
+            tmem_ld16_async(t_row, va);
+            tmem_ld16_async(t_row + 16, vb);
+            tmem_ld_wait(va);
+            tmem_ld_wait(vb);
+            // the accumulator stage is free as soon as its values are in registers
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            const int oy = pos.y * DT_TH + ry, ox = pos.x * DT_TW + rx;
+            const int c0 = pos.c * 64 + half * 32;
+            if (oy < a.Hout && ox < a.Wout) {
+                __nv_bfloat16* op = a.out + ((size_t)(pos.b * a.Hout + oy) * a.Wout + ox) * a.ld_out + a.out_col_off + c0;
+                const float* bs = bias_s + half * 32;
+#pragma unroll
+                for (int h8 = 0; h8 < 4; h8++) {
+                    if (c0 + h8 * 8 >= C) break;
+                    const uint32_t* v = h8 < 2 ? va + h8 * 8 : vb + (h8 - 2) * 8;
+                    float f[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        f[j] = __uint_as_float(v[j]) + bs[h8 * 8 + j];
+                        if (a.relu) f[j] = fmaxf(f[j], 0.f);
+                    }
+                    uint4 ov;
+                    ov.x = pack_bf16(f[0], f[1]); ov.y = pack_bf16(f[2], f[3]);
+                    ov.z = pack_bf16(f[4], f[5]); ov.w = pack_bf16(f[6], f[7]);
+                    *reinterpret_cast<uint4*>(op + h8 * 8) = ov;
+                }
+            }
+            dw_advance(pos, step, a.B, tiles_y, tiles_x);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
 // generic depthwise kxk (any kernel/stride): one output pixel x 8 channels per thread
 __global__ void __launch_bounds__(256) k_dwconv(DwArgs a) {
     const long long total = (long long)a.B * a.Hout * a.Wout * a.C8;
@@ -1478,6 +1733,29 @@ int make_tmap_dw(CUtensorMap* map, const void* base, uint64_t c, uint64_t w, uin
     return PIFPAF_OK;
 }
 
+// 4-D bf16 NHWC view {C, W, H, B} for the tensor-core depthwise kernel: 64 channels x plane_w x box_h window pixels,
+// SWIZZLE_128B (one 128-byte row per pixel: the K-major UMMA A layout), every x_stride-th column (stride 2: one
+// column-phase plane per load)
+int make_tmap_dw_tc(CUtensorMap* map, const void* base, uint64_t c, uint64_t w, uint64_t h, uint64_t b, uint64_t ld,
+                    uint32_t plane_w, uint32_t box_h, uint32_t x_stride) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (!fn) { pifpaf::set_error("cuTensorMapEncodeTiled entry point not available"); return PIFPAF_E_CUDA; }
+    const cuuint64_t dims[4] = {c, w, h, b};
+    const cuuint64_t strides[3] = {ld * 2, w * ld * 2, h * w * ld * 2};
+    const cuuint32_t box[4] = {64, (plane_w - 1) * x_stride + 1, box_h, 1};
+    const cuuint32_t estr[4] = {1, x_stride, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        pifpaf::set_error("cuTensorMapEncodeTiled (dw tc) failed (%d): c=%llu w=%llu h=%llu b=%llu ld=%llu box=%ux%u stride=%u",
+                          (int)r, (unsigned long long)c, (unsigned long long)w, (unsigned long long)h,
+                          (unsigned long long)b, (unsigned long long)ld, plane_w, box_h, x_stride);
+        return PIFPAF_E_CUDA;
+    }
+    return PIFPAF_OK;
+}
+
 // launch with (or without) the programmatic-stream-serialization attribute
 template <typename... KArgs, typename... Args>
 cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
@@ -1504,6 +1782,7 @@ struct Op {
     // dw
     DwArgs dw{};
     CUtensorMap tmap_dw{}; bool dw_tma = false;
+    CUtensorMap tmap_dw_tc{}; bool dw_tc = false;      // tensor-core depthwise (k_dwconv5_tc)
     // fused depthwise -> GEMM (OP_FUSED): g + tmap_dw (windows) + tmap_b
     FusedArgs fu{};
     // input conv
@@ -1532,6 +1811,8 @@ struct pifpaf_net {
     bool setup_synced = false;           // build-time memsets / uploads (legacy stream) ordered before the first forward
     int sm_limit = 0;                    // > 0: persistent grids use at most this many SMs
     bool pdl = true;                     // programmatic dependent launch between the ops of a forward (PIFPAF_PDL=0: off)
+    int dw_tc = 0;                       // depthwise 5x5 on the tensor cores: bit 0 stride 1, bit 1 stride 2 (PIFPAF_DW_TC)
+    int dw_tc_pwid = 12, dw_tc_bo = 0;   // descriptor experiments (PIFPAF_DW_TC_PWID = 12 | 16, PIFPAF_DW_TC_BO = 0 | 1)
     bool dw_cbf = false;                 // stride-2 depthwise: channel-block-fastest item order (PIFPAF_DW_CBF=1; measured neutral)
     int head_fields[4] = {0, 0, 0, 0}, head_comp[4] = {0, 0, 0, 0}, head_h = 0, head_w = 0;
     int in_h = 0, in_w = 0;
@@ -1696,6 +1977,11 @@ int pifpaf_net_create(pifpaf_net_t** out, int32_t device, int32_t max_batch) {
     net->device = device; net->max_batch = max_batch; net->n_sm = prop.multiProcessorCount;
     if (const char* e = std::getenv("PIFPAF_DW_CBF")) net->dw_cbf = std::atoi(e) != 0;
     if (const char* e = std::getenv("PIFPAF_PDL")) net->pdl = std::atoi(e) != 0;
+    if (const char* e = std::getenv("PIFPAF_DW_TC")) net->dw_tc = std::atoi(e);
+    if (const char* e = std::getenv("PIFPAF_DW_TC_PWID")) net->dw_tc_pwid = std::atoi(e) == 16 ? 16 : 12;
+    if (const char* e = std::getenv("PIFPAF_DW_TC_BO")) net->dw_tc_bo = std::atoi(e) != 0;
+    PIFPAF_CUDA_TRY(cudaFuncSetAttribute(k_dwconv5_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    PIFPAF_CUDA_TRY(cudaFuncSetAttribute(k_dwconv5_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     PIFPAF_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     PIFPAF_CUDA_TRY(cudaFuncSetAttribute(k_dwconv5_tma<1, DW1_TH, DW1_TW, 4, 3>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, DwS1::SMEM));
@@ -1972,6 +2258,14 @@ int pifpaf_net_dwconv(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off, 
                           (uint64_t)net->max_batch, (uint64_t)tin.c, bw, bh);
         if (rc != PIFPAF_OK) return rc;
         op.dw_tma = true;
+        if (pad == 2 && ((net->dw_tc >> (stride - 1)) & 1)) {
+            const uint32_t pw = stride == 1 ? (uint32_t)net->dw_tc_pwid : (uint32_t)DwTc<2>::PWID;
+            rc = make_tmap_dw_tc(&op.tmap_dw_tc, tin.data + in_col_off, (uint64_t)C, (uint64_t)tin.w, (uint64_t)tin.h,
+                                 (uint64_t)net->max_batch, (uint64_t)tin.c, pw,
+                                 stride == 1 ? DwTc<1>::IH : DwTc<2>::IH, (uint32_t)stride);
+            if (rc != PIFPAF_OK) return rc;
+            op.dw_tc = true;
+        }
     }
     net->ops.push_back(op);
     return PIFPAF_OK;
@@ -2200,7 +2494,20 @@ static int net_forward_impl(pifpaf_net_t* net, const float* images_dev, int32_t 
         } else if (op.kind == OP_DW) {
             DwArgs a = op.dw;
             a.B = batch;
-            if (op.dw_tma && gemm_impl == 0) {
+            if (op.dw_tc && gemm_impl == 0) {
+                const int cblks = (a.C8 + 7) / 8;
+                const long long total = (long long)batch * ((a.Hout + DT_TH - 1) / DT_TH) * ((a.Wout + DT_TW - 1) / DT_TW) * cblks;
+                const int grid = (int)std::min<long long>(total, (long long)n_sm);
+                DwTcArgs x; x.pwid = a.stride == 1 ? net->dw_tc_pwid : DwTc<2>::PWID; x.base_off_mode = net->dw_tc_bo;
+                if (a.stride == 1) {
+                    const size_t plane = (size_t)((DwTc<1>::IH * x.pwid * 128 + 1023) / 1024) * 1024;
+                    const size_t smem = DwTc<1>::STAGES * plane + DT_B_BYTES + 64 * 4 + 128 + 1024;
+                    PIFPAF_CUDA_TRY(launch_k(pdl, k_dwconv5_tc<1>, dim3(grid), dim3(DT_THREADS), smem, st, op.tmap_dw_tc, a, x));
+                } else {
+                    PIFPAF_CUDA_TRY(launch_k(pdl, k_dwconv5_tc<2>, dim3(grid), dim3(DT_THREADS), (size_t)DwTc<2>::SMEM, st,
+                                             op.tmap_dw_tc, a, x));
+                }
+            } else if (op.dw_tma && gemm_impl == 0) {
                 const int cblks = (a.C8 + 7) / 8;
                 // persistent grid == resident CTAs (stride 1: 2 per SM, stride 2: 1 per SM by shared memory)
                 if (a.stride == 1) {
