@@ -1811,6 +1811,7 @@ struct pifpaf_net {
     bool setup_synced = false;           // build-time memsets / uploads (legacy stream) ordered before the first forward
     int sm_limit = 0;                    // > 0: persistent grids use at most this many SMs
     bool pdl = true;                     // programmatic dependent launch between the ops of a forward (PIFPAF_PDL=0: off)
+    int gemm_res_stages = 0;             // weights-resident GEMMs: split N further until this many A stages fit (PIFPAF_GEMM_RES_STAGES)
     int dw_tc = 0;                       // depthwise 5x5 on the tensor cores: bit 0 stride 1, bit 1 stride 2 (PIFPAF_DW_TC)
     int dw_tc_pwid = 12, dw_tc_bo = 0;   // descriptor experiments (PIFPAF_DW_TC_PWID = 12 | 16, PIFPAF_DW_TC_BO = 0 | 1)
     bool dw_cbf = false;                 // stride-2 depthwise: channel-block-fastest item order (PIFPAF_DW_CBF=1; measured neutral)
@@ -1908,6 +1909,26 @@ int emit_gemm(pifpaf_net* net, Op& op, int in_tensor, int in_col_off, int k_cols
                      "conv1x1 input column window must start on a multiple of 8 channels and lie inside the tensor");
     int block_n, n_blocks;
     choose_block_n(n_out, &block_n, &n_blocks);
+    // weights-resident GEMMs stream A through what the resident weight tile leaves of the shared memory: with
+    // K = 352..416 and a 176..208-column tile that is 4-5 stages of 16 KB, too few bytes in flight per SM to cover
+    // the DRAM latency (the K <= 208 launches with 8 stages reach 5.5-6 TB/s, these 3.4-4.2).  Narrower tiles (more
+    // n blocks, A re-read from L2 by each of them) buy the stages back.
+    if (net->gemm_res_stages > 0) {
+        const int kb = (k_cols + BK - 1) / BK, np = pad16(n_out);
+        auto res_stages = [&](int bn, int nb) {
+            if (gemm_smem_bytes(bn, nb, 3, false, true, kb) > GEMM_SMEM_BUDGET) return 0;       // not resident at all
+            int st = 8;
+            while (gemm_smem_bytes(bn, nb, st, false, true, kb) > GEMM_SMEM_BUDGET) st--;
+            return st;
+        };
+        int st = res_stages(block_n, n_blocks);
+        while (st > 0 && st < net->gemm_res_stages && block_n > 64) {
+            const int nb = n_blocks + 1, bn = pad16((np + nb - 1) / nb);
+            if (bn < 64) break;
+            n_blocks = nb; block_n = bn;
+            st = res_stages(block_n, n_blocks);
+        }
+    }
     const int n_pad = block_n * n_blocks;
     const int k_pad = pad8(k_cols);
     std::vector<__nv_bfloat16> w((size_t)n_pad * k_pad, __float2bfloat16(0.f));
@@ -1977,6 +1998,7 @@ int pifpaf_net_create(pifpaf_net_t** out, int32_t device, int32_t max_batch) {
     net->device = device; net->max_batch = max_batch; net->n_sm = prop.multiProcessorCount;
     if (const char* e = std::getenv("PIFPAF_DW_CBF")) net->dw_cbf = std::atoi(e) != 0;
     if (const char* e = std::getenv("PIFPAF_PDL")) net->pdl = std::atoi(e) != 0;
+    if (const char* e = std::getenv("PIFPAF_GEMM_RES_STAGES")) net->gemm_res_stages = std::atoi(e);
     if (const char* e = std::getenv("PIFPAF_DW_TC")) net->dw_tc = std::atoi(e);
     if (const char* e = std::getenv("PIFPAF_DW_TC_PWID")) net->dw_tc_pwid = std::atoi(e) == 16 ? 16 : 12;
     if (const char* e = std::getenv("PIFPAF_DW_TC_BO")) net->dw_tc_bo = std::atoi(e) != 0;
