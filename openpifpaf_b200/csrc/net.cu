@@ -122,6 +122,30 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
+// ---- thread-block cluster of two CTAs sharing the A operand (TMA multicast)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r;
+}
+// all threads of both CTAs
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the box lands at the same shared-memory offset of every CTA in cta_mask and completes bytes on the mbarrier at
+// the same offset there
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                               uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(cta_mask), "r"(c0), "r"(c1)
+        : "memory");
+}
+// arrives on the mbarrier at this offset in every CTA of cta_mask once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+
 // asynchronous TMEM load of 16 columns; results are valid only after tmem_ld_wait(v)
 __device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t* v) {
     asm volatile(
@@ -200,6 +224,9 @@ struct GemmArgs {
     const __nv_bfloat16* src0; int ld0; int src0_col_off; int half; int gap;
     int src_tma;                 // pass-through tile arrives by TMA in shared memory (else read from global)
     int b_resident;              // all K blocks of this CTA's weight tile stay in shared memory (loaded once)
+    int mc;                      // weights-resident, two n blocks: the two CTAs of an M tile form a cluster and share A --
+                                 // each loads one half (64 rows) of every A stage and multicasts it to both (tmap_src = the
+                                 // 64-row A map); a stage is free when BOTH have consumed it
     // scatter: chunks of 16 columns go to different tensors (the 'bins' layout: every channel is written once,
     // into the buffer of the block that consumes it)
     const DestGroup* dest;       // [n_blocks * block_n / 16]
@@ -421,14 +448,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
-        if (g.src_tma) tma_prefetch_desc(&tmap_src);
+        if (g.src_tma || g.mc) tma_prefetch_desc(&tmap_src);
     }
     for (int i = threadIdx.x; i < g.n_blocks * g.block_n; i += GEMM_THREADS) bias_s[i] = g.bias[i];
     if (g.mode == MODE_SCATTER)
         for (int i = threadIdx.x; i < g.n_blocks * g.block_n / CHUNK; i += GEMM_THREADS) dest_s[i] = g.dest[i];
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < g.stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+            for (int s = 0; s < g.stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], g.mc ? 2 : 1); }
             for (int a = 0; a < 2; a++) {
                 mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], EPI_WARPS); mbar_init(&src_full[a], 1);
             }
@@ -442,6 +469,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // the peer's barriers must be initialised before anything of this CTA (multicast data, commit arrivals) reaches them
+    if (g.mc) cluster_sync_all();
+    const uint32_t mc_rank = g.mc ? cluster_ctarank() : 0;
     // (after the TMEM allocation: a dependent CTA that becomes co-resident must not take the columns first)
     pdl_launch_dependents();
     pdl_wait();
@@ -486,6 +516,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
                         const int tap = kb / g.conv_cblocks;
                         cb = kb - tap * g.conv_cblocks;
                         tma_load_4d(sa, &tmap_a, &full_bar[stage], cb * BK, cx + tap % g.conv_k, cy + tap / g.conv_k, cimg);
+                    } else if (g.mc) {
+                        // this CTA's half of the stage (64 rows = 8 KB, a whole number of swizzle atoms) to both CTAs; the
+                        // peer sends the other half.  The 16 KB expected above arrive from the two loads.
+                        tma_load_2d_mc(sa + mc_rank * (BM / 2) * BK * 2, &tmap_src, &full_bar[stage], g.a_col0 + kb * BK,
+                                       m_blk * BM + (int)mc_rank * (BM / 2), (uint16_t)3);
                     } else {
                         tma_load_2d(sa, &tmap_a, &full_bar[stage], g.a_col0 + kb * BK, m_blk * BM);
                     }
@@ -526,7 +561,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
                         const uint64_t bdesc = make_smem_desc(sb + k * UMMA_K * 2);
                         umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);          // frees the smem slot when the MMAs retire
+                    // frees the smem slot when the MMAs retire (multicast mode: in both CTAs, each refills half of it)
+                    if (g.mc) umma_commit_mc(&empty_bar[stage], (uint16_t)3); else umma_commit(&empty_bar[stage]);
                     if (++stage == g.stages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tmem_full[acc]);                // accumulator ready for the epilogue
@@ -580,6 +616,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
     }
     tcgen05_fence_before();
     __syncthreads();
+    // no CTA of a multicast pair may exit while the other can still send data or barrier arrivals into it
+    if (g.mc) cluster_sync_all();
     if (warp == 1) {
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);
@@ -1758,14 +1796,28 @@ int make_tmap_dw_tc(CUtensorMap* map, const void* base, uint64_t c, uint64_t w, 
 
 // launch with (or without) the programmatic-stream-serialization attribute
 template <typename... KArgs, typename... Args>
-cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+cudaError_t launch_kc(bool pdl, int cluster, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                      Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (pdl) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        n++;
+    }
+    if (cluster > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = (unsigned)cluster; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+        n++;
+    }
+    cfg.attrs = attr; cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    return launch_kc(pdl, 1, kernel, grid, block, smem, st, std::forward<Args>(args)...);
 }
 
 struct Tensor { int h, w, c; __nv_bfloat16* data; };
@@ -1811,6 +1863,7 @@ struct pifpaf_net {
     bool setup_synced = false;           // build-time memsets / uploads (legacy stream) ordered before the first forward
     int sm_limit = 0;                    // > 0: persistent grids use at most this many SMs
     bool pdl = true;                     // programmatic dependent launch between the ops of a forward (PIFPAF_PDL=0: off)
+    int gemm_mc = 0;                     // weights-resident GEMMs with two n blocks: cluster of two CTAs, A by TMA multicast (PIFPAF_GEMM_MC)
     int gemm_res_stages = 0;             // weights-resident GEMMs: split N further until this many A stages fit (PIFPAF_GEMM_RES_STAGES)
     int dw_tc = 0;                       // depthwise 5x5 on the tensor cores: bit 0 stride 1, bit 1 stride 2 (PIFPAF_DW_TC)
     int dw_tc_pwid = 12, dw_tc_bo = 0;   // descriptor experiments (PIFPAF_DW_TC_PWID = 12 | 16, PIFPAF_DW_TC_BO = 0 | 1)
@@ -1898,6 +1951,17 @@ void plan_gemm_smem(GemmArgs& g, size_t* smem, bool src_tma) {
     }
     g.stages = choose_stages(g.block_n, g.n_blocks, g.num_k_blocks, src_tma);
     *smem = gemm_smem_bytes(g.block_n, g.n_blocks, g.stages, src_tma);
+}
+
+// multicast pairs (GemmArgs::mc): weights-resident GEMMs whose N takes two n blocks read every A tile twice, once per
+// n block, and the second read is what bounds them (profiles/r2_history.md, session l: 43 us per pass over A)
+int plan_gemm_mc(pifpaf_net* net, Op& op, const Tensor& tin) {
+    GemmArgs& g = op.g;
+    g.mc = 0;
+    if (!net->gemm_mc || !g.b_resident || g.n_blocks != 2 || g.src_tma || g.conv_k != 0) return PIFPAF_OK;
+    if (g.mode != MODE_PLAIN && g.mode != MODE_SCATTER) return PIFPAF_OK;
+    g.mc = 1;
+    return make_tmap(&op.tmap_src, tin.data, (uint64_t)net->max_batch * tin.h * tin.w, (uint64_t)tin.c, (uint64_t)tin.c, BM / 2);
 }
 
 // common GEMM emit: weights [n_out][k_cols] f32 host -> bf16 [n_pad][k_pad8] device, bias padded
@@ -1999,6 +2063,7 @@ int pifpaf_net_create(pifpaf_net_t** out, int32_t device, int32_t max_batch) {
     if (const char* e = std::getenv("PIFPAF_DW_CBF")) net->dw_cbf = std::atoi(e) != 0;
     if (const char* e = std::getenv("PIFPAF_PDL")) net->pdl = std::atoi(e) != 0;
     if (const char* e = std::getenv("PIFPAF_GEMM_RES_STAGES")) net->gemm_res_stages = std::atoi(e);
+    if (const char* e = std::getenv("PIFPAF_GEMM_MC")) net->gemm_mc = std::atoi(e);
     if (const char* e = std::getenv("PIFPAF_DW_TC")) net->dw_tc = std::atoi(e);
     if (const char* e = std::getenv("PIFPAF_DW_TC_PWID")) net->dw_tc_pwid = std::atoi(e) == 16 ? 16 : 12;
     if (const char* e = std::getenv("PIFPAF_DW_TC_BO")) net->dw_tc_bo = std::atoi(e) != 0;
@@ -2113,6 +2178,7 @@ int pifpaf_net_conv1x1(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off,
         if (rc != PIFPAF_OK) return rc;
     }
     plan_gemm_smem(g, &op.smem, g.src_tma != 0);
+    rc = plan_gemm_mc(net, op, tin); if (rc != PIFPAF_OK) return rc;
     net->ops.push_back(op);
     return PIFPAF_OK;
 }
@@ -2154,6 +2220,7 @@ int pifpaf_net_conv1x1_scatter(pifpaf_net_t* net, int32_t in_tensor, int32_t in_
     g.dest = d_groups;
     op.bytes_per_image += (double)op.rows_per_image * op.n_real * 2.0;
     plan_gemm_smem(g, &op.smem, false);
+    rc = plan_gemm_mc(net, op, tin); if (rc != PIFPAF_OK) return rc;
     net->ops.push_back(op);
     return PIFPAF_OK;
 }
@@ -2190,6 +2257,7 @@ int pifpaf_net_conv(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off, in
             g.res = tr.data; g.ld_res = tr.c; g.res_col_off = residual_col_off;
         }
         plan_gemm_smem(g, &op.smem, false);
+        rc = plan_gemm_mc(net, op, tin); if (rc != PIFPAF_OK) return rc;
         net->ops.push_back(op);
         return PIFPAF_OK;
     }
@@ -2577,8 +2645,9 @@ static int net_forward_impl(pifpaf_net_t* net, const float* images_dev, int32_t 
                 const int tiles = g.m_blocks * g.n_blocks;
                 int grid = std::min(tiles, n_sm);
                 if (g.b_resident) grid = std::max(1, std::min(n_sm / g.n_blocks, g.m_blocks)) * g.n_blocks;
-                PIFPAF_CUDA_TRY(launch_k(pdl, k_gemm_tc, dim3(grid), dim3(GEMM_THREADS), op.smem, st, op.tmap_a, op.tmap_b,
-                                         g.src_tma ? op.tmap_src : op.tmap_a, g));
+                // multicast pairs need at least one whole cluster and whole clusters only (grid is a multiple of n_blocks == 2)
+                PIFPAF_CUDA_TRY(launch_kc(pdl, g.mc ? 2 : 1, k_gemm_tc, dim3(grid), dim3(GEMM_THREADS), op.smem, st, op.tmap_a,
+                                          op.tmap_b, (g.src_tma || g.mc) ? op.tmap_src : op.tmap_a, g));
             }
             PIFPAF_LAUNCH_CHECK();
         }
