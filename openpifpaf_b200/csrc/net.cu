@@ -224,6 +224,9 @@ struct GemmArgs {
     const __nv_bfloat16* src0; int ld0; int src0_col_off; int half; int gap;
     int src_tma;                 // pass-through tile arrives by TMA in shared memory (else read from global)
     int b_resident;              // all K blocks of this CTA's weight tile stay in shared memory (loaded once)
+    int pair, pair_stages;       // k_gemm_tc2 (CTA pairs, cta_group::2): on / ring depth per CTA
+    int debug;                   // timing experiments only (PIFPAF_GEMM_DEBUG; results are wrong): 1 = no epilogue stores,
+                                 // 2 = no MMAs issued, 4 = epilogue does not read TMEM
     int mc;                      // weights-resident, two n blocks: the two CTAs of an M tile form a cluster and share A --
                                  // each loads one half (64 rows) of every A stage and multicasts it to both (tmap_src = the
                                  // 64-row A map); a stage is free when BOTH have consumed it
@@ -349,6 +352,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, int m, int n0,
             if (g.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
             w[j >> 1] = pack_bf16(a0, a1);
         }
+        if (g.debug & 1) { if (w[0] == 0x12345u && w[5] == 0x54321u) g.dest[0].base[0] = __float2bfloat16(0.f); return; }
         if (n0 < g.N) {
             const DestGroup d = dest[n0 >> 4];
             st_global_256(d.base + (size_t)m * d.ld, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
@@ -377,6 +381,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, int m, int n0,
             if (g.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
             w[j >> 1] = pack_bf16(a0, a1);
         }
+        if (g.debug & 1) { if (w[0] == 0x12345u && w[5] == 0x54321u) g.out[0] = __float2bfloat16(0.f); return; }
         // 16 bf16 = 32 bytes, 32-byte aligned (ldo % 16 == 0, out_col_off % 16 == 0, n0 % 16 == 0)
         uint4* dst = reinterpret_cast<uint4*>(g.out + (size_t)m * g.ldo + g.out_col_off + n0);
         const int n_pad8 = (g.N + 7) & ~7;
@@ -559,7 +564,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
                     for (int k = 0; k < BK / UMMA_K; k++) {
                         const uint64_t adesc = make_smem_desc(sa + k * UMMA_K * 2);
                         const uint64_t bdesc = make_smem_desc(sb + k * UMMA_K * 2);
-                        umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (!(g.debug & 2)) umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     // frees the smem slot when the MMAs retire (multicast mode: in both CTAs, each refills half of it)
                     if (g.mc) umma_commit_mc(&empty_bar[stage], (uint16_t)3); else umma_commit(&empty_bar[stage]);
@@ -597,6 +602,18 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
                 if (n0 < ((g.N + 7) & ~7))
                     epilogue_chunk(g, m, n0, accf, bias_s + n0, g.src_tma ? src_tile_row + c : nullptr, dest_s);
             };
+            if (g.debug & 4) {                       // timing experiment: release the accumulator without reading it
+                for (int ci = c_begin; ci < c_end; ci++) {
+#pragma unroll
+                    for (int j = 0; j < CHUNK; j++) va[j] = (uint32_t)(ci + j + m);
+                    process(ci, va);
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                continue;
+            }
             if (c_begin < c_end) tmem_ld16_async(t_row + (uint32_t)(c_begin * CHUNK), va);
             for (int ci = c_begin; ci < c_end; ci += 2) {
                 tmem_ld_wait(va);
@@ -621,6 +638,212 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
     if (warp == 1) {
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------ tcgen05 GEMM, CTA pairs (cta_group::2)
+// Measured (profiles/r2_history.md, sessions l-n): the weights-resident GEMMs of stage 3 are bound by the bytes of A
+// in flight -- the resident weight tile (135-160 KB) leaves 4-5 stages of 16 KB, a load takes 1.7 us under load, and a
+// stage is only free once its MMAs have retired, so loads, MMAs and stores ADD (0.091 + 0.03 + 0.03 ms) instead of
+// overlapping; the streaming GEMMs of stage 4 / conv5 run into the L2 -> SM cap (12 TB/s) re-reading the weights.
+// Both get relief from the two-SM MMA: the two CTAs of a cluster compute ONE 256 x block_n tile; each CTA stages its
+// own 128 rows of A and only HALF of the weight tile (rows [rank * block_n / 2, +block_n / 2) of the n block), the
+// leader issues tcgen05.mma.cta_group::2 (M = 256) and each CTA's TMEM receives the accumulator rows of its own A
+// half.  Per SM: half the weight bytes in shared memory (twice the A stages) and half the weight traffic from L2.
+//   full[stage]    (leader only)  both CTAs' TMA loads complete bytes there (cta_group::2 loads with the peer bit
+//                                 of the barrier address cleared); the leader's producer arms it with the pair's total
+//   empty[stage]   (each CTA)     tcgen05.commit.cta_group::2 ... multicast to both CTAs when the MMAs have read it
+//   tmem_full[a]   (each CTA)     the same commit, after the last K block of a tile
+//   tmem_empty[a]  (leader only)  the 2 x 16 epilogue warps of the pair arrive there (remote arrive from the peer)
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;      // shared::cluster address of the same offset in the even CTA of the pair
+constexpr int PAIR_MAX_STAGES = 12;
+
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+k_gemm_tc2(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_bh, GemmArgs g) {
+    extern __shared__ __align__(1024) unsigned char smem_raw2[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~uintptr_t(1023));
+    const int half_n = g.block_n / 2;
+    const int a_bytes = BM * BK * 2;
+    const int bh_bytes = half_n * BK * 2;                       // this CTA's half of one K block of the weight tile
+    const int stage_bytes = a_bytes + (g.b_resident ? 0 : bh_bytes);
+    unsigned char* b_res = smem + (size_t)g.pair_stages * stage_bytes;
+    const size_t b_res_bytes = g.b_resident ? (size_t)g.num_k_blocks * bh_bytes : 0;
+    float* bias_s = reinterpret_cast<float*>(b_res + ((b_res_bytes + 1023) & ~(size_t)1023));
+    DestGroup* dest_s = reinterpret_cast<DestGroup*>(bias_s + g.n_blocks * g.block_n);
+    unsigned char* tail = reinterpret_cast<unsigned char*>(dest_s + g.n_blocks * g.block_n / CHUNK);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);            // [stages]   used in the leader
+    uint64_t* empty_bar = full_bar + g.pair_stages;                     // [stages]
+    uint64_t* tmem_full = empty_bar + g.pair_stages;                    // [2]
+    uint64_t* tmem_empty = tmem_full + 2;                               // [2]        used in the leader
+    uint64_t* b_full = tmem_empty + 2;                                  // [1]        used in the leader
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t tmem_cols = (2 * g.block_n <= 32) ? 32 : (2 * g.block_n <= 64) ? 64 : (2 * g.block_n <= 128) ? 128
+                               : (2 * g.block_n <= 256) ? 256 : 512;
+
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_bh); }
+    for (int i = threadIdx.x; i < g.n_blocks * g.block_n; i += GEMM_THREADS) bias_s[i] = g.bias[i];
+    if (g.mode == MODE_SCATTER)
+        for (int i = threadIdx.x; i < g.n_blocks * g.block_n / CHUNK; i += GEMM_THREADS) dest_s[i] = g.dest[i];
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < g.pair_stages; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+            for (int a = 0; a < 2; a++) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 2 * EPI_WARPS); }
+            mbar_init(b_full, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        // the same warp of both CTAs: one allocation, the same columns in both tensor memories
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();                 // the peer's barriers exist before any load / commit / arrive reaches them
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    pdl_launch_dependents();
+    pdl_wait();
+
+    // tile schedule over PAIRS (cluster index): weights-resident mode pins one n block per pair and walks the
+    // 256-row tiles; streaming mode walks (m256, n_blk) tiles round-robin
+    const int pair = (int)(blockIdx.x >> 1), n_pairs = (int)(gridDim.x >> 1);
+    const int m2_blocks = (g.M + 2 * BM - 1) / (2 * BM);
+    const int num_tiles = g.b_resident ? 0 : m2_blocks * g.n_blocks;
+    const int my_n = g.b_resident ? pair % g.n_blocks : 0;
+    const int m_first = g.b_resident ? pair / g.n_blocks : 0;
+    const int m_step = g.b_resident ? n_pairs / g.n_blocks : 0;
+#define PIFPAF_PAIR_LOOP(m_blk, n_blk)                                                                             \
+    for (int it__ = g.b_resident ? m_first : pair, m_blk = 0, n_blk = 0;                                            \
+         (g.b_resident ? it__ < m2_blocks : it__ < num_tiles) &&                                                    \
+         ((m_blk = g.b_resident ? it__ : it__ / g.n_blocks), (n_blk = g.b_resident ? my_n : it__ % g.n_blocks), true); \
+         it__ += g.b_resident ? m_step : n_pairs)
+
+    if (warp == 0) {
+        // ===== TMA producer (one lane in each CTA) =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            if (g.b_resident) {
+                if (rank == 0) mbar_expect_tx(b_full, (uint32_t)(2 * b_res_bytes));
+                const uint32_t lb = smem_u32(b_full) & PEER_BIT_MASK;
+                for (int kb = 0; kb < g.num_k_blocks; kb++)
+                    tma_load_2d_pair(b_res + (size_t)kb * bh_bytes, &tmap_bh, lb, kb * BK, my_n * g.block_n + (int)rank * half_n);
+            }
+            PIFPAF_PAIR_LOOP(m_blk, n_blk) {
+                for (int kb = 0; kb < g.num_k_blocks; kb++) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char* sa = smem + (size_t)stage * stage_bytes;
+                    if (rank == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(2 * stage_bytes));
+                    const uint32_t lb = smem_u32(&full_bar[stage]) & PEER_BIT_MASK;
+                    tma_load_2d_pair(sa, &tmap_a, lb, g.a_col0 + kb * BK, m_blk * 2 * BM + (int)rank * BM);
+                    if (!g.b_resident)
+                        tma_load_2d_pair(sa + a_bytes, &tmap_bh, lb, kb * BK, n_blk * g.block_n + (int)rank * half_n);
+                    if (++stage == g.pair_stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one lane of the LEADER CTA =====
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = make_instr_desc(2 * BM, g.block_n);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            if (g.b_resident) mbar_wait(b_full, 0);
+            PIFPAF_PAIR_LOOP(m_blk, n_blk) {
+                (void)m_blk; (void)n_blk;
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * g.block_n);
+                for (int kb = 0; kb < g.num_k_blocks; kb++) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint32_t sb = g.b_resident ? smem_u32(b_res + (size_t)kb * bh_bytes) : sa + a_bytes;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; k++) {
+                        const uint64_t adesc = make_smem_desc(sa + k * UMMA_K * 2);
+                        const uint64_t bdesc = make_smem_desc(sb + k * UMMA_K * 2);
+                        umma_bf16_pair(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit_pair(&empty_bar[stage]);
+                    if (++stage == g.pair_stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_pair(&tmem_full[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue warps of both CTAs: this CTA's 128 rows of the tile =====
+        const int q = warp & 3;
+        const int n_chunks = g.block_n / CHUNK;
+        const int part = (warp - 2) >> 2, parts = EPI_WARPS / 4;
+        const int c_begin = n_chunks * part / parts;
+        const int c_end = n_chunks * (part + 1) / parts;
+        int acc = 0; uint32_t acc_phase = 0;
+        PIFPAF_PAIR_LOOP(m_blk, n_blk) {
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tcgen05_fence_after();
+            const int mrow = m_blk * 2 * BM + (int)rank * BM + q * 32 + lane;
+            const int m = mrow < g.M ? mrow : -1;
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (uint32_t)(acc * g.block_n);
+            uint32_t va[CHUNK], vb[CHUNK];
+            auto process = [&](int ci, const uint32_t* v) {
+                const int c = ci * CHUNK;
+                float accf[CHUNK];
+#pragma unroll
+                for (int j = 0; j < CHUNK; j++) accf[j] = __uint_as_float(v[j]);
+                const int n0 = n_blk * g.block_n + c;
+                if (n0 < ((g.N + 7) & ~7)) epilogue_chunk(g, m, n0, accf, bias_s + n0, nullptr, dest_s);
+            };
+            if (c_begin < c_end) tmem_ld16_async(t_row + (uint32_t)(c_begin * CHUNK), va);
+            for (int ci = c_begin; ci < c_end; ci += 2) {
+                tmem_ld_wait(va);
+                if (ci + 1 < c_end) tmem_ld16_async(t_row + (uint32_t)((ci + 1) * CHUNK), vb);
+                process(ci, va);
+                if (ci + 1 < c_end) {
+                    tmem_ld_wait(vb);
+                    if (ci + 2 < c_end) tmem_ld16_async(t_row + (uint32_t)((ci + 2) * CHUNK), va);
+                    process(ci + 1, vb);
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();                 // nobody leaves (or frees tensor memory) while the pair is still at work
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
     }
 }
 
@@ -1829,6 +2052,7 @@ struct Op {
     // gemm
     GemmArgs g{};
     CUtensorMap tmap_a{}, tmap_b{}, tmap_src{};
+    CUtensorMap tmap_bh{}; int pair_resident = 0, pair_stages = 0; size_t pair_smem = 0; bool pair = false;   // k_gemm_tc2
     int a_tensor = -1; int rows_per_image = 0; int tiles_per_image = 0;
     size_t smem = 0;
     // dw
@@ -1863,6 +2087,8 @@ struct pifpaf_net {
     bool setup_synced = false;           // build-time memsets / uploads (legacy stream) ordered before the first forward
     int sm_limit = 0;                    // > 0: persistent grids use at most this many SMs
     bool pdl = true;                     // programmatic dependent launch between the ops of a forward (PIFPAF_PDL=0: off)
+    int gemm_pair = 11;                  // k_gemm_tc2 (CTA pairs, cta_group::2): bit mask of the GEMM classes that use it (PIFPAF_GEMM_PAIR)
+    int gemm_debug = 0;                  // GemmArgs::debug for every tcgen05 GEMM launch (PIFPAF_GEMM_DEBUG; timing experiments, wrong results)
     int gemm_mc = 0;                     // weights-resident GEMMs with two n blocks: cluster of two CTAs, A by TMA multicast (PIFPAF_GEMM_MC)
     int gemm_res_stages = 0;             // weights-resident GEMMs: split N further until this many A stages fit (PIFPAF_GEMM_RES_STAGES)
     int dw_tc = 0;                       // depthwise 5x5 on the tensor cores: bit 0 stride 1, bit 1 stride 2 (PIFPAF_DW_TC)
@@ -1962,6 +2188,33 @@ int plan_gemm_mc(pifpaf_net* net, Op& op, const Tensor& tin) {
     if (g.mode != MODE_PLAIN && g.mode != MODE_SCATTER) return PIFPAF_OK;
     g.mc = 1;
     return make_tmap(&op.tmap_src, tin.data, (uint64_t)net->max_batch * tin.h * tin.w, (uint64_t)tin.c, (uint64_t)tin.c, BM / 2);
+}
+
+// CTA pairs (k_gemm_tc2): each CTA stages half of the weight tile.  PIFPAF_GEMM_PAIR is a mask of GEMM classes:
+//   1  weights-resident, two or more n blocks (stage 3: 0.150 -> 0.130 ms per launch, session o)
+//   2  streaming (stage 4, conv5, the 1x1 in front of a stride-2 depthwise: 0.109 -> 0.091, 0.377 -> 0.330)
+//   4  weights-resident, one n block, several K blocks (stage 2: DRAM-bound already, 0.208 -> 0.235: off)
+//   8  weights-resident, one n block, one K block (the K = 32 GEMM at 321 x 321: 0.602 -> 0.544)
+//  16  the heads GEMM
+int plan_gemm_pair(pifpaf_net* net, Op& op) {
+    GemmArgs& g = op.g;
+    op.pair = false;
+    if (!net->gemm_pair || g.src_tma || g.conv_k != 0 || g.mc) return PIFPAF_OK;
+    if (g.mode != MODE_PLAIN && g.mode != MODE_SCATTER && g.mode != MODE_HEADS) return PIFPAF_OK;
+    const int want = g.mode == MODE_HEADS ? 16 : g.b_resident ? (g.n_blocks >= 2 ? 1 : (g.num_k_blocks <= 1 ? 8 : 4)) : 2;
+    if (!(net->gemm_pair & want)) return PIFPAF_OK;
+    const size_t n_pad = (size_t)g.block_n * g.n_blocks;
+    const size_t bh = (size_t)(g.block_n / 2) * BK * 2;
+    const size_t fixed = 1024 + n_pad * 4 + n_pad / 16 * sizeof(DestGroup) + 64;
+    auto total = [&](int stages, bool res) {
+        const size_t b_res = res ? (((size_t)g.num_k_blocks * bh + 1023) & ~(size_t)1023) : 0;
+        return fixed + (size_t)stages * (BM * BK * 2 + (res ? 0 : bh)) + b_res + (2 * (size_t)stages + 5) * 8;
+    };
+    const bool res = g.mode != MODE_HEADS && total(4, true) <= GEMM_SMEM_BUDGET;
+    int stages = PAIR_MAX_STAGES;
+    while (stages > 2 && total(stages, res) > GEMM_SMEM_BUDGET) stages--;
+    op.pair = true; op.pair_resident = res ? 1 : 0; op.pair_stages = stages; op.pair_smem = total(stages, res);
+    return make_tmap(&op.tmap_bh, g.wgt, (uint64_t)n_pad, (uint64_t)g.ldw, (uint64_t)g.ldw, (uint32_t)(g.block_n / 2));
 }
 
 // common GEMM emit: weights [n_out][k_cols] f32 host -> bf16 [n_pad][k_pad8] device, bias padded
@@ -2064,6 +2317,9 @@ int pifpaf_net_create(pifpaf_net_t** out, int32_t device, int32_t max_batch) {
     if (const char* e = std::getenv("PIFPAF_PDL")) net->pdl = std::atoi(e) != 0;
     if (const char* e = std::getenv("PIFPAF_GEMM_RES_STAGES")) net->gemm_res_stages = std::atoi(e);
     if (const char* e = std::getenv("PIFPAF_GEMM_MC")) net->gemm_mc = std::atoi(e);
+    if (const char* e = std::getenv("PIFPAF_GEMM_DEBUG")) net->gemm_debug = std::atoi(e);
+    if (const char* e = std::getenv("PIFPAF_GEMM_PAIR")) net->gemm_pair = std::atoi(e);
+    PIFPAF_CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     if (const char* e = std::getenv("PIFPAF_DW_TC")) net->dw_tc = std::atoi(e);
     if (const char* e = std::getenv("PIFPAF_DW_TC_PWID")) net->dw_tc_pwid = std::atoi(e) == 16 ? 16 : 12;
     if (const char* e = std::getenv("PIFPAF_DW_TC_BO")) net->dw_tc_bo = std::atoi(e) != 0;
@@ -2179,6 +2435,7 @@ int pifpaf_net_conv1x1(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off,
     }
     plan_gemm_smem(g, &op.smem, g.src_tma != 0);
     rc = plan_gemm_mc(net, op, tin); if (rc != PIFPAF_OK) return rc;
+    rc = plan_gemm_pair(net, op); if (rc != PIFPAF_OK) return rc;
     net->ops.push_back(op);
     return PIFPAF_OK;
 }
@@ -2221,6 +2478,7 @@ int pifpaf_net_conv1x1_scatter(pifpaf_net_t* net, int32_t in_tensor, int32_t in_
     op.bytes_per_image += (double)op.rows_per_image * op.n_real * 2.0;
     plan_gemm_smem(g, &op.smem, false);
     rc = plan_gemm_mc(net, op, tin); if (rc != PIFPAF_OK) return rc;
+    rc = plan_gemm_pair(net, op); if (rc != PIFPAF_OK) return rc;
     net->ops.push_back(op);
     return PIFPAF_OK;
 }
@@ -2258,6 +2516,7 @@ int pifpaf_net_conv(pifpaf_net_t* net, int32_t in_tensor, int32_t in_col_off, in
         }
         plan_gemm_smem(g, &op.smem, false);
         rc = plan_gemm_mc(net, op, tin); if (rc != PIFPAF_OK) return rc;
+        rc = plan_gemm_pair(net, op); if (rc != PIFPAF_OK) return rc;
         net->ops.push_back(op);
         return PIFPAF_OK;
     }
@@ -2516,6 +2775,7 @@ int pifpaf_net_heads_upsampled(pifpaf_net_t* net, int32_t in_tensor, int32_t k_c
     g.hw = tin.h * tin.w; g.w = tin.w;
     g.up = up; g.up_low = low; g.out_h = out_h; g.out_w = out_w;
     net->n_heads = n_heads; net->head_h = out_h; net->head_w = out_w;
+    rc = plan_gemm_pair(net, op); if (rc != PIFPAF_OK) return rc;
     net->ops.push_back(op);
     return PIFPAF_OK;
 }
@@ -2633,6 +2893,7 @@ static int net_forward_impl(pifpaf_net_t* net, const float* images_dev, int32_t 
             PIFPAF_LAUNCH_CHECK();
         } else {
             GemmArgs g = op.g;
+            g.debug = net->gemm_debug;
             if (g.mode == MODE_HEADS)
                 for (int i = 0; i < net->n_heads; i++) g.head_base[i] = net->head_out[net->head_cur][i];
             g.M = batch * op.rows_per_image;
@@ -2641,6 +2902,14 @@ static int net_forward_impl(pifpaf_net_t* net, const float* images_dev, int32_t 
                 const long long jobs = (long long)g.m_blocks * 4 * (g.n_blocks * g.block_n / CHUNK);
                 const int grid = (int)std::min<long long>((jobs + 3) / 4, (long long)n_sm * 16);
                 k_gemm_simt<<<grid, 128, 0, st>>>(g);
+            } else if (op.pair) {
+                g.pair = 1; g.pair_stages = op.pair_stages; g.b_resident = op.pair_resident;
+                const int m2 = (g.M + 2 * BM - 1) / (2 * BM);
+                const int max_pairs = std::max(1, n_sm / 2);
+                int pairs = std::min(max_pairs, m2 * g.n_blocks);
+                if (g.b_resident) pairs = std::max(1, std::min(max_pairs / g.n_blocks, m2)) * g.n_blocks;
+                PIFPAF_CUDA_TRY(launch_kc(pdl, 2, k_gemm_tc2, dim3(2 * pairs), dim3(GEMM_THREADS), op.pair_smem, st, op.tmap_a,
+                                          op.tmap_bh, g));
             } else {
                 const int tiles = g.m_blocks * g.n_blocks;
                 int grid = std::min(tiles, n_sm);
