@@ -135,18 +135,24 @@ def max_over_ranks(value, world, device):
     return value
 
 
-def measured_traffic(kernel, launches_per_step):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture of this same command (profiles/), or None.
-    Only accepted if the capture holds a whole number of steps of the kernel's launches."""
+def measured_traffic(kernels, launches_per_step):
+    """DRAM bytes per launch of the GEMM kernels (`kernels`: the names that together make up the launches of one step)
+    from the committed ncu capture of this same command (profiles/), or None.  Only accepted if the capture holds a
+    whole number of steps of their launches -- a capture of an older build (other kernel mix) is not quoted."""
     for name in ('r2_dram_traffic_bench_step.json', 'r1_dram_traffic_bench_step.json'):
         path = os.path.join(ROOT, 'profiles', name)
         try:
-            k = json.load(open(path))['kernels'][kernel]
+            table = json.load(open(path))['kernels']
         except (OSError, KeyError, ValueError):
             continue
-        if k['launches'] % launches_per_step != 0:
+        found = [table[k] for k in kernels if k in table]
+        if name.startswith('r2') and len(found) != len(kernels):
             continue
-        return round(k['dram_bytes_per_launch']), f'profiles/{name} (ncu, one bs64 step)'
+        launches = sum(k['launches'] for k in found)
+        if not found or launches % launches_per_step != 0 or (name.startswith('r1') and len(kernels) > 1):
+            continue
+        total = sum(k['dram_read_bytes'] + k['dram_write_bytes'] for k in found)
+        return round(total / launches), f'profiles/{name} (ncu, one bs64 step)'
     return None, 'no ncu capture of this build committed'
 
 
@@ -400,9 +406,10 @@ def run_b200(args):
         sel = kind == 1
         n_gemm = int(sel.sum())
         gemm_ms = float(ms_op[sel].sum())
-        traffic, traffic_src = measured_traffic('k_gemm_tc', n_gemm)
+        traffic, traffic_src = measured_traffic(('k_gemm_tc', 'k_gemm_tc2'), n_gemm)
         roofline = {
-            'kernel': 'k_gemm_tc (tcgen05 1x1-conv GEMMs, %d launches/step)' % n_gemm,
+            'kernel': 'k_gemm_tc + k_gemm_tc2 (tcgen05 1x1-conv GEMMs: one CTA M=128 / CTA pairs cta_group::2 M=256; '
+                      '%d launches/step)' % n_gemm,
             'bound': 'hbm', 'achieved': prof['gemm_gbs'], 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
             'frac': round(prof['gemm_gbs'] / pk['hbm_gbs'], 4), 'traffic': traffic,
             'traffic_unit': 'bytes/launch (dram read+write)', 'traffic_source': traffic_src,

@@ -2087,7 +2087,7 @@ struct pifpaf_net {
     bool setup_synced = false;           // build-time memsets / uploads (legacy stream) ordered before the first forward
     int sm_limit = 0;                    // > 0: persistent grids use at most this many SMs
     bool pdl = true;                     // programmatic dependent launch between the ops of a forward (PIFPAF_PDL=0: off)
-    int gemm_pair = 11;                  // k_gemm_tc2 (CTA pairs, cta_group::2): bit mask of the GEMM classes that use it (PIFPAF_GEMM_PAIR)
+    int gemm_pair = 27;                  // k_gemm_tc2 (CTA pairs, cta_group::2): bit mask of the GEMM classes that use it (PIFPAF_GEMM_PAIR)
     int gemm_debug = 0;                  // GemmArgs::debug for every tcgen05 GEMM launch (PIFPAF_GEMM_DEBUG; timing experiments, wrong results)
     int gemm_mc = 0;                     // weights-resident GEMMs with two n blocks: cluster of two CTAs, A by TMA multicast (PIFPAF_GEMM_MC)
     int gemm_res_stages = 0;             // weights-resident GEMMs: split N further until this many A stages fit (PIFPAF_GEMM_RES_STAGES)

@@ -92,6 +92,36 @@ def test_fused_depthwise_gemm_equals_two_kernels_bitwise():
         fused.close(); plain.close()
 
 
+def test_pair_gemm_equals_single_cta_gemm_bitwise(monkeypatch):
+    """k_gemm_tc2 (CTA pairs, tcgen05.mma.cta_group::2, M = 256, half of the weight tile per CTA; the default for the
+    weights-resident GEMMs with two n blocks, the streaming GEMMs and the heads) accumulates every output element over
+    the same K blocks in the same order as k_gemm_tc (one CTA, M = 128): every tensor and every field is identical bit
+    for bit -- at a size with a partial last 256-row tile in every stage, batch > 1, for the k16 and k30 widths, and
+    with ALL GEMM classes forced onto the pair kernel as well."""
+    for base in ('shufflenetv2k16', 'shufflenetv2k30'):
+        plan = network.random_plan(base, seed=9)
+        B, H, W = 3, 273, 369
+        x = torch.randn(B, 3, H, W, generator=torch.Generator().manual_seed(5)).cuda()
+        outs = []
+        for mask in ('0', None, '31'):
+            if mask is None:
+                monkeypatch.delenv('PIFPAF_GEMM_PAIR', raising=False)
+            else:
+                monkeypatch.setenv('PIFPAF_GEMM_PAIR', mask)
+            net = network.CompiledNet(plan, H, W, B)
+            heads = [t.clone() for t in net.forward(x)]
+            torch.cuda.synchronize()
+            taps = [net.tap(t, B)[..., lay.cols()] for (t, lay) in net.info['block_outputs']]
+            outs.append((heads, taps))
+            net.close()
+        for heads, taps in outs[1:]:
+            for a, b in zip(heads, outs[0][0]):
+                assert torch.isfinite(a).all()
+                assert torch.equal(a, b), float((a - b).abs().max())
+            for a, b in zip(taps, outs[0][1]):
+                np.testing.assert_array_equal(a, b)
+
+
 def test_linearity_property_of_conv_path():
     """size-independent property: with ReLU-free positive scaling, fields scale consistently --
     forward(x) is deterministic and batch-position independent (image b alone == image b in a batch)."""
