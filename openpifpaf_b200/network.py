@@ -406,6 +406,18 @@ def _branch_pitch(bf):
     return (bf + mult - 1) // mult * mult
 
 
+def _dw_in_pitch(bf):
+    """Physical channel count of the tensor BETWEEN the first 1x1 of a branch and its depthwise conv.  DRAM serves the
+    depthwise kernels' TMA reads (one 128-byte 64-channel block per pixel) in aligned 128-byte lines: with 352- / 704-byte
+    pixels (176 / 352 channels) a block straddles two lines and the launch reads 1.96x / 1.55x the tensor
+    (profiles/r2_history.md, "analysis"); tensors whose pixels are a multiple of 128 bytes read 1.00x.  Only this tensor
+    is padded (to 64 channels): its producer writes the real channels with the same stores as before, and the tensor
+    behind the depthwise conv -- the A operand of a GEMM, which would read the padding -- keeps the 16-channel pitch.
+    PIFPAF_DWIN_PAD selects the multiple (16 = the old layout)."""
+    mult = int(os.environ.get('PIFPAF_DWIN_PAD', '64'))
+    return max(_branch_pitch(bf), (bf + mult - 1) // mult * mult)
+
+
 def default_layout():
     """'bins' (no pass-through copies, see _plan_stage_bins) or 'shuffle' (every block writes the interleaved
     2*bf-channel tensor through the fused cat+shuffle epilogue); PIFPAF_LAYOUT overrides."""
@@ -533,7 +545,10 @@ def build_ops(plan, in_h, in_w, layout=None, fuse_dw=None):
         t_a = tensor(ho, wo, lay.width)
         dwconv(cur, cols, lay.width, e0['b1_dw'], kk, st, pd, t_a)
         conv1x1_scatter(t_a, cols, lay.width, e0['b1_pw'], True, producers[0]['order'], pieces_of(0))
-        t_c = tensor(h, w, hp)
+        # the tensor in front of the STRIDE-2 depthwise conv gets 128-byte pixels (_dw_in_pitch).  (Measured, session s:
+        # letting its producer write the padding channels too -- whole rows instead of rows with a 32-byte hole -- costs
+        # that GEMM more (0.53 -> 0.69 ms at 321 x 321) than the hole does (0.53 -> 0.64).)
+        t_c = tensor(h, w, _dw_in_pitch(bf))
         conv1x1(cur, 0, cols, lay.width, e0['b2_pw1'], True, t_c)
         t_d = tensor(ho, wo, hp)
         dwconv(t_c, np.arange(bf), hp, e0['b2_dw'], kk, st, pd, t_d)
@@ -546,7 +561,7 @@ def build_ops(plan, in_h, in_w, layout=None, fuse_dw=None):
             in_cols = np.empty((bf,), dtype=np.int64)
             in_cols[wcol[wcol >= 0]] = np.nonzero(wcol >= 0)[0]
             width = tensors[t_bin[t]][2]
-            t_c = tensor(h, w, hp)
+            t_c = tensor(h, w, hp)          # stride-1 depthwise launches are issue bound: the padding buys nothing there
             conv1x1(t_bin[t], 0, in_cols, width, e['b2_pw1'], True, t_c)
             order = producers[t + 1]['order']
             if fuse_dw and e['kernel'] == 5 and e['pad'] == 2 and len(order) <= 512:

@@ -1,3 +1,4 @@
+import os
 """End-to-end batch API: images -> backbone+heads -> CifCaf decode -> annotations.
 
 Mirror of the reference's hot loop (paths relative to /root/reference/src/openpifpaf/):
@@ -49,7 +50,10 @@ class Predictor:
             net.set_head_buffers(2)
             n_sm = torch.cuda.get_device_properties(self.device).multi_processor_count
             if reserve_sms is None:
-                reserve_sms = min(net.max_batch, n_sm // 8)
+                env = os.environ.get('PIFPAF_RESERVE_SMS')
+                # measured (profiles/r2_history.md, sessions r / s): at 64 images per step the network wants every SM
+                # (4357 -> 4579 images/s from 18 -> 0 reserved), at 8-16 images the decode wants 8 of its own
+                reserve_sms = int(env) if env is not None else (8 if net.max_batch <= 16 else 4 if net.max_batch <= 32 else 0)
             net.set_sm_limit(n_sm - int(reserve_sms) if reserve_sms else 0)
         self._dev_images = None
         self.last_nn_time = 0.0
