@@ -477,6 +477,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
     // the peer's barriers must be initialised before anything of this CTA (multicast data, commit arrivals) reaches them
     if (g.mc) cluster_sync_all();
     const uint32_t mc_rank = g.mc ? cluster_ctarank() : 0;
+    // the resident weight tile does not depend on the predecessor kernel: its loads go out before the grid-dependency
+    // wait and land while the predecessor's last CTAs drain (counts at 8 images per GPU, where a launch lasts 15-40 us)
+    if (warp == 0 && lane == 0 && g.b_resident) {
+        mbar_expect_tx(b_full, (uint32_t)b_res_bytes);
+        for (int kb = 0; kb < g.num_k_blocks; kb++)
+            tma_load_2d(b_res + (size_t)kb * b_bytes, &tmap_b, b_full, kb * BK, (int)(blockIdx.x % g.n_blocks) * g.block_n);
+    }
     // (after the TMEM allocation: a dependent CTA that becomes co-resident must not take the columns first)
     pdl_launch_dependents();
     pdl_wait();
@@ -498,11 +505,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CU
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             int sacc = 0; uint32_t sacc_phase = 0;
-            if (g.b_resident) {
-                mbar_expect_tx(b_full, (uint32_t)b_res_bytes);
-                for (int kb = 0; kb < g.num_k_blocks; kb++)
-                    tma_load_2d(b_res + (size_t)kb * b_bytes, &tmap_b, b_full, kb * BK, my_n * g.block_n);
-            }
             PIFPAF_TILE_LOOP(m_blk, n_blk) {
                 int cb = 0, cy = 0, cx = 0, cimg = 0;
                 if (g.conv_k > 0) {
@@ -728,6 +730,14 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ C
     cluster_sync_all();                 // the peer's barriers exist before any load / commit / arrive reaches them
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // resident weights: loaded before the grid-dependency wait (they do not depend on the predecessor kernel)
+    if (warp == 0 && lane == 0 && g.b_resident) {
+        const int my_n0 = (int)(blockIdx.x >> 1) % g.n_blocks;
+        if (rank == 0) mbar_expect_tx(b_full, (uint32_t)(2 * b_res_bytes));
+        const uint32_t lb = smem_u32(b_full) & PEER_BIT_MASK;
+        for (int kb = 0; kb < g.num_k_blocks; kb++)
+            tma_load_2d_pair(b_res + (size_t)kb * bh_bytes, &tmap_bh, lb, kb * BK, my_n0 * g.block_n + (int)rank * half_n);
+    }
     pdl_launch_dependents();
     pdl_wait();
 
@@ -749,12 +759,6 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ C
         // ===== TMA producer (one lane in each CTA) =====
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            if (g.b_resident) {
-                if (rank == 0) mbar_expect_tx(b_full, (uint32_t)(2 * b_res_bytes));
-                const uint32_t lb = smem_u32(b_full) & PEER_BIT_MASK;
-                for (int kb = 0; kb < g.num_k_blocks; kb++)
-                    tma_load_2d_pair(b_res + (size_t)kb * bh_bytes, &tmap_bh, lb, kb * BK, my_n * g.block_n + (int)rank * half_n);
-            }
             PIFPAF_PAIR_LOOP(m_blk, n_blk) {
                 for (int kb = 0; kb < g.num_k_blocks; kb++) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);

@@ -37,6 +37,8 @@ def _build_class():
     class CifCafB200(Decoder):
         """CifCaf decoding on a B200 (same CLI knobs as the reference's CifCaf)."""
         fast_batch = True
+        #: read by TrackingPose.soft_nms (tracking_pose.py:160) when this class is its pose generator
+        occupancy_visualizer = None
         #: compiled (model, input shape) entries kept alive; each owns every activation buffer of its max batch
         compile_cache_size = 2
 
@@ -128,6 +130,11 @@ def _build_class():
                     init_t[i, :, 2] = torch.from_numpy(ann_py.data[:, 1].astype(np.float32))
                     init_t[i, :, 3] = torch.from_numpy(np.asarray(ann_py.joint_scales, dtype=np.float32))
                     ids_t[i] = getattr(ann_py, 'id_', -1)
+            # the reference's C++ decoder takes the CIF field count from the tensor, not from n_keypoints: the tracking
+            # pose has 2 x K keypoints over the K single-frame CIF fields (tracking_pose.py:47-65, 192-199)
+            n_cif = int(fields[self.cif_metas[0].head_index].shape[0])
+            if n_cif != self.native.n_cif_fields:
+                self.native = b200_decoder.CifCaf(self.native.n_keypoints, self.native.skeleton, n_cif_fields=n_cif)
             self.sync_statics()
             start = time.perf_counter()
             ann_t, ids = self.native.call_with_initial_annotations(
@@ -257,7 +264,29 @@ def _build_class():
                 out.append(ann)
             return out
 
-    return openpifpaf, CifCafB200, CifCafDenseB200, CifDetB200
+    class TrackingPoseB200(openpifpaf.decoder.TrackingPose):
+        """decoder/tracking_pose.py:18-296 (TrackingPose): the tracker's Python bookkeeping (active tracks, soft NMS over
+        tracks, track recovery, pruning) is the reference's own, inherited unchanged; what runs per frame on the hot
+        path -- the CifCaf decode of the 2 x K-keypoint "tracking pose" over [cif, cat(caf, tcaf)] seeded with the
+        previous frame's poses (``call_with_initial_annotations``, csrc/src/cifcaf.cpp:177-202; tracking_pose.py:165-218)
+        -- goes to the GPU decoder: the reference constructor takes a ``pose_generator`` and this class hands it a
+        CifCafB200 over the tracking metas."""
+
+        def __init__(self, cif_meta, caf_meta, tcaf_meta):
+            super().__init__(cif_meta, caf_meta, tcaf_meta)
+            self.pose_generator = CifCafB200([self.tracking_cif_meta], [self.tracking_caf_meta])
+            self.priority += 1.0          # outrank the reference's TrackingPose (tracking_pose.py:36-39: same base)
+
+        @classmethod
+        def cli(cls, parser):
+            """The reference's TrackingPose.cli already owns --trackingpose-* (both classes sit in DECODERS)."""
+
+        @classmethod
+        def configure(cls, args):
+            cls.track_recovery = args.trackingpose_track_recovery
+            cls.single_seed = args.trackingpose_single_seed
+
+    return openpifpaf, CifCafB200, CifCafDenseB200, CifDetB200, TrackingPoseB200
 
 
 _CLASS = None
@@ -271,12 +300,13 @@ def decoder_class():
 
 
 def register():
-    openpifpaf, cls, dense_cls, det_cls = _build_class()
+    openpifpaf, cls, dense_cls, det_cls, track_cls = _build_class()
     global _CLASS
     _CLASS = cls
     openpifpaf.DECODERS.add(cls)
     openpifpaf.DECODERS.add(dense_cls)
     openpifpaf.DECODERS.add(det_cls)
+    openpifpaf.DECODERS.add(track_cls)
 
     # Predictor calls Multi.batch (predictor.py:131); let it delegate to the GPU-resident batch path when the
     # selected decoder provides one.

@@ -103,18 +103,21 @@ def _poisson(rng, lam):
 
 
 def make_fields(workload='cocokp', h=41, w=41, n_people=None, seed=0,
-                n_distractors=0, people_lambda=4.0, skeleton=None):
+                n_distractors=0, people_lambda=4.0, skeleton=None, poses=None):
     """One image worth of fields.
 
     Returns dict(cif [F,5,h,w] f32, caf [C,8,h,w] f32, skeleton [C,2] int64 0-based,
     n_keypoints, n_planted, keypoints [n_planted,K,2] in field units).
     n_people=None draws Poisson(people_lambda)+1 (COCO-like).  skeleton: optional 1-based connection list replacing the
-    workload's own (e.g. the sparse + dense COCO connections of CifCafDense)."""
+    workload's own (e.g. the sparse + dense COCO connections of CifCafDense).  poses: optional list of
+    (keypoints [K,2] in field units, person scale) to plant instead of randomly placed ones (tracking sequences)."""
     K, _, template_fn, (smin, smax), joint_scale = WORKLOADS[workload]
     skeleton1 = np.asarray(skeleton_for(workload) if skeleton is None else skeleton, dtype=np.int64)
     C = skeleton1.shape[0]
     rng = np.random.Generator(np.random.PCG64(seed))
     template = template_fn()
+    if poses is not None:
+        n_people = len(poses)
     if n_people is None:
         n_people = _poisson(rng, people_lambda) + 1
 
@@ -135,14 +138,17 @@ def make_fields(workload='cocokp', h=41, w=41, n_people=None, seed=0,
 
     tmin, tmax = template.min(axis=0), template.max(axis=0)
     planted = []
-    for _ in range(n_people):
-        ps = smin + (smax - smin) * rng.random()
-        ext = (tmax - tmin) * ps
-        # keep the whole pose inside the field with a 1-cell margin where possible
-        ox = 1.0 + rng.random() * max(w - 3.0 - ext[0], 0.0) - tmin[0] * ps
-        oy = 1.0 + rng.random() * max(h - 3.0 - ext[1], 0.0) - tmin[1] * ps
-        kps = template * ps + np.array([ox, oy])
-        kps = kps + (rng.random(kps.shape) - 0.5) * 0.2          # per-joint jitter
+    for person in range(n_people):
+        if poses is not None:
+            kps, ps = np.asarray(poses[person][0], dtype=np.float64), float(poses[person][1])
+        else:
+            ps = smin + (smax - smin) * rng.random()
+            ext = (tmax - tmin) * ps
+            # keep the whole pose inside the field with a 1-cell margin where possible
+            ox = 1.0 + rng.random() * max(w - 3.0 - ext[0], 0.0) - tmin[0] * ps
+            oy = 1.0 + rng.random() * max(h - 3.0 - ext[1], 0.0) - tmin[1] * ps
+            kps = template * ps + np.array([ox, oy])
+            kps = kps + (rng.random(kps.shape) - 0.5) * 0.2          # per-joint jitter
         planted.append(kps)
         sc = joint_scale * ps
         for k in range(K):
@@ -213,6 +219,59 @@ def make_fields(workload='cocokp', h=41, w=41, n_people=None, seed=0,
         'n_planted': n_people,
         'keypoints': np.asarray(planted, dtype=np.float64).reshape(n_people, K, 2),
     }
+
+
+def make_tracking_sequence(h=33, w=41, n_people=4, n_frames=4, seed=0, step=0.45):
+    """Fields of a COCO-17 tracking model (TSingleImageCif, TSingleImageCaf, Tcaf heads; decoder/tracking_pose.py) for
+    `n_frames` consecutive frames of `n_people` planted people drifting by up to `step` cells per frame.
+
+    Returns a list of dict(cif [17,5,h,w], caf [19,8,h,w], tcaf [17,8,h,w], keypoints [n,17,2]); the Tcaf field of
+    joint k connects the joint in THIS frame (x1, y1) with the same joint in the PREVIOUS frame (x2, y2), headmeta.py
+    Tcaf.skeleton; frame 0 has background only."""
+    K, _, template_fn, (smin, smax), joint_scale = WORKLOADS['cocokp']
+    rng = np.random.Generator(np.random.PCG64(seed + 77))
+    first = make_fields('cocokp', h, w, n_people, seed)
+    scales = []
+    for kps in first['keypoints']:
+        ext = kps.max(axis=0) - kps.min(axis=0)
+        t = template_fn()
+        scales.append(float(ext[1] / (t[:, 1].max() - t[:, 1].min())))
+    poses = [np.asarray(k, dtype=np.float64) for k in first['keypoints']]
+    velocity = [(rng.random(2) - 0.5) * 2.0 * step for _ in poses]
+    frames, prev = [], None
+    for t in range(n_frames):
+        f = make_fields('cocokp', h, w, seed=seed * 100 + t, poses=[(p, s) for p, s in zip(poses, scales)])
+        ii, jj = np.meshgrid(np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64))
+        tcaf = np.zeros((K, 8, h, w), dtype=np.float64)
+        tcaf[:, 1] = rng.random((K, h, w)) * 0.05
+        tcaf[:, 2] = ii; tcaf[:, 3] = jj; tcaf[:, 4] = ii; tcaf[:, 5] = jj
+        tcaf[:, 6] = 1.0; tcaf[:, 7] = 1.0
+        if prev is not None:
+            for p_now, p_old, ps in zip(poses, prev, scales):
+                sc = joint_scale * ps
+                for k in range(K):
+                    xa, ya = p_now[k]
+                    xb, yb = p_old[k]
+                    for dj in (-1, 0, 1):
+                        for di in (-1, 0, 1):
+                            i, j = int(np.floor(xa)) + di, int(np.floor(ya)) + dj
+                            if i < 0 or i >= w or j < 0 or j >= h:
+                                continue
+                            conf = 0.9 - 0.02 * rng.random()
+                            if conf <= tcaf[k, 1, j, i]:
+                                continue
+                            tcaf[k, 1, j, i] = conf
+                            tcaf[k, 2, j, i] = xa + 0.002 * (i - xa)
+                            tcaf[k, 3, j, i] = ya + 0.002 * (j - ya)
+                            tcaf[k, 4, j, i] = xb + 0.002 * (i - xa)
+                            tcaf[k, 5, j, i] = yb + 0.002 * (j - ya)
+                            tcaf[k, 6, j, i] = sc
+                            tcaf[k, 7, j, i] = sc
+        frames.append({'cif': f['cif'], 'caf': f['caf'], 'tcaf': tcaf.astype(np.float32),
+                       'keypoints': np.asarray(poses).copy()})
+        prev = [p.copy() for p in poses]
+        poses = [p + v + (rng.random(p.shape) - 0.5) * 0.05 for p, v in zip(poses, velocity)]
+    return frames
 
 
 def make_batch(workload='cocokp', batch=8, h=41, w=41, n_people=None, seed=0, n_distractors=0):

@@ -210,6 +210,39 @@ SCRIPT = textwrap.dedent('''
     assert report['upsample2'] > 0
     openpifpaf.plugins.coco.CocoKp.upsample_stride = 1
     openpifpaf.decoder.configure(parser.parse_args([]))
+
+    # ---- 8. tracking: TrackingPoseB200 (the reference's tracker with the GPU decoder as its pose generator) against
+    # the reference's TrackingPose (CPU CifCaf) over a 4-frame sequence of moving planted people
+    tcif = openpifpaf.headmeta.TSingleImageCif('cif', 'posetrack2018', keypoints=COCO_KEYPOINTS, sigmas=COCO_PERSON_SIGMAS)
+    tcaf = openpifpaf.headmeta.TSingleImageCaf('caf', 'posetrack2018', keypoints=COCO_KEYPOINTS, sigmas=COCO_PERSON_SIGMAS,
+                                               skeleton=COCO_PERSON_SKELETON)
+    ttcaf = openpifpaf.headmeta.Tcaf('tcaf', 'posetrack2018', keypoints_single_frame=COCO_KEYPOINTS,
+                                     sigmas_single_frame=COCO_PERSON_SIGMAS,
+                                     pose_single_frame=openpifpaf.plugins.coco.constants.COCO_UPRIGHT_POSE)
+    for i, m in enumerate((tcif, tcaf, ttcaf)):
+        m.head_index, m.base_stride = i, 16
+    track_multi = openpifpaf.decoder.factory([tcif, tcaf, ttcaf])
+    track_top = [d for d in track_multi.decoders if d is not None][0]
+    assert type(track_top).__name__ == 'TrackingPoseB200', type(track_top).__name__
+    assert type(track_top.pose_generator).__name__ == 'CifCafB200'
+    track_ref = openpifpaf.decoder.TrackingPose(tcif, tcaf, ttcaf)
+    frames = synth.make_tracking_sequence(33, 41, n_people=4, n_frames=4, seed=5)
+    n_tracked = 0
+    for t, fr in enumerate(frames):
+        fields_t = [torch.from_numpy(fr['cif']), torch.from_numpy(fr['caf']), torch.from_numpy(fr['tcaf'])]
+        want = track_ref([f.clone() for f in fields_t])
+        got = track_top([f.clone() for f in fields_t])
+        assert len(got) == len(want), (t, len(got), len(want))
+        key = lambda a: (-a.score, a.id_)
+        for a, b in zip(sorted(got, key=key), sorted(want, key=key)):
+            assert np.abs(a.data - b.data).max() <= 1e-4, (t, float(np.abs(a.data - b.data).max()))
+        if t >= 1:
+            # identities persist: the same set of track ids relative to each tracker's first id (the id counter is global)
+            ids_g = sorted(a.id_ for a in got); ids_w = sorted(a.id_ for a in want)
+            assert [i - ids_g[0] for i in ids_g] == [i - ids_w[0] for i in ids_w], (ids_g, ids_w)
+        n_tracked += len(want)
+    assert n_tracked >= 4 * 3, n_tracked
+    report['tracking'] = n_tracked
     print('PLUGIN_GPU_OK', json.dumps(report))
 ''')
 

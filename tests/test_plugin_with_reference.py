@@ -77,6 +77,40 @@ def test_plugin_registers_and_is_selected(tmp_path):
         assert type(top).__name__ == 'CifCafDenseB200', type(top).__name__
         assert tuple(top.cifcaf.native.skeleton.shape) == (19 + len(DENSER_COCO_PERSON_CONNECTIONS), 2)
         openpifpaf.decoder.configure(parser.parse_args([]))
+        # tracking heads select the tracker whose pose generator is the GPU decoder (decoder/tracking_pose.py:102-123)
+        tcif = openpifpaf.headmeta.TSingleImageCif('cif', 'posetrack2018', keypoints=COCO_KEYPOINTS, sigmas=COCO_PERSON_SIGMAS)
+        tcaf = openpifpaf.headmeta.TSingleImageCaf('caf', 'posetrack2018', keypoints=COCO_KEYPOINTS,
+                                                   sigmas=COCO_PERSON_SIGMAS, skeleton=COCO_PERSON_SKELETON)
+        ttcaf = openpifpaf.headmeta.Tcaf('tcaf', 'posetrack2018', keypoints_single_frame=COCO_KEYPOINTS,
+                                         sigmas_single_frame=COCO_PERSON_SIGMAS,
+                                     pose_single_frame=openpifpaf.plugins.coco.constants.COCO_UPRIGHT_POSE)
+        for i, m in enumerate((tcif, tcaf, ttcaf)):
+            m.head_index, m.base_stride = i, 16
+        multi = openpifpaf.decoder.factory([tcif, tcaf, ttcaf])
+        top = [d_ for d_ in multi.decoders if d_ is not None][0]
+        assert type(top).__name__ == 'TrackingPoseB200', type(top).__name__
+        gen = top.pose_generator
+        assert type(gen).__name__ == 'CifCafB200' and gen.native.n_keypoints == 34
+        assert tuple(gen.native.skeleton.shape) == (19 + 17, 2)
+        ref_tracker = openpifpaf.decoder.TrackingPose(tcif, tcaf, ttcaf)
+        assert top.priority > ref_tracker.priority
+        # the synthetic tracking sequence of the GPU test does what it is meant to with the reference's own tracker:
+        # every planted person becomes one track that keeps its id over the frames
+        import numpy as np
+        from openpifpaf_b200 import synth
+        torch.ops.openpifpaf.set_quiet(True)
+        frames = synth.make_tracking_sequence(33, 41, n_people=4, n_frames=4, seed=5)
+        ids_by_frame = []
+        for fr in frames:
+            anns = ref_tracker([torch.from_numpy(fr['cif']), torch.from_numpy(fr['caf']), torch.from_numpy(fr['tcaf'])])
+            assert len(anns) == 4, len(anns)
+            for a in anns:
+                ok = a.data[:, 2] > 0          # (posetrack2018: the tracker zeroes the ears, tracking_pose.py:42-46)
+                assert ok.sum() >= 13, ok.sum()
+                d2 = ((fr['keypoints'][:, ok] - a.data[None, ok, :2] / 16.0) ** 2).sum(-1).mean(-1)
+                assert d2.min() < 0.05, d2.min()
+            ids_by_frame.append(sorted(a.id_ for a in anns))
+        assert all(ids == ids_by_frame[0] for ids in ids_by_frame), ids_by_frame
         print('PLUGIN_OK')
     ''')
     env = dict(os.environ, PYTHONPATH=f'{stage}:{ROOT}')
