@@ -355,6 +355,9 @@ def _plan_stage_bins(bf, n_blocks):
       bins[t]      = {'width': W (multiple of 16), 'wcol': int[W] (slot -> weight column of block t's first 1x1, -1 padding)}
       final        = {'width': W, 'logical': int[W] (slot -> channel index of the stage output, -1 padding)}"""
     T = n_blocks
+    # piece granularity in channels (16 = 32 bytes: whole sectors).  PIFPAF_BIN_PAD=32 makes every piece a whole number of
+    # 64-byte DRAM bursts (more padding columns: experiment of session v)
+    G = int(os.environ.get('PIFPAF_BIN_PAD', '16'))
 
     def route(v, p):
         for t in range(max(v, 1), T):
@@ -376,7 +379,7 @@ def _plan_stage_bins(bf, n_blocks):
             members = [n for n in range(bf) if routed[n][0] == d]
             if not members:
                 continue
-            padded = (len(members) + 15) // 16 * 16
+            padded = (len(members) + G - 1) // G * G
             pieces.append((len(order), padded, d, dest_fill[d]))
             slots[d].append((dest_fill[d], [routed[n][1] for n in members] + [-1] * (padded - len(members))))
             order += members + [-1] * (padded - len(members))
