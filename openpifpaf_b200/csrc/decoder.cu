@@ -522,16 +522,18 @@ __global__ void __launch_bounds__(NT) k_caf_scored(const float* __restrict__ caf
 }
 
 // ---------------------------------------------------------------------------
-// grow_connection_blend (src/cifcaf.cpp:32-103), one warp per call.  L is the SoA list base (component stride
-// `cap`), n its length; C0/X1/Y1 point at the scanned components (c, x_src, y_src), in shared memory when staged.
+// grow_connection_blend (src/cifcaf.cpp:32-103), one warp per call.  The list is SoA: C0/X1/Y1 point at the scanned
+// components (c, x_src, y_src), X2/Y2/S2 at the components read for the one or two winning entries (x_dst, y_dst,
+// s_dst); both groups in shared memory when staged (a read of the winners from global memory is an L2 round trip on the
+// serial path of every evaluation), n = the list's length.
 // The reference's loop is order dependent (">=" shifts 1 -> 2, ">" replaces 2).  It is reproduced literally: the
 // warp evaluates 32 entries at a time, then every lane replays the entries that passed the box filter -- in index
 // order, values broadcast by shuffle -- through the same two-register update.  Few entries pass (the filter box is
 // one joint scale wide), so the replay is short; no score cache, no reduction tree, any list length.
 struct Joint { double v, x, y, s; };
 
-__device__ Joint warp_blend(const float* __restrict__ L, int cap, int n,
-                            const float* C0, const float* X1, const float* Y1,
+__device__ Joint warp_blend(const float* C0, const float* X1, const float* Y1,
+                            const float* X2, const float* Y2, const float* S2, int n,
                             double x, double y, double xy_scale, double filter_sigmas, bool only_max, int lane) {
     Joint zero; zero.v = 0.0; zero.x = 0.0; zero.y = 0.0; zero.s = 0.0;
     xy_scale = fmax(xy_scale, 0.5);
@@ -564,15 +566,15 @@ __device__ Joint warp_blend(const float* __restrict__ L, int cap, int n,
         }
     }
     if (score_1 == 0.0f) return zero;
-    const float e1x = L[3 * (size_t)cap + i1], e1y = L[4 * (size_t)cap + i1];
-    const float e1s = fmaxf(0.0f, L[6 * (size_t)cap + i1]);
+    const float e1x = X2[i1], e1y = Y2[i1];
+    const float e1s = fmaxf(0.0f, S2[i1]);
     Joint r;
     if (only_max) { r.v = score_1; r.x = e1x; r.y = e1y; r.s = e1s; return r; }
     if ((double)score_2 < 0.01 || (double)score_2 < 0.5 * (double)score_1) {
         r.v = 0.5 * (double)score_1; r.x = e1x; r.y = e1y; r.s = e1s; return r;
     }
-    const float e2x = L[3 * (size_t)cap + i2], e2y = L[4 * (size_t)cap + i2];
-    const float e2s = fmaxf(0.0f, L[6 * (size_t)cap + i2]);
+    const float e2x = X2[i2], e2y = Y2[i2];
+    const float e2s = fmaxf(0.0f, S2[i2]);
     const double bdx = (double)(e1x - e2x), bdy = (double)(e1y - e2y);
     const float blend_d2 = (float)(bdx * bdx + bdy * bdy);
     if ((double)blend_d2 > ((double)e1s * (double)e1s) / 4.0) {
@@ -598,8 +600,9 @@ struct GrowShared {
     const int* edge_lookup; // [2C]: caf_i*2 + forward  (first-match rule of src/cifcaf.cpp:360-373)
     const int* pair_id;     // [2C]: canonical id of the (start,end) pair for in_frontier
     const float* s_cxy;     // [3][list_cap] staged (c, x_src, y_src)
+    const float* s_ext;     // [3][ext_cap] staged (x_dst, y_dst, s_dst) of the lists that end below ext_cap
     const int* s_loff;      // [2C] offset in s_cxy or -1
-    int list_cap;
+    int list_cap, ext_cap;
     const float* lists;     // image base: [C][2][7][hw]
     const int* list_counts; // image base: [C][2]
     int K, C, F, hw;
@@ -718,8 +721,12 @@ __device__ WJoint warp_connection_value(const GrowShared& g, const Worker& w, in
     const float* fC = of >= 0 ? g.s_cxy + of : Lf;
     const float* fX = of >= 0 ? g.s_cxy + g.list_cap + of : Lf + g.hw;
     const float* fY = of >= 0 ? g.s_cxy + 2 * g.list_cap + of : Lf + 2 * (size_t)g.hw;
+    const bool fe = of >= 0 && of + nf <= g.ext_cap;
+    const float* fX2 = fe ? g.s_ext + of : Lf + 3 * (size_t)g.hw;
+    const float* fY2 = fe ? g.s_ext + g.ext_cap + of : Lf + 4 * (size_t)g.hw;
+    const float* fS2 = fe ? g.s_ext + 2 * g.ext_cap + of : Lf + 6 * (size_t)g.hw;
     WJoint out; out.v = 0.0; out.x = 0.f; out.y = 0.f; out.s = 0.f; out.pad = 0;
-    const Joint nj = warp_blend(Lf, g.hw, nf, fC, fX, fY, (double)sj.x, (double)sj.y, (double)sj.s, filter_sigmas, false, lane);
+    const Joint nj = warp_blend(fC, fX, fY, fX2, fY2, fS2, nf, (double)sj.x, (double)sj.y, (double)sj.s, filter_sigmas, false, lane);
     if (nj.v == 0.0) return out;
     double v = sqrt(nj.v * sj.v);
     if (v < g.gp.keypoint_threshold || v < sj.v * g.gp.keypoint_threshold_rel) return out;
@@ -727,7 +734,11 @@ __device__ WJoint warp_connection_value(const GrowShared& g, const Worker& w, in
         const float* bC = ob >= 0 ? g.s_cxy + ob : Lb;
         const float* bX = ob >= 0 ? g.s_cxy + g.list_cap + ob : Lb + g.hw;
         const float* bY = ob >= 0 ? g.s_cxy + 2 * g.list_cap + ob : Lb + 2 * (size_t)g.hw;
-        const Joint rev = warp_blend(Lb, g.hw, nb, bC, bX, bY, nj.x, nj.y, nj.s, filter_sigmas, false, lane);
+        const bool be = ob >= 0 && ob + nb <= g.ext_cap;
+        const float* bX2 = be ? g.s_ext + ob : Lb + 3 * (size_t)g.hw;
+        const float* bY2 = be ? g.s_ext + g.ext_cap + ob : Lb + 4 * (size_t)g.hw;
+        const float* bS2 = be ? g.s_ext + 2 * g.ext_cap + ob : Lb + 6 * (size_t)g.hw;
+        const Joint rev = warp_blend(bC, bX, bY, bX2, bY2, bS2, nb, nj.x, nj.y, nj.s, filter_sigmas, false, lane);
         if (rev.v == 0.0) return out;
         if (fabs((double)sj.x - rev.x) + fabs((double)sj.y - rev.y) > (double)sj.s) return out;
     }
@@ -852,11 +863,11 @@ __device__ __forceinline__ bool occ_joint_covers(const Occ& o, const WJoint& j, 
 
 constexpr int GROW_MAX_WORKERS = 16;       // warps per grow CTA == annotations grown concurrently per image
 
-struct GrowLayout { int workers, list_cap; size_t smem; };
+struct GrowLayout { int workers, list_cap, ext_cap; size_t smem; };
 
 // shared memory plan of a grow CTA: graph tables | list offsets | staged lists | per-warp workers | control
 __host__ __device__ inline size_t grow_fixed_bytes(int K, int C) {
-    return (((size_t)(8 * C + K + 1 + 2 * C + 8) * sizeof(int)) + 15) & ~(size_t)15;
+    return (((size_t)(8 * C + K + 1 + 2 * C + 2 * C + 8) * sizeof(int)) + 15) & ~(size_t)15;
 }
 
 inline GrowLayout plan_grow(int K, int C) {
@@ -868,7 +879,11 @@ inline GrowLayout plan_grow(int K, int C) {
     if (fixed + lists + 4 * wb > budget) { l.list_cap = LIST_SMEM_ENTRIES / 2; lists /= 2; }
     long w = (long)((budget - fixed - lists) / wb);
     l.workers = (int)std::max(1L, std::min((long)GROW_MAX_WORKERS, w));
-    l.smem = fixed + lists + (size_t)l.workers * wb;
+    // what is left stages the destination components (x_dst, y_dst, s_dst) of the first ext_cap entries
+    const size_t used = fixed + lists + (size_t)l.workers * wb;
+    long ext = used < budget ? (long)((budget - used) / (3 * sizeof(float))) : 0;
+    l.ext_cap = (int)std::max(0L, std::min((long)l.list_cap, ext / 32 * 32));
+    l.smem = used + sizeof(float) * 3 * (size_t)l.ext_cap;
     return l;
 }
 
@@ -877,7 +892,7 @@ struct Graph {
 };
 
 // carve the CTA's shared memory, stage the graph tables and the scanned list components; whole CTA
-__device__ void grow_shared_init(GrowShared& g, unsigned char* smem, const Graph& gr, const Dims& d, int list_cap,
+__device__ void grow_shared_init(GrowShared& g, unsigned char* smem, const Graph& gr, const Dims& d, int list_cap, int ext_cap,
                                  const float* lists, const int* list_counts, const GrowParams& gp,
                                  unsigned char** workers_base, int** ctl) {
     const int K = d.K, C = d.C;
@@ -888,10 +903,13 @@ __device__ void grow_shared_init(GrowShared& g, unsigned char* smem, const Graph
     int* s_lookup = s_adj_edge + 2 * C;   // 2C
     int* s_pair = s_lookup + 2 * C;       // 2C
     int* s_loff = s_pair + 2 * C;         // 2C
-    int* s_ctl = s_loff + 2 * C;          // 8
+    int* s_lcnt = s_loff + 2 * C;         // 2C: list lengths (read on the serial path of every evaluation)
+    int* s_ctl = s_lcnt + 2 * C;          // 8
     unsigned char* p = smem + grow_fixed_bytes(K, C);
     float* s_cxy = reinterpret_cast<float*>(p);
     p += sizeof(float) * 3 * (size_t)list_cap;
+    float* s_ext = reinterpret_cast<float*>(p);
+    p += sizeof(float) * 3 * (size_t)ext_cap;
     *workers_base = p;
     *ctl = s_ctl;
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
@@ -903,7 +921,7 @@ __device__ void grow_shared_init(GrowShared& g, unsigned char* smem, const Graph
     // list offsets in the staging area: counts fetched in parallel (s_loff doubles as scratch), then one thread runs
     // the greedy first-fit prefix over shared memory (a serial walk over global memory cost 20 us per image with 38
     // lists and 210 us with the 320 lists of the wholebody skeleton, measured round 2)
-    for (int li = threadIdx.x; li < 2 * C; li += blockDim.x) s_loff[li] = list_counts[li];
+    for (int li = threadIdx.x; li < 2 * C; li += blockDim.x) { const int n = list_counts[li]; s_loff[li] = n; s_lcnt[li] = n; }
     __syncthreads();
     if (threadIdx.x == 0) {
         int run = 0;
@@ -920,18 +938,25 @@ __device__ void grow_shared_init(GrowShared& g, unsigned char* smem, const Graph
         for (int li = warp_i; li < 2 * C; li += n_warps) {
             const int off = s_loff[li];
             if (off < 0) continue;
-            const int n = list_counts[li];
+            const int n = s_lcnt[li];
             const float* L = lists + ((size_t)li * 7) * d.hw;
             for (int i = lane_i; i < n; i += 32) {
                 s_cxy[off + i] = L[i];
                 s_cxy[list_cap + off + i] = L[d.hw + i];
                 s_cxy[2 * list_cap + off + i] = L[2 * (size_t)d.hw + i];
             }
+            if (off + n <= ext_cap) {
+                for (int i = lane_i; i < n; i += 32) {
+                    s_ext[off + i] = L[3 * (size_t)d.hw + i];
+                    s_ext[ext_cap + off + i] = L[4 * (size_t)d.hw + i];
+                    s_ext[2 * ext_cap + off + i] = L[6 * (size_t)d.hw + i];
+                }
+            }
         }
     }
     g.skeleton = s_skel; g.adj_start = s_adj_start; g.adj_edge = s_adj_edge; g.edge_lookup = s_lookup; g.pair_id = s_pair;
-    g.s_cxy = s_cxy; g.s_loff = s_loff; g.list_cap = list_cap;
-    g.lists = lists; g.list_counts = list_counts;
+    g.s_cxy = s_cxy; g.s_ext = s_ext; g.s_loff = s_loff; g.list_cap = list_cap; g.ext_cap = ext_cap;
+    g.lists = lists; g.list_counts = s_lcnt;
     g.K = K; g.C = C; g.F = d.F; g.hw = d.hw; g.gp = gp;
     __syncthreads();
 }
@@ -944,7 +969,7 @@ __device__ void grow_shared_init(GrowShared& g, unsigned char* smem, const Graph
 //   3. commits them in seed order: seed i is dropped iff a joint of an annotation committed earlier IN THIS ROUND
 //      covers it (the same box arithmetic as Occupancy::set/get), else it marks the map and is stored,
 // which yields exactly the annotations, in exactly the order, of the sequential loop.
-__global__ void __launch_bounds__(32 * GROW_MAX_WORKERS) k_grow(Dims d, Graph gr, GrowParams gp, int list_cap,
+__global__ void __launch_bounds__(32 * GROW_MAX_WORKERS) k_grow(Dims d, Graph gr, GrowParams gp, int list_cap, int ext_cap,
                                              const int* __restrict__ seed_f, const float4* __restrict__ seed_vxys,
                                              const int* __restrict__ n_seeds,
                                              const float* __restrict__ lists, const int* __restrict__ list_counts,
@@ -969,7 +994,7 @@ __global__ void __launch_bounds__(32 * GROW_MAX_WORKERS) k_grow(Dims d, Graph gr
     long long t_mark = clock64(), t_init = 0, t_sel = 0, t_grow = 0, t_commit = 0;
     int n_rounds = 0, n_picks = 0;
     auto lap = [&](long long& acc) { const long long now = clock64(); acc += now - t_mark; t_mark = now; };
-    grow_shared_init(g, smem, gr, d, list_cap, lists + ((size_t)b * d.C * 2 * 7) * d.hw,
+    grow_shared_init(g, smem, gr, d, list_cap, ext_cap, lists + ((size_t)b * d.C * 2 * 7) * d.hw,
                      list_counts + (size_t)b * d.C * 2, gp, &workers_base, &ctl);
     (void)ctl;
     Worker w;
@@ -1177,7 +1202,7 @@ __global__ void __launch_bounds__(32 * GROW_MAX_WORKERS) k_grow(Dims d, Graph gr
 
 // _force_complete + _flood_fill (src/cifcaf.cpp:233-236, 414-449); lists were refilled at force_complete_caf_th by
 // k_caf_scored.  Annotations are independent here: one warp each, W at a time.
-__global__ void __launch_bounds__(32 * GROW_MAX_WORKERS) k_force_complete(Dims d, Graph gr, GrowParams gp, int list_cap,
+__global__ void __launch_bounds__(32 * GROW_MAX_WORKERS) k_force_complete(Dims d, Graph gr, GrowParams gp, int list_cap, int ext_cap,
                                                        const float* __restrict__ lists,
                                                        const int* __restrict__ list_counts,
                                                        Joint* __restrict__ anns, const int* __restrict__ n_anns) {
@@ -1186,7 +1211,7 @@ __global__ void __launch_bounds__(32 * GROW_MAX_WORKERS) k_force_complete(Dims d
     const int W = blockDim.x >> 5;
     GrowShared g;
     unsigned char* workers_base; int* ctl;
-    grow_shared_init(g, smem, gr, d, list_cap, lists + ((size_t)b * d.C * 2 * 7) * d.hw,
+    grow_shared_init(g, smem, gr, d, list_cap, ext_cap, lists + ((size_t)b * d.C * 2 * 7) * d.hw,
                      list_counts + (size_t)b * d.C * 2, gp, &workers_base, &ctl);
     (void)ctl;
     Worker w;
@@ -1345,8 +1370,8 @@ __global__ void __launch_bounds__(NT) k_pack(Dims d, const float4* __restrict__ 
 
 __global__ void k_blend_single(const float* __restrict__ L, int n, double x, double y, double s,
                                double filter_sigmas, int only_max, double* __restrict__ out) {
-    const Joint j = warp_blend(L, n, n, L, L + n, L + 2 * (size_t)n, x, y, s, filter_sigmas, only_max != 0,
-                               threadIdx.x & 31);
+    const Joint j = warp_blend(L, L + n, L + 2 * (size_t)n, L + 3 * (size_t)n, L + 4 * (size_t)n, L + 6 * (size_t)n, n,
+                               x, y, s, filter_sigmas, only_max != 0, threadIdx.x & 31);
     if (threadIdx.x == 0) { out[0] = j.x; out[1] = j.y; out[2] = j.s; out[3] = j.v; }
 }
 
@@ -1675,7 +1700,7 @@ int pifpaf_decoder_decode_device(pifpaf_decoder_t* dec, const float* cif_dev, co
     }
     const size_t gs = dec->grow.smem;
     const int grow_threads = 32 * dec->grow.workers;
-    k_grow<<<d.B, grow_threads, gs, st>>>(d, gr, gp, dec->grow.list_cap, dec->d_seed_f, dec->d_seed_vxys, dec->d_n_seeds, dec->d_lists,
+    k_grow<<<d.B, grow_threads, gs, st>>>(d, gr, gp, dec->grow.list_cap, dec->grow.ext_cap, dec->d_seed_f, dec->d_seed_vxys, dec->d_n_seeds, dec->d_lists,
                                 dec->d_list_counts, dec->d_occ, tag_seed, init_ann_dev,
                                 reinterpret_cast<const long long*>(init_ids_dev), init_counts_dev, init_cap,
                                 dec->d_anns, dec->d_ann_ids, dec->d_n_anns, dec->d_flags, dec->d_grow_dbg);
@@ -1686,7 +1711,7 @@ int pifpaf_decoder_decode_device(pifpaf_decoder_t* dec, const float* cif_dev, co
         k_caf_scored<<<dim3(d.C, d.B), NT, 0, st>>>(caf_dev, d, dec->d_skeleton, dec->d_cifhr, dec->d_tile_epoch,
                                                     hr_epoch, p.cifhr_revision, th, 0.1, p.caf_ablation_no_rescore, dec->d_lists, dec->d_list_counts);
         PIFPAF_LAUNCH_CHECK();
-        k_force_complete<<<d.B, grow_threads, gs, st>>>(d, gr, gp, dec->grow.list_cap, dec->d_lists, dec->d_list_counts, dec->d_anns, dec->d_n_anns);
+        k_force_complete<<<d.B, grow_threads, gs, st>>>(d, gr, gp, dec->grow.list_cap, dec->grow.ext_cap, dec->d_lists, dec->d_list_counts, dec->d_anns, dec->d_n_anns);
         PIFPAF_LAUNCH_CHECK();
     }
     const size_t ns = (sizeof(double) + 2 * sizeof(int)) * (size_t)d.max_ann + 16;
