@@ -534,7 +534,13 @@ struct Joint { double v, x, y, s; };
 
 __device__ Joint warp_blend(const float* C0, const float* X1, const float* Y1,
                             const float* X2, const float* Y2, const float* S2, int n,
-                            double x, double y, double xy_scale, double filter_sigmas, bool only_max, int lane) {
+                            double x, double y, double xy_scale, double filter_sigmas, bool only_max, int lane,
+                            int* cand) {
+    // cand: 32 ints of per-warp scratch (shared memory).  Two phases per round: (A) the cheap box test over the list, the
+    // indices of the entries that pass compacted -- in index order -- into cand; (B) ONE pass of the expensive part
+    // (double division, exp) with lane k on the k-th candidate, then the in-order replay.  A list whose 32-entry chunks
+    // each hold a passing entry used to pay the double chain once per chunk (1-2 times per scan, two scans per
+    // evaluation); the per-entry arithmetic and the replay order are unchanged.
     Joint zero; zero.v = 0.0; zero.x = 0.0; zero.y = 0.0; zero.s = 0.0;
     xy_scale = fmax(xy_scale, 0.5);
     const float sigma_filter = (float)(filter_sigmas * xy_scale / 2.0);
@@ -543,27 +549,40 @@ __device__ Joint warp_blend(const float* C0, const float* X1, const float* Y1,
     const double ylo = y - (double)sigma_filter, yhi = y + (double)sigma_filter;
     float score_1 = 0.0f, score_2 = 0.0f;
     int i1 = 0, i2 = 0;
-    for (int base = 0; base < n; base += 32) {
-        const int i = base + lane;
-        bool pass = false;
-        float sc = 0.0f;
-        if (i < n) {
-            const float ex = X1[i], ey = Y1[i];
-            pass = !((double)ex < xlo) && !((double)ex > xhi) && !((double)ey < ylo) && !((double)ey > yhi);
-            if (pass) {
-                const double dx = (double)ex - x, dy = (double)ey - y;
-                const float d2 = (float)(dx * dx + dy * dy);
-                sc = (float)(exp(-0.5 * (double)d2 / (double)sigma2) * (double)C0[i]);
+    const unsigned lt = (1u << lane) - 1u;
+    int base = 0;
+    while (base < n) {
+        int cnt = 0, next = base;
+        for (; next < n; next += 32) {
+            const int i = next + lane;
+            bool pass = false;
+            if (i < n) {
+                const float ex = X1[i], ey = Y1[i];
+                pass = !((double)ex < xlo) && !((double)ex > xhi) && !((double)ey < ylo) && !((double)ey > yhi);
             }
+            const unsigned mask = __ballot_sync(0xffffffffu, pass);
+            const int pc = __popc(mask);
+            if (cnt + pc > 32) break;                 // does not fit any more: this chunk is scanned again next round
+            if (pass) cand[cnt + __popc(mask & lt)] = i;
+            cnt += pc;
         }
-        unsigned mask = __ballot_sync(0xffffffffu, pass);
-        while (mask) {
-            const int l = __ffs(mask) - 1;
-            mask &= mask - 1;
+        __syncwarp();
+        float sc = 0.0f;
+        int ci = 0;
+        if (lane < cnt) {
+            ci = cand[lane];
+            const double dx = (double)X1[ci] - x, dy = (double)Y1[ci] - y;
+            const float d2 = (float)(dx * dx + dy * dy);
+            sc = (float)(exp(-0.5 * (double)d2 / (double)sigma2) * (double)C0[ci]);
+        }
+        __syncwarp();
+        for (int l = 0; l < cnt; l++) {
             const float v = __shfl_sync(0xffffffffu, sc, l);
-            if (v >= score_1) { score_2 = score_1; i2 = i1; score_1 = v; i1 = base + l; }
-            else if (v > score_2) { score_2 = v; i2 = base + l; }
+            const int vi = __shfl_sync(0xffffffffu, ci, l);
+            if (v >= score_1) { score_2 = score_1; i2 = i1; score_1 = v; i1 = vi; }
+            else if (v > score_2) { score_2 = v; i2 = vi; }
         }
+        base = next;
     }
     if (score_1 == 0.0f) return zero;
     const float e1x = X2[i1], e1y = Y2[i1];
@@ -617,12 +636,13 @@ struct Worker {
     int* heap_item;         // [2C + 1]: edge | computed << 30
     int* new_edges;         // [2C]
     unsigned char* in_frontier;   // [2C] by pair id
+    int* cand;              // [32] scratch of warp_blend
     int heap_n, n_new;      // lane 0's registers
 };
 
 __host__ __device__ inline size_t worker_bytes(int K, int C) {
     size_t b = sizeof(WJoint) * (size_t)K + sizeof(WJoint) * 2 * (size_t)C + (sizeof(float) + 2 * sizeof(int)) * (2 * (size_t)C + 2)
-               + 2 * (size_t)C;
+               + ((2 * (size_t)C + 3) & ~(size_t)3) + 32 * sizeof(int);
     return (b + 15) & ~(size_t)15;
 }
 
@@ -633,7 +653,8 @@ __device__ inline void worker_init(Worker& w, unsigned char* base, int K, int C)
     w.heap_score = reinterpret_cast<float*>(base + off); off += sizeof(float) * (2 * C + 2);
     w.heap_item = reinterpret_cast<int*>(base + off); off += sizeof(int) * (2 * C + 2);
     w.new_edges = reinterpret_cast<int*>(base + off); off += sizeof(int) * (2 * C + 2);
-    w.in_frontier = base + off;
+    w.in_frontier = base + off; off += (2 * (size_t)C + 3) & ~(size_t)3;
+    w.cand = reinterpret_cast<int*>(base + off);
     w.heap_n = 0; w.n_new = 0;
 }
 
@@ -726,7 +747,8 @@ __device__ WJoint warp_connection_value(const GrowShared& g, const Worker& w, in
     const float* fY2 = fe ? g.s_ext + g.ext_cap + of : Lf + 4 * (size_t)g.hw;
     const float* fS2 = fe ? g.s_ext + 2 * g.ext_cap + of : Lf + 6 * (size_t)g.hw;
     WJoint out; out.v = 0.0; out.x = 0.f; out.y = 0.f; out.s = 0.f; out.pad = 0;
-    const Joint nj = warp_blend(fC, fX, fY, fX2, fY2, fS2, nf, (double)sj.x, (double)sj.y, (double)sj.s, filter_sigmas, false, lane);
+    const Joint nj = warp_blend(fC, fX, fY, fX2, fY2, fS2, nf, (double)sj.x, (double)sj.y, (double)sj.s, filter_sigmas, false, lane,
+                                w.cand);
     if (nj.v == 0.0) return out;
     double v = sqrt(nj.v * sj.v);
     if (v < g.gp.keypoint_threshold || v < sj.v * g.gp.keypoint_threshold_rel) return out;
@@ -738,7 +760,7 @@ __device__ WJoint warp_connection_value(const GrowShared& g, const Worker& w, in
         const float* bX2 = be ? g.s_ext + ob : Lb + 3 * (size_t)g.hw;
         const float* bY2 = be ? g.s_ext + g.ext_cap + ob : Lb + 4 * (size_t)g.hw;
         const float* bS2 = be ? g.s_ext + 2 * g.ext_cap + ob : Lb + 6 * (size_t)g.hw;
-        const Joint rev = warp_blend(bC, bX, bY, bX2, bY2, bS2, nb, nj.x, nj.y, nj.s, filter_sigmas, false, lane);
+        const Joint rev = warp_blend(bC, bX, bY, bX2, bY2, bS2, nb, nj.x, nj.y, nj.s, filter_sigmas, false, lane, w.cand);
         if (rev.v == 0.0) return out;
         if (fabs((double)sj.x - rev.x) + fabs((double)sj.y - rev.y) > (double)sj.s) return out;
     }
@@ -1370,8 +1392,9 @@ __global__ void __launch_bounds__(NT) k_pack(Dims d, const float4* __restrict__ 
 
 __global__ void k_blend_single(const float* __restrict__ L, int n, double x, double y, double s,
                                double filter_sigmas, int only_max, double* __restrict__ out) {
+    __shared__ int cand[32];
     const Joint j = warp_blend(L, L + n, L + 2 * (size_t)n, L + 3 * (size_t)n, L + 4 * (size_t)n, L + 6 * (size_t)n, n,
-                               x, y, s, filter_sigmas, only_max != 0, threadIdx.x & 31);
+                               x, y, s, filter_sigmas, only_max != 0, threadIdx.x & 31, cand);
     if (threadIdx.x == 0) { out[0] = j.x; out[1] = j.y; out[2] = j.s; out[3] = j.v; }
 }
 
