@@ -263,3 +263,20 @@ def test_resnet_lowering_reproduces_oracle_net(name, shape):
         assert float((g - wnt).abs().max()) < 1e-5 * max(1.0, float(wnt.abs().max()))
     n_conv = sum(o['kind'] == 'conv' for o in ops)
     assert n_conv == (20 if name == 'resnet18' else 53) - 1       # all convs but the stem
+
+
+def test_stride2_depthwise_inputs_have_128_byte_pixels():
+    """network._dw_in_pitch: the tensor in front of the stride-2 depthwise conv of a stage's first block is padded to a
+    multiple of 64 channels (DRAM serves the depthwise TMA reads in aligned 128-byte lines: 1.96x over-read with 352-byte
+    pixels, profiles/r2_history.md), every other branch-internal tensor keeps the 16-channel pitch, and the depthwise op
+    still covers the real channels only."""
+    plan = network.random_plan('shufflenetv2k16', seed=3)
+    tensors, ops, _ = network.build_ops(plan, 161, 161, layout='bins', fuse_dw=False)
+    s2 = [o for o in ops if o['kind'] == 'dwconv' and o['stride'] == 2]
+    s1 = [o for o in ops if o['kind'] == 'dwconv' and o['stride'] == 1]
+    assert len(s2) == 6 and len(s1) == 13
+    for o in s2:
+        c_phys = tensors[o['in']][2]
+        assert (c_phys * 2) % 128 == 0 or c_phys <= 32, (o['in'], c_phys)       # (the 24-channel stem output: 64-byte pixels)
+        assert o['channels'] <= c_phys and o['channels'] % 16 == 0
+    assert {tensors[o['in']][2] for o in s1} == {176, 352, 704}
