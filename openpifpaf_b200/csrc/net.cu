@@ -226,7 +226,8 @@ struct GemmArgs {
     int b_resident;              // all K blocks of this CTA's weight tile stay in shared memory (loaded once)
     int pair, pair_stages;       // k_gemm_tc2 (CTA pairs, cta_group::2): on / ring depth per CTA
     int debug;                   // timing experiments only (PIFPAF_GEMM_DEBUG; results are wrong): 1 = no epilogue stores,
-                                 // 2 = no MMAs issued, 4 = epilogue does not read TMEM, 8 = scatter pieces written as one row
+                                 // 2 = no MMAs issued, 4 = epilogue does not read TMEM, 8 = scatter pieces written as one row,
+                                 // 16 = every scatter piece written as its own [pixels][width] tensor
     int mc;                      // weights-resident, two n blocks: the two CTAs of an M tile form a cluster and share A --
                                  // each loads one half (64 rows) of every A stage and multicasts it to both (tmap_src = the
                                  // 64-row A map); a stage is free when BOTH have consumed it
@@ -357,6 +358,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& g, int m, int n0,
             // debug 8 (timing only, wrong results): every piece goes to the first destination tensor, as one contiguous row
             DestGroup d = dest[n0 >> 4];
             if (g.debug & 8) { d = dest[0]; d.base += n0; }
+            // debug 16 (timing only): every piece as its own [pixels][piece width] tensor (rows of one piece contiguous)
+            if (g.debug & 16) { const int pw = d.pad >> 16, ci = d.pad & 0xffff; d.base = d.base - ci + (size_t)0; d.ld = pw; d.base += ci; }
             st_global_256(d.base + (size_t)m * d.ld, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
         }
         return;
