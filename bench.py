@@ -400,7 +400,7 @@ def run_b200(args):
 
     out = None
     if rank == 0:
-        # ---- roofline of the dominant kernel (k_gemm_tc), measured live with CUDA events per launch
+        # ---- roofline of the dominant kernels (the tcgen05 GEMMs k_gemm_tc / k_gemm_tc2), measured live with CUDA events per launch
         prof_images = dev_images if not args.raw_input else torch.randn((B, 3, SIZE, SIZE), device=device)
         ms_op, kind, flops, nbytes, prof = forward_profile(net, prof_images, pk)
         sel = kind == 1

@@ -37,3 +37,19 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
 def test_reference_arm_is_silent_on_other_ranks():
     r = _run({'RANK': '1', 'WORLD_SIZE': '2'})
     assert r.returncode == 0 and r.stdout.strip() == ''
+
+
+def test_roofline_traffic_comes_from_the_committed_capture_of_both_gemm_kernels():
+    """bench.measured_traffic: DRAM bytes per GEMM launch = the committed ncu capture of one bench step, summed over the
+    one-CTA and the CTA-pair kernel; a capture whose launch count does not make whole steps is not quoted."""
+    sys.path.insert(0, ROOT)
+    import bench
+    per_launch, src = bench.measured_traffic(('k_gemm_tc', 'k_gemm_tc2'), 37)
+    table = json.load(open(os.path.join(ROOT, 'profiles', 'r2_dram_traffic_bench_step.json')))['kernels']
+    total = sum(table[k]['dram_read_bytes'] + table[k]['dram_write_bytes'] for k in ('k_gemm_tc', 'k_gemm_tc2'))
+    assert table['k_gemm_tc']['launches'] + table['k_gemm_tc2']['launches'] == 37
+    assert per_launch == round(total / 37) and 'r2_dram_traffic_bench_step.json' in src
+    # within 5 % of the algorithmic bytes per launch of the committed bench line: no wasted traffic in the GEMMs
+    line = json.loads(open(os.path.join(ROOT, 'profiles', 'r2_final_bench_n1_full.json')).read().strip().splitlines()[-1])
+    assert abs(per_launch / line['roofline']['algorithmic_bytes_per_launch'] - 1.0) < 0.05
+    assert bench.measured_traffic(('k_gemm_tc', 'k_gemm_tc2'), 36)[0] is None
